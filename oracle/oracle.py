@@ -1,0 +1,183 @@
+"""ctypes front-end of the CPU oracle (oracle/flutas_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under flutas_b200/ imports this module.
+
+Arrays are numpy float64, Fortran-ordered, shaped like the reference's Fortran arrays:
+p(0:n1+1,0:n2+1,0:n3+1), u/v/w(1-nh_u:n+nh_u)^3, dzci/dzfi(1-nh_d:n3+nh_d).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KINDS = dict(R2HC=0, HC2R=1, REDFT00=3, REDFT01=4, REDFT10=5, REDFT11=6,
+             RODFT00=7, RODFT01=8, RODFT10=9, RODFT11=10)   # src/fftw.f90:41-61
+
+_dp = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "flutas_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.oracle_r2r_create.restype = C.c_void_p
+        L.oracle_r2r_create.argtypes = [C.c_int, C.c_int]
+        L.oracle_r2r_destroy.argtypes = [C.c_void_p]
+        L.oracle_r2r_execute.argtypes = [C.c_void_p, _dp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_long]
+        L.oracle_normfft.restype = C.c_double
+        L.oracle_normfft.argtypes = [C.c_int, C.c_int, C.c_char_p]
+        L.oracle_find_fft.argtypes = [C.c_char, C.c_char, C.c_char, C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]
+        L.oracle_eigenvalues.argtypes = [C.c_int, C.c_char, C.c_char, _dp]
+        L.oracle_tridmatrix.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.oracle_initgrid.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp, _dp]
+        L.oracle_gaussel.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.oracle_gaussel_periodic.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.oracle_solver_cpu.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_double, _dp, _dp, _dp, _dp,
+                                        C.c_char_p, _dp, _dp]
+        L.oracle_fillps.argtypes = [C.c_int] * 5 + [C.c_double] * 3 + [_dp, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+        L.oracle_updt_rhs_b.argtypes = [C.c_int] * 3 + [_dp] * 4
+        L.oracle_correc.argtypes = [C.c_int] * 5 + [C.c_double] * 3 + [_dp, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+        L.oracle_chkdiv.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2 + [_dp] * 4 + [_dp, _dp]
+        L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    assert a.dtype == np.float64 and (a.flags.f_contiguous or a.ndim == 1), "need float64 Fortran-contiguous"
+    return a.ctypes.data_as(_dp)
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def find_fft(bc, c_or_f="c"):
+    kf, kb = C.c_int(), C.c_int()
+    norm = np.zeros(2)
+    rc = lib().oracle_find_fft(bc[0].encode(), bc[1].encode(), c_or_f.encode(), C.byref(kf), C.byref(kb), _p(norm))
+    if rc:
+        raise ValueError("unsupported BC pair %r / %r" % (bc, c_or_f))
+    return kf.value, kb.value, norm
+
+
+def normfft(ng1, ng2, bcx, bcy):
+    return lib().oracle_normfft(ng1, ng2, (bcx + bcy).encode())
+
+
+def eigenvalues(n, bc):
+    lam = np.zeros(n)
+    lib().oracle_eigenvalues(n, bc[0].encode(), bc[1].encode(), _p(lam))
+    return lam
+
+
+def tridmatrix(bcz, n, nh_d, dzci, dzfi):
+    a, b, c = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().oracle_tridmatrix(bcz[0].encode(), bcz[1].encode(), n, nh_d, _p(dzci), _p(dzfi), _p(a), _p(b), _p(c))
+    return a, b, c
+
+
+def initgrid(n, gr, lz, nh_d):
+    dzc, dzf = np.zeros(n + 2 * nh_d), np.zeros(n + 2 * nh_d)
+    lib().oracle_initgrid(n, gr, lz, nh_d, _p(dzc), _p(dzf))
+    return dzc, dzf
+
+
+def r2r(kind, arr, axis):
+    """In-place FFTW-r2r-equivalent transform of a Fortran-ordered 3-D array along axis 0 or 1."""
+    L = lib()
+    n1, n2, n3 = arr.shape
+    kind = KINDS[kind] if isinstance(kind, str) else kind
+    pl = L.oracle_r2r_create(arr.shape[axis], kind)
+    if not pl:
+        raise ValueError("unsupported kind")
+    try:
+        if axis == 0:
+            L.oracle_r2r_execute(pl, _p(arr), 1, n2, n1, n3, n1 * n2)
+        elif axis == 1:
+            L.oracle_r2r_execute(pl, _p(arr), n1, n1, 1, n3, n1 * n2)
+        else:
+            raise ValueError("axis")
+    finally:
+        L.oracle_r2r_destroy(pl)
+    return arr
+
+
+class Solver:
+    """fftini + solver_cpu on one rank (src/fft.f90:24-157, src/solver_cpu.f90:20-115)."""
+
+    def __init__(self, n, bcx, bcy):
+        L = lib()
+        self.n = tuple(int(x) for x in n)
+        kfx, kbx, _ = find_fft(bcx)
+        kfy, kby, _ = find_fft(bcy)
+        self.plans = (C.c_void_p * 4)(L.oracle_r2r_create(self.n[0], kfx), L.oracle_r2r_create(self.n[0], kbx),
+                                      L.oracle_r2r_create(self.n[1], kfy), L.oracle_r2r_create(self.n[1], kby))
+        self.normfft = normfft(self.n[0], self.n[1], bcx, bcy)
+        self.work = np.zeros(self.n[0] * self.n[1] * self.n[2])
+
+    def solve(self, lambdaxy, a, b, c, bcz, p):
+        n = (C.c_int * 3)(*self.n)
+        lib().oracle_solver_cpu(n, self.plans, self.normfft, _p(np.asfortranarray(lambdaxy)), _p(a), _p(b), _p(c),
+                                bcz.encode(), _p(p), _p(self.work))
+        return p
+
+    def close(self):
+        for h in self.plans:
+            lib().oracle_r2r_destroy(h)
+        self.plans = None
+
+    def __del__(self):
+        if getattr(self, "plans", None) is not None:
+            try:
+                self.close()
+            except Exception:
+                pass
+
+
+def fillps(n, nh_d, nh_u, dli, dzfi, dti, rho0, u, v, w, p):
+    lib().oracle_fillps(n[0], n[1], n[2], nh_d, nh_u, dli[0], dli[1], dli[2], _p(dzfi), dti, rho0,
+                        _p(u), _p(v), _p(w), _p(p))
+    return p
+
+
+def updt_rhs_b(n, rhsbx, rhsby, rhsbz, p):
+    lib().oracle_updt_rhs_b(n[0], n[1], n[2], _p(rhsbx), _p(rhsby), _p(rhsbz), _p(p))
+    return p
+
+
+def correc(n, nh_d, nh_u, dli, dzci, dt, rho0, p, u, v, w):
+    lib().oracle_correc(n[0], n[1], n[2], nh_d, nh_u, dli[0], dli[1], dli[2], _p(dzci), dt, rho0,
+                        _p(p), _p(u), _p(v), _p(w))
+
+
+def chkdiv(n, dli, nh_d, nh_u, dzfi, u, v, w):
+    tot, mx = C.c_double(), C.c_double()
+    lib().oracle_chkdiv(n[0], n[1], n[2], dli[0], dli[1], dli[2], nh_d, nh_u, _p(dzfi), _p(u), _p(v), _p(w),
+                        C.byref(tot), C.byref(mx))
+    return tot.value, mx.value
+
+
+def gaussel(a, b, c, lambdaxy, pz, periodic):
+    nx, ny, n = pz.shape
+    f = lib().oracle_gaussel_periodic if periodic else lib().oracle_gaussel
+    f(nx, ny, n, _p(a), _p(b), _p(c), _p(np.asfortranarray(lambdaxy)), _p(pz))
+    return pz
