@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference's operator interface for the pressure path, on top of the C ABI.
+
+Same names, argument order and meaning as the Fortran module procedures:
+    fftini   src/fft.f90:24        fftend  src/fft.f90:159       solver  src/solver_cpu.f90:20
+    fillps   src/fillps.f90:16     correc  src/correc.f90:16     chkdiv  src/chkdiv.f90:18
+    updt_rhs_b  src/bound.f90:829
+Fields may be numpy arrays (host memory, Fortran order; staged through the device inside the call) or
+torch CUDA tensors holding the same Fortran-ordered storage (used in place, asynchronously on torch's
+current stream).  torch is only used for device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+_dp = C.POINTER(C.c_double)
+
+
+def _ptr(x):
+    """address of the first element of a numpy array or torch tensor"""
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float64:
+            raise TypeError("float64 required")
+        if not (x.flags.f_contiguous or x.ndim <= 1):
+            raise ValueError("Fortran-contiguous array required")
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        import torch
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            raise TypeError("contiguous float64 tensor required")
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("unsupported array type %r" % type(x))
+
+
+def _use_torch_stream():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            _lib.load().flutas_b200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    except ImportError:
+        pass
+
+
+def init(device=0, rank=0, nranks=1):
+    _lib.check(_lib.load().flutas_b200_init(device, rank, nranks))
+
+
+def device_field(arr):
+    """Copy a Fortran-ordered numpy array into a torch CUDA tensor with identical storage order."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr.T)).cuda()      # C-order of the transpose == F-order storage
+    return t
+
+
+def host_field(t, shape):
+    a = np.asfortranarray(t.cpu().numpy().T)
+    assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+class Plans:
+    """arrplan(2,2): four opaque handles, Fortran order fwd-x, bwd-x, fwd-y, bwd-y."""
+
+    def __init__(self):
+        self.h = (C.c_void_p * 4)()
+        self.normfft = None
+
+    def __del__(self):
+        try:
+            if self.h[0]:
+                fftend(self)
+        except Exception:
+            pass
+
+
+def fftini(n_x, n_y, bcxy, c_or_f=("c", "c")):
+    """bcxy = ("PP","NN") style pair of BC strings for x and y. Returns (arrplan, normfft)."""
+    L = _lib.load()
+    pl = Plans()
+    nf = C.c_double()
+    nx = (C.c_int * 3)(*n_x)
+    ny = (C.c_int * 3)(*n_y)
+    _lib.check(L.flutas_b200_fftini(nx, ny, (bcxy[0] + bcxy[1]).encode(), "".join(c_or_f).encode(), pl.h, C.byref(nf)))
+    pl.normfft = nf.value
+    return pl, nf.value
+
+
+def fftend(arrplan):
+    _lib.check(_lib.load().flutas_b200_fftend(arrplan.h))
+
+
+def solver(n, arrplan, normfft, lambdaxy, a, b, c, bcz, c_or_f, p):
+    _use_torch_stream()
+    nn = (C.c_int * 3)(*n)
+    _lib.check(_lib.load().flutas_b200_solver(nn, arrplan.h, normfft, _ptr(lambdaxy), _ptr(a), _ptr(b), _ptr(c),
+                                              bcz.encode(), "".join(c_or_f).encode(), _ptr(p)))
+    return p
+
+
+def fillps(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, dzfi, dti, rho0, u, v, w, p):
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_fillps(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, _ptr(dzfi), dti, rho0,
+                                              _ptr(u), _ptr(v), _ptr(w), _ptr(p)))
+    return p
+
+
+def updt_rhs_b(nx, ny, nz, cbc, rhsbx, rhsby, rhsbz, p):
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_updt_rhs_b(nx, ny, nz, "".join(cbc).encode(), _ptr(rhsbx), _ptr(rhsby),
+                                                  _ptr(rhsbz), _ptr(p)))
+    return p
+
+
+def correc(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, dzci, dt, rho0, p, u, v, w, rho=None):
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_correc(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, _ptr(dzci), dt, rho0,
+                                              _ptr(p), _ptr(u), _ptr(v), _ptr(w), None))
+
+
+def chkdiv(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzfi, u, v, w):
+    _use_torch_stream()
+    tot, mx = C.c_double(), C.c_double()
+    _lib.check(_lib.load().flutas_b200_chkdiv(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, _ptr(dzfi), _ptr(u), _ptr(v),
+                                              _ptr(w), C.byref(tot), C.byref(mx)))
+    return tot.value, mx.value
+
+
+def launch_count():
+    return _lib.load().flutas_b200_launch_count()

@@ -1,0 +1,356 @@
+// kernels.cuh -- sm_100a kernels of the pressure-Poisson path.
+//
+//   xfft_kernel   x-line transforms (lines contiguous; p with halo <-> dense work array)   fft.f90:75-86 / solver_cpu.f90:59,89,93
+//   yfft_kernel   y-line transforms (stride n1; staged as (TB x N2) smem tiles, in place)  fft.f90:113-124 / solver_cpu.f90:65,86
+//   thomas_*      z tridiagonal solves, one thread per (i,j) column                        solver_cpu.f90:117-223
+//   fillps/correc/chkdiv stencils                                                          fillps.f90:42-61, correc.f90:49-73, chkdiv.f90:46-58
+//
+// All FP64, all bandwidth-bound; no tensor cores by design (BASELINE.json north_star).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tile_fft.cuh"
+
+namespace fb {
+
+// Where a set of x-lines lives: line l = j + n2*k  ->  base[off0 + j*sj + k*sk + i]
+struct LineGeom {
+  long off0, sj, sk;
+  int n2;
+  long nlines;
+};
+
+__device__ __forceinline__ long line_offset(const LineGeom& g, long line) {
+  const long k = line / g.n2, j = line - k * g.n2;
+  return g.off0 + j * g.sj + k * g.sk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x direction.  One block = TB consecutive lines.  FWD: physical -> spectral rows, BWD: the reverse
+// (times `scale`, = normfft on the last stage, solver_cpu.f90:93).
+template <int TB, bool FWD>
+__global__ void __launch_bounds__(256) xfft_kernel(LinePlan P, const double* __restrict__ src, LineGeom gs,
+                                                   double* __restrict__ dst, LineGeom gd, double scale) {
+  extern __shared__ double tile[];
+  const int N = P.N, M = P.M, kind = P.kind;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long line0 = (long)blockIdx.x * TB;
+
+  for (int L = 0; L < TB; ++L) {
+    const long line = line0 + L;
+    const bool live = line < gs.nlines;
+    const double* s = src + (live ? line_offset(gs, line) : 0);
+    for (int e = tid; e < N; e += nthr) {
+      int m, part;
+      double sgn = 1.0;
+      if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
+      else { part = (e >= M); m = e - part * M; }
+      const double v = live ? __ldg(s + e) : 0.0;
+      tile[taddr<TB, true>(m, part, M, L)] = sgn * v;
+    }
+  }
+  __syncthreads();
+
+  const int lane = tid & (TB - 1), worker = tid / TB, nworkers = nthr / TB;
+  if (FWD) {
+    for (int q = 0; q < P.npass; ++q) {
+      fft_pass<TB, true, true>(tile, P, q, lane, worker, nworkers);
+      __syncthreads();
+    }
+    split_fwd<TB, true>(tile, P, lane, worker, nworkers);
+  } else {
+    merge_bwd<TB, true>(tile, P, lane, worker, nworkers);
+    for (int q = P.npass - 1; q >= 0; --q) {
+      __syncthreads();
+      fft_pass<TB, true, false>(tile, P, q, lane, worker, nworkers);
+    }
+  }
+  __syncthreads();
+
+  for (int L = 0; L < TB; ++L) {
+    const long line = line0 + L;
+    if (line >= gd.nlines) break;
+    double* d = dst + line_offset(gd, line);
+    for (int e = tid; e < N; e += nthr) {
+      int m, part;
+      double sgn = 1.0;
+      if (!FWD) elem_to_slot(kind, N, e, m, part, sgn);
+      else { part = (e >= M); m = e - part * M; }
+      d[e] = sgn * scale * tile[taddr<TB, true>(m, part, M, L)];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y direction, in place on the dense work array W(n1, N, n3).  One block = lanes i0..i0+TB-1 of one
+// k plane, all N rows.  Global accesses are TB*8 contiguous bytes per row.
+template <int TB, bool FWD>
+__global__ void __launch_bounds__(256) yfft_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
+  extern __shared__ double tile[];
+  const int N = P.N, M = P.M, kind = P.kind;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ti = blockIdx.x % ntile_i;
+  const long k = blockIdx.x / ntile_i;
+  const int i0 = ti * TB;
+  const int lane = tid & (TB - 1), worker = tid / TB, nworkers = nthr / TB;
+  const bool live = (i0 + lane) < n1;
+  double* base = W + (long)n1 * N * k + i0 + lane;
+
+  for (int e = worker; e < N; e += nworkers) {
+    int m, part;
+    double sgn = 1.0;
+    if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
+    else { part = (e >= M); m = e - part * M; }
+    const double v = live ? base[(long)e * n1] : 0.0;
+    tile[taddr<TB, false>(m, part, M, lane)] = sgn * v;
+  }
+  __syncthreads();
+
+  if (FWD) {
+    for (int q = 0; q < P.npass; ++q) {
+      fft_pass<TB, false, true>(tile, P, q, lane, worker, nworkers);
+      __syncthreads();
+    }
+    split_fwd<TB, false>(tile, P, lane, worker, nworkers);
+  } else {
+    merge_bwd<TB, false>(tile, P, lane, worker, nworkers);
+    for (int q = P.npass - 1; q >= 0; --q) {
+      __syncthreads();
+      fft_pass<TB, false, false>(tile, P, q, lane, worker, nworkers);
+    }
+  }
+  __syncthreads();
+
+  if (!live) return;
+  for (int e = worker; e < N; e += nworkers) {
+    int m, part;
+    double sgn = 1.0;
+    if (!FWD) elem_to_slot(kind, N, e, m, part, sgn);
+    else { part = (e >= M); m = e - part * M; }
+    base[(long)e * n1] = sgn * tile[taddr<TB, false>(m, part, M, lane)];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z direction, generic version: one thread per (i,j) column of W(ncol, nz), coalesced over columns.
+// Follows dgtsv_homebrewed / gaussel_periodic (solver_cpu.f90:147-223) with the forward-sweep
+// intermediates spilled to scratch fields D (and P2 for periodic z).
+// `pin`: the (kx,ky)=(0,0) column of an all-Neumann/periodic problem is singular; the reference
+// leaves its additive constant to round-off (z ~ 1e-16 pivot, :209-214 and :175-176).  We define the
+// gauge instead: p(nz) = 0 for that column (the reference's own `z == 0` branch).
+__global__ void thomas_generic_kernel(long ncol, int nz, const double* __restrict__ a, const double* __restrict__ b,
+                                      const double* __restrict__ c, const double* __restrict__ lam,
+                                      double* __restrict__ W, double* __restrict__ D, int singular) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const double l = lam[col];
+  const bool pin = singular && (l == 0.0);
+  const int n = nz;
+  double z = 1.0 / (b[0] + l);
+  double d = c[0] * z;
+  double p = W[col] * z;
+  D[col] = d;
+  W[col] = p;
+  for (int k = 1; k < n - 1; ++k) {
+    const double ak = a[k];
+    z = 1.0 / ((b[k] + l) - ak * d);
+    d = c[k] * z;
+    p = (W[col + k * ncol] - ak * p) * z;
+    D[col + k * ncol] = d;
+    W[col + k * ncol] = p;
+  }
+  z = (b[n - 1] + l) - a[n - 1] * d;
+  {
+    const double num = W[col + (long)(n - 1) * ncol] - a[n - 1] * p;
+    p = (pin || z == 0.0) ? 0.0 : num / z;
+    W[col + (long)(n - 1) * ncol] = p;
+  }
+  for (int k = n - 2; k >= 0; --k) {
+    p = W[col + k * ncol] - D[col + k * ncol] * p;
+    W[col + k * ncol] = p;
+  }
+}
+
+__global__ void thomas_periodic_generic_kernel(long ncol, int nz, const double* __restrict__ a,
+                                               const double* __restrict__ b, const double* __restrict__ c,
+                                               const double* __restrict__ lam, double* __restrict__ W,
+                                               double* __restrict__ D, double* __restrict__ P2, int singular) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncol) return;
+  const double l = lam[col];
+  const bool pin = singular && (l == 0.0);
+  const int n = nz, m = nz - 1;                 // reduced system size (solver_cpu.f90:168-174)
+  double z = 1.0 / (b[0] + l);
+  double d = c[0] * z;
+  double p1 = W[col] * z;
+  double p2 = -a[0] * z;
+  D[col] = d; W[col] = p1; P2[col] = p2;
+  for (int k = 1; k < m - 1; ++k) {
+    const double ak = a[k];
+    z = 1.0 / ((b[k] + l) - ak * d);
+    d = c[k] * z;
+    p1 = (W[col + k * ncol] - ak * p1) * z;
+    p2 = (0.0 - ak * p2) * z;
+    D[col + k * ncol] = d; W[col + k * ncol] = p1; P2[col + k * ncol] = p2;
+  }
+  {
+    const int k = m - 1;
+    z = (b[k] + l) - a[k] * d;
+    const double n1 = W[col + (long)k * ncol] - a[k] * p1, n2 = -c[k] - a[k] * p2;
+    p1 = (z != 0.0) ? n1 / z : 0.0;
+    p2 = (z != 0.0) ? n2 / z : 0.0;
+    W[col + (long)k * ncol] = p1; P2[col + (long)k * ncol] = p2;
+  }
+  const double p1m = p1, p2m = p2;
+  for (int k = m - 2; k >= 0; --k) {
+    const double dk = D[col + k * ncol];
+    p1 = W[col + k * ncol] - dk * p1;
+    p2 = P2[col + k * ncol] - dk * p2;
+    W[col + k * ncol] = p1; P2[col + k * ncol] = p2;
+  }
+  const double num = W[col + (long)m * ncol] - c[m] * p1 - a[m] * p1m;
+  const double den = (b[m] + l) + c[m] * p2 + a[m] * p2m;
+  const double pn = pin ? 0.0 : num / den;
+  W[col + (long)m * ncol] = pn;
+  for (int k = 0; k < m; ++k) W[col + k * ncol] = W[col + k * ncol] + P2[col + k * ncol] * pn;
+  (void)n;
+}
+
+// lambda in the internal spectral layout: lam_int(rx, ry) = lambdaxy(mode_x[rx], mode_y[ry])
+__global__ void permute_lambda_kernel(int n1, int n2, const double* __restrict__ lam, const int* __restrict__ mx,
+                                      const int* __restrict__ my, double* __restrict__ out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)n1 * n2) return;
+  const int ry = (int)(idx / n1), rx = (int)(idx - (long)ry * n1);
+  out[idx] = lam[mx[rx] + (long)n1 * my[ry]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// stencils.  u,v,w have halo nh_u (lower bound 1-nh_u), p has halo 1 (lower bound 0).
+struct StencilGeom {
+  int nx, ny, nz, nh_u;
+  long su1, su2, sp1, sp2;   // leading dimensions: u(su1, su2, *), p(sp1, sp2, *)
+};
+__device__ __forceinline__ long uidx(const StencilGeom& g, int i, int j, int k) {
+  return (long)(i + g.nh_u - 1) + g.su1 * ((long)(j + g.nh_u - 1) + g.su2 * (long)(k + g.nh_u - 1));
+}
+__device__ __forceinline__ long pidx(const StencilGeom& g, int i, int j, int k) {
+  return (long)i + g.sp1 * ((long)j + g.sp2 * (long)k);
+}
+
+// fillps.f90:50-57 (+ updt_rhs_b, bound.f90:858-942, folded in when rhsb* are given)
+__global__ void __launch_bounds__(256) fillps_kernel(StencilGeom g, double dtidxi, double dtidyi, double dti,
+                                                     const double* __restrict__ dzfi, double rho0,
+                                                     const double* __restrict__ u, const double* __restrict__ v,
+                                                     const double* __restrict__ w, double* __restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k);
+  const double uc = u[c], vc = v[c], wc = w[c];
+  // evaluation order exactly as written in fillps.f90:50-57, no FMA contraction (bit-exact with the oracle)
+  const double tz = __dmul_rn(__dmul_rn(__dsub_rn(wc, w[c - g.su1 * g.su2]), dti), dzfi[k]);
+  const double ty = __dmul_rn(__dsub_rn(vc, v[c - g.su1]), dtidyi);
+  const double tx = __dmul_rn(__dsub_rn(uc, u[c - 1]), dtidxi);
+  const double val = __dadd_rn(__dadd_rn(tz, ty), tx);
+  p[pidx(g, i, j, k)] = __dmul_rn(val, rho0);
+}
+
+// bound.f90:858-942 for one rank owning all six faces; which faces apply is encoded in rhsb pointers
+__global__ void updt_rhs_b_kernel(StencilGeom g, const double* __restrict__ rx, double* __restrict__ p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  // the three face families run as three launches in x, y, z order, like the reference's three loops
+  if (idx < (long)ny * nz) {
+    const int j = (int)(idx % ny) + 1, k = (int)(idx / ny) + 1;
+    p[pidx(g, 1, j, k)] += rx[idx];
+    p[pidx(g, nx, j, k)] += rx[idx + (long)ny * nz];
+  }
+}
+__global__ void updt_rhs_b_y_kernel(StencilGeom g, const double* __restrict__ ry, double* __restrict__ p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  if (idx < (long)nx * nz) {
+    const int i = (int)(idx % nx) + 1, k = (int)(idx / nx) + 1;
+    p[pidx(g, i, 1, k)] += ry[idx];
+    p[pidx(g, i, ny, k)] += ry[idx + (long)nx * nz];
+  }
+}
+__global__ void updt_rhs_b_z_kernel(StencilGeom g, const double* __restrict__ rz, double* __restrict__ p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  if (idx < (long)nx * ny) {
+    const int i = (int)(idx % nx) + 1, j = (int)(idx / nx) + 1;
+    p[pidx(g, i, j, 1)] += rz[idx];
+    p[pidx(g, i, j, nz)] += rz[idx + (long)nx * ny];
+  }
+}
+
+// correc.f90:57-60 (constant-coefficient branch; rho is never touched)
+__global__ void __launch_bounds__(256) correc_kernel(StencilGeom g, double factori, double factorj, double dt,
+                                                     const double* __restrict__ dzci, double rho0i,
+                                                     const double* __restrict__ p, double* __restrict__ u,
+                                                     double* __restrict__ v, double* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k), q = pidx(g, i, j, k);
+  const double pc = p[q];
+  // correc.f90:57-60, evaluated left to right without FMA contraction
+  u[c] = __dsub_rn(u[c], __dmul_rn(__dmul_rn(factori, __dsub_rn(p[q + 1], pc)), rho0i));
+  v[c] = __dsub_rn(v[c], __dmul_rn(__dmul_rn(factorj, __dsub_rn(p[q + g.sp1], pc)), rho0i));
+  w[c] = __dsub_rn(w[c], __dmul_rn(__dmul_rn(__dmul_rn(dt, dzci[k]), __dsub_rn(p[q + g.sp1 * g.sp2], pc)), rho0i));
+}
+
+// chkdiv.f90:46-58: per-block partial (sum, max|div|), finished by chkdiv_final_kernel (deterministic)
+__global__ void __launch_bounds__(256) chkdiv_kernel(StencilGeom g, double dxi, double dyi,
+                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
+                                                     const double* __restrict__ v, const double* __restrict__ w,
+                                                     double* __restrict__ part_sum, double* __restrict__ part_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  double div = 0.0;
+  if (i <= g.nx && j <= g.ny) {
+    const long c = uidx(g, i, j, k);
+    div = __dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(w[c], w[c - g.su1 * g.su2]), dzfi[k]),
+                              __dmul_rn(__dsub_rn(v[c], v[c - g.su1]), dyi)),
+                    __dmul_rn(__dsub_rn(u[c], u[c - 1]), dxi));
+  }
+  double s = div, m = fabs(div);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  }
+  __shared__ double ss[8], sm[8];
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  if ((t & 31) == 0) { ss[t >> 5] = s; sm[t >> 5] = m; }
+  __syncthreads();
+  if (t == 0) {
+    const int nw = (blockDim.x * blockDim.y + 31) / 32;
+    for (int q = 1; q < nw; ++q) { s += ss[q]; m = fmax(m, sm[q]); }
+    const long bid = blockIdx.x + (long)gridDim.x * (blockIdx.y + (long)gridDim.y * blockIdx.z);
+    part_sum[bid] = s; part_max[bid] = m;
+  }
+}
+
+__global__ void chkdiv_final_kernel(long nparts, const double* __restrict__ part_sum,
+                                    const double* __restrict__ part_max, double* __restrict__ out) {
+  __shared__ double ss[256], sm[256];
+  double s = 0.0, m = 0.0;
+  for (long q = threadIdx.x; q < nparts; q += blockDim.x) { s += part_sum[q]; m = fmax(m, part_max[q]); }
+  ss[threadIdx.x] = s; sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = ss[0]; out[1] = sm[0]; }
+}
+
+}  // namespace fb

@@ -1,0 +1,78 @@
+// line_plan.h -- host-side construction of a LinePlan: radix schedule, twiddle tables, digit-reversal
+// table and the row -> FFTW-mode map used to permute lambdaxy at plan time.
+// Plain C++ (no CUDA) so tests/emulate can build it with g++.
+//
+// Reference counterparts: plan creation in fftini (src/fft.f90:64-157) and the BC -> transform table
+// of find_fft (src/fft.f90:233-291); the eigenvalue ordering that has to match the spectral layout is
+// built in eigenvalues() (src/initsolver.f90:122-186).
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "tile_fft.cuh"
+
+namespace fb {
+
+struct HostLinePlan {
+  int N = 0, M = 0, kind = 0;
+  std::vector<int> radix, sub;
+  std::vector<cpx> wM, wN, wQ;
+  std::vector<int> pos;        // pos[k]  : row of complex mode k
+  std::vector<int> mode;       // mode[r] : index into the reference's lambda array for tile row r (0-based)
+  bool ok = false;
+};
+
+inline cpx unit_root(long double num, long double den) {   // exp(-i pi num/den)
+  const long double PI_L = 3.14159265358979323846264338327950288L;
+  const long double ang = -PI_L * num / den;
+  cpx r; r.x = (double)cosl(ang); r.y = (double)sinl(ang);
+  return r;
+}
+
+// BC pair -> kind; returns -1 if the transform is not available on this path
+inline int kind_from_bc(char b0, char b1) {
+  if (b0 == 'P' && b1 == 'P') return KIND_PP;
+  if (b0 == 'N' && b1 == 'N') return KIND_NN;
+  if (b0 == 'D' && b1 == 'D') return KIND_DD;
+  return -1;
+}
+
+inline HostLinePlan make_line_plan(int N, int kind) {
+  HostLinePlan hp;
+  hp.N = N; hp.M = N / 2; hp.kind = kind;
+  if (N < 2 || (N & 1)) return hp;                        // FluTAS requires even ng (sanity.f90:155)
+  int rem = hp.M;
+  while (rem % 8 == 0) { hp.radix.push_back(8); rem /= 8; }
+  while (rem % 4 == 0) { hp.radix.push_back(4); rem /= 4; }
+  while (rem % 2 == 0) { hp.radix.push_back(2); rem /= 2; }
+  while (rem % 3 == 0) { hp.radix.push_back(3); rem /= 3; }
+  while (rem % 5 == 0) { hp.radix.push_back(5); rem /= 5; }
+  if (rem != 1 || (int)hp.radix.size() > FB_MAX_PASS) return hp;   // other prime factors: unsupported
+  const int M = hp.M;
+  int prod = 1;
+  for (int r : hp.radix) { prod *= r; hp.sub.push_back(M / prod); }
+  hp.wM.resize(M > 0 ? M : 1);
+  for (int k = 0; k < M; ++k) hp.wM[k] = unit_root(2.0L * k, (long double)M);
+  hp.wN.resize(M / 2 + 1);
+  for (int k = 0; k <= M / 2; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
+  hp.wQ.resize(M + 1);
+  for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  hp.pos.resize(M);
+  for (int k = 0; k < M; ++k) {                           // k = t0 + r0 (t1 + r1 (t2 + ...)) -> sum t_q sub_q
+    int kk = k, p = 0;
+    for (size_t q = 0; q < hp.radix.size(); ++q) { p += (kk % hp.radix[q]) * hp.sub[q]; kk /= hp.radix[q]; }
+    hp.pos[k] = p;
+  }
+  hp.mode.resize(N);
+  for (int k = 0; k < M; ++k) {
+    const int r = hp.pos[k];
+    int q0 = k, q1 = (k == 0) ? M : N - k;                // part 0 / part 1 content (see split_fwd)
+    if (kind == KIND_DD) { q0 = N - 1 - q0; q1 = N - 1 - q1; }
+    hp.mode[r] = q0;
+    hp.mode[M + r] = q1;
+  }
+  hp.ok = true;
+  return hp;
+}
+
+}  // namespace fb

@@ -1,0 +1,312 @@
+// tile_fft.cuh -- batched 1-D real transforms on a shared-memory tile, written once for x and y lines.
+//
+// Replaces, for the pressure solver only, what the reference gets from FFTW r2r plans
+// (src/fft.f90:75-86,113-124 -> dfftw_execute_r2r, :181-193) and, on its GPU path, from cuFFT D2Z/Z2D
+// plus the separate Makhoul pre/post "signal processing" sweeps (src/fft.f90:294-887).
+//
+// A tile holds TB lines of N reals as [row][lane]: lane = line index (fastest), row = element.  Every
+// butterfly/post-processing access is "TB consecutive doubles of one row", so lanes never bank-conflict
+// and all lanes share one twiddle (broadcast).  A length-N real transform is one length-M=N/2 complex
+// FFT (split re/im planes: row m = Re z_m, row M+m = Im z_m) plus a fused split/Makhoul step:
+//
+//   forward : load (PP: v=e | NN: Makhoul even/odd permutation | DD: same + sign of odd e)
+//             -> in-place DIF passes (natural -> digit-reversed) -> split (+ e^{-i pi k/2N} twiddle)
+//   backward: inverse twiddle/split -> in-place DIT passes (digit-reversed -> natural) -> un-permute store
+//
+// The spectral layout is whatever the forward leaves in the tile (digit-reversed, re/im planes); it
+// is never reordered: `mode_index()` in plan.h tells the host which FFTW mode sits in which row so
+// that lambdaxy is permuted once at plan time ("physical order free").
+//
+// The same code compiles for the host (tests/emulate) so index logic is testable without a GPU.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
+
+namespace fb {
+
+struct cpx { double x, y; };
+
+enum LineKind { KIND_PP = 0, KIND_NN = 1, KIND_DD = 2 };
+enum { FB_MAX_PASS = 12 };
+
+// Device-visible description of one transform length/kind (tables live in global memory).
+struct LinePlan {
+  int N;                    // real length (even)
+  int M;                    // complex length N/2
+  int kind;                 // LineKind
+  int npass;
+  int radix[FB_MAX_PASS];   // DIF pass q uses radix[q]
+  int sub[FB_MAX_PASS];     // butterfly stride of pass q: M / (radix[0]*...*radix[q])
+  const cpx* wM;            // [M]      exp(-2 pi i k / M)
+  const cpx* wN;            // [M/2+1]  exp(-2 pi i k / N)
+  const cpx* wQ;            // [M+1]    exp(-i pi k / (2N))      (NN/DD only)
+  const int* pos;           // [M]      row of complex mode k after the forward passes
+};
+
+// ---------------------------------------------------------------------------------------------
+// tile addressing.  ROT=false: column == lane (y lines, loaded lane-contiguous from global).
+// ROT=true : column rotated by a row-dependent amount so that the transposing x-line load/store
+// (a warp writes 32 consecutive elements of ONE line, i.e. 32 different rows) is conflict-free.
+template <int TB>
+struct TileShape {
+  static constexpr int SH = (TB >= 16) ? 0 : (TB == 8) ? 1 : (TB == 4) ? 2 : 3;   // log2(16/TB)
+};
+
+template <int TB, bool ROT>
+FB_HD int taddr(int m, int part, int M, int lane) {
+  const int row = m + part * M;
+  if (ROT) {
+    const int rot = ((m >> TileShape<TB>::SH) & (TB / 2 - 1)) | (part * (TB / 2));
+    return row * TB + ((lane + rot) & (TB - 1));
+  }
+  return row * TB + lane;
+}
+
+// element e of a physical line -> (row m, plane part, sign) of the packed complex sequence
+FB_HD void elem_to_slot(int kind, int N, int e, int& m, int& part, double& sgn) {
+  int v = e;
+  sgn = 1.0;
+  if (kind != KIND_PP) {                       // Makhoul: v(n)=x(2n), v(N-1-n)=x(2n+1)  (fft.f90:431-444)
+    v = (e & 1) ? (N - 1 - (e >> 1)) : (e >> 1);
+    if (kind == KIND_DD && (e & 1)) sgn = -1.0;   // DST-II/III via sign flip of odd inputs (fft.f90:417-428,859-875)
+  }
+  m = v >> 1;
+  part = v & 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix butterflies: y_t = sum_m u_m exp(SIGN * 2 pi i m t / R), in place on (re[], im[])
+template <int SIGN> FB_HD void bfly2(double* re, double* im) {
+  const double ar = re[0], ai = im[0];
+  re[0] = ar + re[1]; im[0] = ai + im[1];
+  re[1] = ar - re[1]; im[1] = ai - im[1];
+}
+
+template <int SIGN> FB_HD void bfly3(double* re, double* im) {
+  const double c = -0.5, s = SIGN * 0.86602540378443864676;   // exp(SIGN 2 pi i/3) = c + i s
+  const double sr = re[1] + re[2], si = im[1] + im[2];
+  const double dr = re[1] - re[2], di = im[1] - im[2];
+  const double tr = re[0] + c * sr, ti = im[0] + c * si;
+  re[0] += sr; im[0] += si;
+  re[1] = tr - s * di; im[1] = ti + s * dr;
+  re[2] = tr + s * di; im[2] = ti - s * dr;
+}
+
+template <int SIGN> FB_HD void bfly4(double* re, double* im) {
+  const double s02r = re[0] + re[2], s02i = im[0] + im[2], d02r = re[0] - re[2], d02i = im[0] - im[2];
+  const double s13r = re[1] + re[3], s13i = im[1] + im[3], d13r = re[1] - re[3], d13i = im[1] - im[3];
+  // (SIGN i) * d13
+  const double jr = -SIGN * d13i, ji = SIGN * d13r;
+  re[0] = s02r + s13r; im[0] = s02i + s13i;
+  re[1] = d02r + jr;   im[1] = d02i + ji;
+  re[2] = s02r - s13r; im[2] = s02i - s13i;
+  re[3] = d02r - jr;   im[3] = d02i - ji;
+}
+
+template <int SIGN> FB_HD void bfly5(double* re, double* im) {
+  const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+  const double s1 = SIGN * 0.95105651629515357212, s2 = SIGN * 0.58778525229247312917;
+  const double a1r = re[1] + re[4], a1i = im[1] + im[4], b1r = re[1] - re[4], b1i = im[1] - im[4];
+  const double a2r = re[2] + re[3], a2i = im[2] + im[3], b2r = re[2] - re[3], b2i = im[2] - im[3];
+  const double x0r = re[0], x0i = im[0];
+  const double p1r = x0r + c1 * a1r + c2 * a2r, p1i = x0i + c1 * a1i + c2 * a2i;
+  const double p2r = x0r + c2 * a1r + c1 * a2r, p2i = x0i + c2 * a1i + c1 * a2i;
+  const double q1r = s1 * b1r + s2 * b2r, q1i = s1 * b1i + s2 * b2i;   // multiplied by i below
+  const double q2r = s2 * b1r - s1 * b2r, q2i = s2 * b1i - s1 * b2i;
+  re[0] = x0r + a1r + a2r; im[0] = x0i + a1i + a2i;
+  re[1] = p1r - q1i; im[1] = p1i + q1r;
+  re[4] = p1r + q1i; im[4] = p1i - q1r;
+  re[2] = p2r - q2i; im[2] = p2i + q2r;
+  re[3] = p2r + q2i; im[3] = p2i - q2r;
+}
+
+template <int SIGN> FB_HD void bfly8(double* re, double* im) {
+  const double h = 0.70710678118654752440;
+  double er[4] = { re[0], re[2], re[4], re[6] }, ei[4] = { im[0], im[2], im[4], im[6] };
+  double qr[4] = { re[1], re[3], re[5], re[7] }, qi[4] = { im[1], im[3], im[5], im[7] };
+  bfly4<SIGN>(er, ei);
+  bfly4<SIGN>(qr, qi);
+  // twiddles exp(SIGN 2 pi i t/8), t = 1,2,3
+  double tr, ti;
+  tr = h * (qr[1] - SIGN * qi[1]); ti = h * (qi[1] + SIGN * qr[1]); qr[1] = tr; qi[1] = ti;
+  tr = -SIGN * qi[2]; ti = SIGN * qr[2]; qr[2] = tr; qi[2] = ti;
+  tr = h * (-qr[3] - SIGN * qi[3]); ti = h * (-qi[3] + SIGN * qr[3]); qr[3] = tr; qi[3] = ti;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < 4; ++t) {
+    re[t] = er[t] + qr[t]; im[t] = ei[t] + qi[t];
+    re[t + 4] = er[t] - qr[t]; im[t + 4] = ei[t] - qi[t];
+  }
+}
+
+template <int R, int SIGN> FB_HD void bfly(double* re, double* im) {
+  if (R == 2) bfly2<SIGN>(re, im);
+  else if (R == 3) bfly3<SIGN>(re, im);
+  else if (R == 4) bfly4<SIGN>(re, im);
+  else if (R == 5) bfly5<SIGN>(re, im);
+  else bfly8<SIGN>(re, im);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one radix-R pass over the tile.  FWD: DIF (butterfly, then twiddle).  !FWD: DIT (conj twiddle, then
+// inverse butterfly) -- exactly undoes the FWD pass up to the factor R.
+template <int TB, bool ROT, int R, bool FWD>
+FB_HD void pass_R(double* tile, const LinePlan& P, int q, int lane, int worker, int nworkers) {
+  const int M = P.M, s = P.sub[q], Lc = s * R;
+  const int tstep = M / Lc;
+  const int nb = M / R;
+  for (int b = worker; b < nb; b += nworkers) {
+    const int blk = b / s, n = b - blk * s;
+    const int base = blk * Lc + n;
+    double re[R], im[R];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < R; ++t) {
+      const int m = base + t * s;
+      re[t] = tile[taddr<TB, ROT>(m, 0, M, lane)];
+      im[t] = tile[taddr<TB, ROT>(m, 1, M, lane)];
+    }
+    if (FWD) {
+      bfly<R, -1>(re, im);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 1; t < R; ++t) {
+        const cpx w = P.wM[n * t * tstep];
+        const double xr = re[t] * w.x - im[t] * w.y, xi = re[t] * w.y + im[t] * w.x;
+        re[t] = xr; im[t] = xi;
+      }
+    } else {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 1; t < R; ++t) {
+        const cpx w = P.wM[n * t * tstep];          // multiply by conj(w)
+        const double xr = re[t] * w.x + im[t] * w.y, xi = im[t] * w.x - re[t] * w.y;
+        re[t] = xr; im[t] = xi;
+      }
+      bfly<R, +1>(re, im);
+    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < R; ++t) {
+      const int m = base + t * s;
+      tile[taddr<TB, ROT>(m, 0, M, lane)] = re[t];
+      tile[taddr<TB, ROT>(m, 1, M, lane)] = im[t];
+    }
+  }
+}
+
+template <int TB, bool ROT, bool FWD>
+FB_HD void fft_pass(double* tile, const LinePlan& P, int q, int lane, int worker, int nworkers) {
+  switch (P.radix[q]) {
+    case 2: pass_R<TB, ROT, 2, FWD>(tile, P, q, lane, worker, nworkers); break;
+    case 3: pass_R<TB, ROT, 3, FWD>(tile, P, q, lane, worker, nworkers); break;
+    case 4: pass_R<TB, ROT, 4, FWD>(tile, P, q, lane, worker, nworkers); break;
+    case 5: pass_R<TB, ROT, 5, FWD>(tile, P, q, lane, worker, nworkers); break;
+    default: pass_R<TB, ROT, 8, FWD>(tile, P, q, lane, worker, nworkers); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward split: complex FFT of the packed sequence -> spectrum of the real line.
+//   PP : slot(pos k) <- (Re X_k, Im X_k), k=1..M-1 ; slot(0) <- (X_0, X_M)        [R2HC content]
+//   NN : slot(pos k) <- (Y_k, Y_{N-k}) ; slot(0) <- (Y_0, Y_M)                    [REDFT10 content]
+//   DD : as NN on the sign-flipped input; row holding DCT mode q holds DST mode N-1-q (fft.f90:537-560)
+template <int TB, bool ROT>
+FB_HD void split_fwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
+  const int M = P.M;
+  const bool mk = (P.kind != KIND_PP);
+  for (int k = worker; 2 * k <= M; k += nworkers) {
+    if (k == 0) {
+      const int a0 = taddr<TB, ROT>(0, 0, M, lane), a1 = taddr<TB, ROT>(0, 1, M, lane);
+      const double zr = tile[a0], zi = tile[a1];
+      double x0 = zr + zi, xm = zr - zi;
+      if (mk) { x0 = 2.0 * x0; xm = 2.0 * P.wQ[M].x * xm; }
+      tile[a0] = x0; tile[a1] = xm;
+      continue;
+    }
+    const int pk = P.pos[k];
+    const int akr = taddr<TB, ROT>(pk, 0, M, lane), aki = taddr<TB, ROT>(pk, 1, M, lane);
+    if (2 * k == M) {                                   // X = conj(Z)
+      double xr = tile[akr], xi = -tile[aki];
+      if (mk) {
+        const cpx q = P.wQ[k];
+        const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
+        xr = 2.0 * tr; xi = -2.0 * ti;
+      }
+      tile[akr] = xr; tile[aki] = xi;
+      continue;
+    }
+    const int pj = P.pos[M - k];
+    const int ajr = taddr<TB, ROT>(pj, 0, M, lane), aji = taddr<TB, ROT>(pj, 1, M, lane);
+    const double zkr = tile[akr], zki = tile[aki], zjr = tile[ajr], zji = tile[aji];
+    // E = (Z_k + conj Z_j)/2 ; O = -(i/2)(Z_k - conj Z_j) ; X_k = E + w^k O ; X_j = conj(E - w^k O)
+    const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
+    const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
+    const cpx w = P.wN[k];
+    const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
+    double xkr = er + wor, xki = ei + woi, xjr = er - wor, xji = -(ei - woi);
+    if (mk) {
+      const cpx qk = P.wQ[k], qj = P.wQ[M - k];
+      const double tkr = xkr * qk.x - xki * qk.y, tki = xkr * qk.y + xki * qk.x;
+      const double tjr = xjr * qj.x - xji * qj.y, tji = xjr * qj.y + xji * qj.x;
+      xkr = 2.0 * tkr; xki = -2.0 * tki; xjr = 2.0 * tjr; xji = -2.0 * tji;
+    }
+    tile[akr] = xkr; tile[aki] = xki; tile[ajr] = xjr; tile[aji] = xji;
+  }
+}
+
+// backward merge: inverse of split_fwd up to the FFTW scale (HC2R: N, REDFT01/RODFT01: 2N)
+template <int TB, bool ROT>
+FB_HD void merge_bwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
+  const int M = P.M;
+  const bool mk = (P.kind != KIND_PP);
+  for (int k = worker; 2 * k <= M; k += nworkers) {
+    if (k == 0) {
+      const int a0 = taddr<TB, ROT>(0, 0, M, lane), a1 = taddr<TB, ROT>(0, 1, M, lane);
+      double x0 = tile[a0], xm = tile[a1];
+      if (mk) xm = 2.0 * P.wQ[M].x * xm;               // V'_M = sqrt(2) Y_M
+      tile[a0] = x0 + xm; tile[a1] = x0 - xm;
+      continue;
+    }
+    const int pk = P.pos[k];
+    const int akr = taddr<TB, ROT>(pk, 0, M, lane), aki = taddr<TB, ROT>(pk, 1, M, lane);
+    if (2 * k == M) {                                   // Z' = 2 conj(X)
+      double xr = tile[akr], xi = tile[aki];
+      if (mk) {                                         // V' = conj(q) (Y_k - i Y_{N-k})
+        const cpx q = P.wQ[k];
+        const double vr = xr * q.x - xi * q.y, vi = -xi * q.x - xr * q.y;
+        xr = vr; xi = vi;
+      }
+      tile[akr] = 2.0 * xr; tile[aki] = -2.0 * xi;
+      continue;
+    }
+    const int pj = P.pos[M - k];
+    const int ajr = taddr<TB, ROT>(pj, 0, M, lane), aji = taddr<TB, ROT>(pj, 1, M, lane);
+    double xkr = tile[akr], xki = tile[aki], xjr = tile[ajr], xji = tile[aji];
+    if (mk) {
+      const cpx qk = P.wQ[k], qj = P.wQ[M - k];
+      const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
+      const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
+      xkr = vkr; xki = vki; xjr = vjr; xji = vji;
+    }
+    // S = X_k + conj X_j ; D = X_k - conj X_j ; T = i conj(w^k) D ; Z'_k = S + T ; Z'_j = conj(S - T)
+    const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
+    const cpx w = P.wN[k];
+    const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
+    const double tr = -ci, ti = cr;                                       // i * (.)
+    tile[akr] = sr + tr; tile[aki] = si + ti;
+    tile[ajr] = sr - tr; tile[aji] = -(si - ti);
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,59 @@
+"""ctypes binding of libflutas_b200.so (include/flutas_b200.h).  Fails loudly when the library is
+missing or there is no CUDA device -- there is no CPU fallback on this path."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_dp = C.POINTER(C.c_double)
+_LIB = None
+
+
+class FlutasB200Error(RuntimeError):
+    pass
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = _build.SO
+    if not os.path.exists(so):
+        so = _build.build()
+    L = C.CDLL(so)
+    vp, ci, cd, cc = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+    ip = C.POINTER(C.c_int)
+    L.flutas_b200_version.restype = cc
+    L.flutas_b200_last_error.restype = cc
+    L.flutas_b200_launch_count.restype = C.c_long
+    L.flutas_b200_init.argtypes = [ci, ci, ci]
+    L.flutas_b200_set_stream.argtypes = [vp]
+    L.flutas_b200_alloc.restype = vp
+    L.flutas_b200_alloc.argtypes = [C.c_size_t]
+    L.flutas_b200_free.argtypes = [vp]
+    L.flutas_b200_memcpy.argtypes = [vp, vp, C.c_size_t]
+    L.flutas_b200_fftini.argtypes = [ip, ip, cc, cc, C.POINTER(vp), _dp]
+    L.flutas_b200_fftend.argtypes = [C.POINTER(vp)]
+    L.flutas_b200_solver.argtypes = [ip, C.POINTER(vp), cd, vp, vp, vp, vp, cc, cc, vp]
+    L.flutas_b200_solver_invalidate.argtypes = [C.POINTER(vp)]
+    L.flutas_b200_debug_thomas_mode.argtypes = [C.POINTER(vp), ci]
+    L.flutas_b200_fillps.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp]
+    L.flutas_b200_updt_rhs_b.argtypes = [ci] * 3 + [cc, vp, vp, vp, vp]
+    L.flutas_b200_correc.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp, vp]
+    L.flutas_b200_chkdiv.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] * 4 + [_dp, _dp]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise FlutasB200Error(load().flutas_b200_last_error().decode())
+
+
+EXPORTS = [
+    "flutas_b200_version", "flutas_b200_last_error", "flutas_b200_init", "flutas_b200_set_stream",
+    "flutas_b200_alloc", "flutas_b200_free", "flutas_b200_memcpy", "flutas_b200_synchronize",
+    "flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_solver_invalidate",
+    "flutas_b200_fillps", "flutas_b200_updt_rhs_b", "flutas_b200_correc", "flutas_b200_chkdiv",
+    "flutas_b200_launch_count",
+]

@@ -1,0 +1,102 @@
+/*
+ * flutas_b200.h -- C ABI of libflutas_b200.so: the B200-native (sm_100a) pressure-Poisson path of FluTAS.
+ *
+ * Every entry point is what a thin Fortran `iso_c_binding` shim with the reference's subroutine names
+ * and argument lists forwards to (the shim is shown in INTEGRATION.md).  Conventions:
+ *   - all reals are FP64, all arrays Fortran column-major, passed as the address of their FIRST element
+ *     (c_loc(arr)), with the halo widths the reference uses:
+ *         p(0:n1+1, 0:n2+1, 0:n3+1)                      u,v,w(1-nh_u:n1+nh_u, 1-nh_u:n2+nh_u, 1-nh_u:n3+nh_u)
+ *         dzci, dzfi(1-nh_d:n3+nh_d)                     lambdaxy(n_z(1), n_z(2))      a,b,c(n_z(3))
+ *   - field pointers (p,u,v,w) may be DEVICE pointers (cudaMalloc / flutas_b200_alloc / managed memory;
+ *     the call is then asynchronous on the library stream, like a kernel launch) or plain HOST pointers
+ *     (the library stages them through device buffers and returns after the result is back on the host).
+ *     Small coefficient arrays (lambdaxy, a, b, c, dzci, dzfi, rhsb*) may live on either side.
+ *   - return value 0 = success; anything else is an error whose text is flutas_b200_last_error().
+ *     The reference has no status arguments on this path (errors print and stop, src/fft.f90:879-883);
+ *     the Fortran shim does the same with a non-zero return.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ */
+#ifndef FLUTAS_B200_H
+#define FLUTAS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUTAS_B200_OK 0
+#define FLUTAS_B200_ERR_CUDA 1        /* a CUDA runtime call failed / no device                     */
+#define FLUTAS_B200_ERR_UNSUPPORTED 2 /* BC pair / transform length not available on this path      */
+#define FLUTAS_B200_ERR_ARG 3         /* inconsistent arguments                                     */
+
+/* Library version string, e.g. "flutas_b200 0.1 (sm_100a)". */
+const char *flutas_b200_version(void);
+const char *flutas_b200_last_error(void);
+
+/* Replaces the GPU binding of initmpi (src/initmpi.f90:59-63: cudaSetDevice(local rank)) and records
+ * the slab decomposition: `rank` of `nranks` owns z-planes [rank*ng3/nranks, (rank+1)*ng3/nranks)
+ * (= the reference's _DECOMP_X layout with dims_in = (1, nranks), src/initmpi.f90:87-104). */
+int flutas_b200_init(int device, int rank, int nranks);
+
+/* CUDA stream (cudaStream_t) all subsequent work is enqueued on; NULL = the legacy default stream. */
+int flutas_b200_set_stream(void *cuda_stream);
+
+/* Device memory for fields (the reference uses CUDA managed arrays, main__single_phase.f90:157-163;
+ * a gfortran host maps these with c_f_pointer). */
+void *flutas_b200_alloc(size_t bytes);
+void flutas_b200_free(void *ptr);
+int flutas_b200_memcpy(void *dst, const void *src, size_t bytes);   /* any direction, synchronous */
+int flutas_b200_synchronize(void);
+
+/* fftini, src/fft.f90:24-157.  n_x, n_y: x- and y-pencil sizes (mod_common_mpi); bcxy(0:1,2) as four
+ * characters x0,x1,y0,y1; c_or_f(2).  Fills arrplan(2,2) (Fortran order: fwd-x, bwd-x, fwd-y, bwd-y)
+ * with opaque handles and normfft exactly as :71,87,125,150.  Supported: 'c' with PP, NN, DD
+ * (the set the reference's own GPU path supports, src/fft.f90:879-883) and even lengths whose half
+ * factors into 2,3,5. */
+int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], const char c_or_f[2],
+                       void *arrplan[4], double *normfft);
+
+/* fftend, src/fft.f90:159-179. */
+int flutas_b200_fftend(void *arrplan[4]);
+
+/* solver_cpu / solver_gpu, src/solver_cpu.f90:20-115, src/solver_gpu.f90:31-472.
+ * n = local x-pencil interior size; lambdaxy, a, b, c as returned by initsolver (CPU, i.e. FFTW
+ * half-complex eigenvalue order, src/initsolver.f90:87-93,136-139); bcz(0:1); c_or_f(3) (must be 'c').
+ * Solves in place on the interior of p; halos are left untouched.  lambdaxy/a/b/c are cached on the
+ * device at the first call (they are constant after initsolver); call flutas_b200_solver_invalidate
+ * if they ever change. */
+int flutas_b200_solver(const int n[3], void *const arrplan[4], double normfft, const double *lambdaxy,
+                       const double *a, const double *b, const double *c, const char bcz[2],
+                       const char c_or_f[3], double *p);
+int flutas_b200_solver_invalidate(void *const arrplan[4]);
+
+/* fillps, src/fillps.f90:16-69 (with _CONSTANT_COEFFS_POISSON: the result is multiplied by rho0). */
+int flutas_b200_fillps(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, double dyi, double dzi,
+                       const double *dzfi, double dti, double rho0, const double *u, const double *v,
+                       const double *w, double *p);
+
+/* updt_rhs_b, src/bound.f90:829-944, for a rank that owns all six faces (cell-centred).
+ * cbc(0:1,3) as six characters; rhsbx(ny,nz,0:1), rhsby(nx,nz,0:1), rhsbz(nx,ny,0:1). */
+int flutas_b200_updt_rhs_b(int nx, int ny, int nz, const char cbc[6], const double *rhsbx,
+                           const double *rhsby, const double *rhsbz, double *p);
+
+/* correc, src/correc.f90:16-81 (constant-coefficient branch).  `rho` is accepted for signature
+ * compatibility and never dereferenced (it is a (0,0,0)-sized dummy in single-phase runs). */
+int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, double dyi, double dzi,
+                       const double *dzci, double dt, double rho0, const double *p, double *u, double *v,
+                       double *w, const double *rho);
+
+/* chkdiv, src/chkdiv.f90:18-69.  Returns this rank's divtot / divmax (the caller all-reduces across
+ * ranks exactly where the reference calls MPI_ALLREDUCE, :64-65).  Synchronous. */
+int flutas_b200_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u,
+                       const double *dzfi, const double *u, const double *v, const double *w,
+                       double *divtot, double *divmax);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches claim). */
+long flutas_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUTAS_B200_H */

@@ -1,0 +1,49 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/flutas_b200.h declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from flutas_b200 import api, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "flutas_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(flutas_b200_\w+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(lib.EXPORTS) == set(names)
+
+
+def test_version_string():
+    assert b"sm_100a" in lib.load().flutas_b200_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lib.FlutasB200Error, match="no CUDA device"):
+        api.fftini((8, 8, 8), (8, 8, 8), ("PP", "PP"))
+    with pytest.raises(lib.FlutasB200Error, match="no CUDA device"):
+        api.init(0)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "flutas_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("with the oracle", ""), f

@@ -1,0 +1,158 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+Tolerance: max|dp|/max|p| <= 1e-12 in FP64 after removing the mean when the operator is singular
+(BASELINE.json north_star); stencils (fillps/correc/chkdiv divmax) bit-exact."""
+import numpy as np
+import pytest
+
+from flutas_b200 import api, lib
+from flutas_b200.cases import Case
+from oracle import oracle
+from util import gauge_rel_err, golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _solve_gpu(case, rhs, device=False, generic_z=False):
+    s = case.setup
+    n = case.ng
+    pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
+    assert nf == s.normfft
+    if generic_z:
+        lib.check(lib.load().flutas_b200_debug_thomas_mode(pl.h, 1))
+    p = case.new_p()
+    p[...] = 7.0                                      # halos must come back untouched
+    p[1:-1, 1:-1, 1:-1] = rhs
+    if device:
+        import torch
+        pd = api.device_field(p)
+        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", pd)
+        torch.cuda.synchronize()
+        p = api.host_field(pd, p.shape)
+    else:
+        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", p)
+    api.fftend(pl)
+    halo = p.copy()
+    halo[1:-1, 1:-1, 1:-1] = 7.0
+    assert np.all(halo == 7.0)
+    return p
+
+
+@pytest.mark.parametrize("path", [f for f in golden_files() if "ndp" not in f and "pdn" not in f],
+                         ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("generic_z", [False, True], ids=["ztile", "zgeneric"])
+def test_solver_matches_golden(path, generic_z):
+    case, rhs, pgold = load_golden(path)
+    p = _solve_gpu(case, rhs, generic_z=generic_z)
+    err = gauge_rel_err(p[1:-1, 1:-1, 1:-1], pgold, case.singular)
+    assert err <= TOL, err
+    case.boundp(p)
+    res = np.max(np.abs(case.laplacian(p) - rhs)) / np.max(np.abs(rhs))
+    assert res <= 1e-11, res
+
+
+def test_unsupported_bc_fails_loudly():
+    with pytest.raises(lib.FlutasB200Error, match="only PP, NN, DD"):
+        api.fftini((8, 8, 8), (8, 8, 8), ("ND", "PP"))
+    with pytest.raises(lib.FlutasB200Error, match="factors into 2,3,5"):
+        api.fftini((14, 8, 8), (14, 8, 8), ("PP", "PP"))
+
+
+CASES = [
+    ("C1", (64, 64, 64), ("PP", "PP", "PP"), (2 * np.pi,) * 3, 0.0),
+    ("chan", (128, 64, 32), ("PP", "PP", "NN"), (6.0, 3.0, 1.0), 2.0),
+    ("chan72", (64, 32, 72), ("PP", "PP", "NN"), (6.0, 3.0, 1.0), 1.0),
+    ("rb", (96, 80, 40), ("NN", "NN", "NN"), (2.0, 2.0, 1.0), 0.0),
+    ("dd", (40, 48, 16), ("DD", "NN", "DD"), (1.0, 2.0, 1.0), 0.0),
+    ("pnp", (32, 36, 24), ("PP", "NN", "PP"), (2.0, 1.0, 1.0), 0.0),
+    ("ragged", (20, 12, 10), ("NN", "DD", "NN"), (1.0, 1.0, 1.0), 0.5),
+    ("wide", (1024, 16, 8), ("PP", "NN", "NN"), (4.0, 1.0, 1.0), 0.0),
+    ("tall", (16, 2048, 4), ("DD", "PP", "NN"), (1.0, 4.0, 1.0), 0.0),
+    ("deep", (16, 16, 256), ("PP", "PP", "PP"), (1.0, 1.0, 4.0), 0.0),
+]
+
+
+@pytest.mark.parametrize("name,ng,cbc,lengths,gr", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("device", [False, True], ids=["hostptr", "devptr"])
+def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device):
+    case = Case(ng, cbc, lengths, gr=gr, seed=4242 + len(name), name=name)
+    s = case.setup
+    u, v, w = case.velocity()
+    rhs_p = case.new_p()
+    oracle.fillps(ng, case.nh_d, case.nh_u, s.dli, s.dzfi, case.dti, case.rho0, u, v, w, rhs_p)
+    rhs = rhs_p[1:-1, 1:-1, 1:-1].copy(order="F")
+    pref = rhs_p.copy(order="F")
+    oracle.Solver(ng, cbc[0], cbc[1]).solve(s.lambdaxy, s.a, s.b, s.c, cbc[2], pref)
+    p = _solve_gpu(case, rhs, device=device)
+    err = gauge_rel_err(p[1:-1, 1:-1, 1:-1], pref[1:-1, 1:-1, 1:-1], case.singular)
+    assert err <= TOL, err
+
+
+@pytest.mark.parametrize("nh_u", [1, 3])
+@pytest.mark.parametrize("cbc", [("PP", "PP", "PP"), ("PP", "PP", "NN"), ("NN", "NN", "NN"), ("DD", "NN", "PP")],
+                         ids=lambda c: "".join(c))
+def test_pressure_step_stencils_bit_exact_and_divergence_free(cbc, nh_u):
+    case = Case((48, 40, 24), cbc, (2.0, 1.0, 1.0), rho0=0.1, gr=(1.5 if cbc[2] != "PP" else 0.0), nh_u=nh_u, seed=99)
+    s = case.setup
+    n = case.ng
+    u, v, w = case.velocity()
+    uo, vo, wo = u.copy(order="F"), v.copy(order="F"), w.copy(order="F")
+    # fillps: bit-exact
+    p = case.new_p()
+    po = case.new_p()
+    api.fillps(*n, case.nh_d, nh_u, *s.dli, s.dzfi, case.dti, case.rho0, u, v, w, p)
+    oracle.fillps(n, case.nh_d, nh_u, s.dli, s.dzfi, case.dti, case.rho0, uo, vo, wo, po)
+    assert np.array_equal(p, po)
+    api.updt_rhs_b(*n, cbc, s.rhsbx, s.rhsby, s.rhsbz, p)
+    oracle.updt_rhs_b(n, s.rhsbx, s.rhsby, s.rhsbz, po)
+    assert np.array_equal(p, po)
+    rhs = p[1:-1, 1:-1, 1:-1].copy()
+    # solver
+    pl, nf = api.fftini(n, n, (cbc[0], cbc[1]))
+    api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, cbc[2], "ccc", p)
+    oracle.Solver(n, cbc[0], cbc[1]).solve(s.lambdaxy, s.a, s.b, s.c, cbc[2], po)
+    assert gauge_rel_err(p[1:-1, 1:-1, 1:-1], po[1:-1, 1:-1, 1:-1], case.singular) <= TOL
+    case.boundp(p)
+    # correc: bit-exact on identical p
+    u2, v2, w2 = u.copy(order="F"), v.copy(order="F"), w.copy(order="F")
+    api.correc(*n, case.nh_d, nh_u, *s.dli, s.dzci, case.dt, case.rho0, p, u, v, w)
+    oracle.correc(n, case.nh_d, nh_u, s.dli, s.dzci, case.dt, case.rho0, p, u2, v2, w2)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2) and np.array_equal(w, w2)
+    case.correct_dirichlet_faces(p, u, v, w)
+    case.refresh_velocity_halos(u, v, w)
+    divtot, divmax = api.chkdiv(*n, *s.dli, case.nh_d, nh_u, s.dzfi, u, v, w)
+    otot, omax = oracle.chkdiv(n, s.dli, case.nh_d, nh_u, s.dzfi, u, v, w)
+    assert divmax == omax
+    assert abs(divtot - otot) <= 1e-9 * max(1.0, abs(otot)) + 1e-12
+    assert divmax <= 1e-12, divmax
+    del rhs
+    api.fftend(pl)
+
+
+def test_device_resident_step_and_linearity():
+    """Size-independent properties on a larger grid: linearity of the solve and discrete residual."""
+    import torch
+    case = Case((256, 128, 64), ("PP", "PP", "NN"), (6.0, 3.0, 1.0), gr=1.0, seed=5)
+    s = case.setup
+    n = case.ng
+    rng = np.random.default_rng(1)
+    r1 = rng.uniform(-1, 1, n)
+    r2 = rng.uniform(-1, 1, n)
+    r1 -= r1.mean()
+    r2 -= r2.mean()
+    pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
+    sols = []
+    for r in (r1, r2, 2.0 * r1 - 3.0 * r2):
+        p = case.new_p()
+        p[1:-1, 1:-1, 1:-1] = r
+        pd = api.device_field(p)
+        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", pd)
+        torch.cuda.synchronize()
+        sols.append(api.host_field(pd, p.shape))
+    comb = 2.0 * sols[0] - 3.0 * sols[1]
+    assert gauge_rel_err(sols[2][1:-1, 1:-1, 1:-1], comb[1:-1, 1:-1, 1:-1], True) <= 1e-11
+    # weights of the z-stretched operator are not uniform, so compare the residual, not the mean
+    p = case.boundp(sols[0])
+    res = np.max(np.abs(case.laplacian(p) - r1)) / np.max(np.abs(r1))
+    assert res <= 1e-10, res
+    api.fftend(pl)
