@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 Poisson-solve throughput of the FluTAS pressure path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
+
+A "step" is one `solver` call (x/y transforms + z tridiagonal solve + inverse transforms) on one
+synthetic right-hand side of the named grid, device resident, in place.  `value` = grid points / step
+time (Gpts/s, whole job).  `e2e` is the same call through the C ABI with HOST (pinned) buffers, i.e.
+including the host->device and device->host copies of p.  `roofline` describes the slowest kernel of
+the solve, timed live with CUDA events on the launching stream; `cpu_baseline` is the CPU oracle
+(a restatement of solver_cpu.f90 -- NOT FluTAS+FFTW, which cannot be built here) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_PT = {"xfft_fwd": 16, "yfft_fwd": 16, "thomas_z": 16, "yfft_bwd": 16, "xfft_bwd": 16,
+                    "fillps": 32, "correc": 56}
+SOLVER_BYTES_PER_PT = 80
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy peak)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + ",".join(self.FIELDS),
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded sample of the workload (per-stage sampling, summed per point)
+def cpu_sample(case, budget_s, threads=None):
+    from oracle import oracle
+    if threads:
+        oracle.set_num_threads(threads)
+    n1, n2, n3 = case.ng
+    s = case.setup
+    rng = np.random.default_rng(0)
+    kfx, kbx, _ = oracle.find_fft(case.cbc[0])
+    kfy, kby, _ = oracle.find_fft(case.cbc[1])
+    periodic = case.cbc[2] == "PP"
+
+    def run(nk, nj):
+        """x/y transforms on nk planes, z solves on nj rows of columns; returns seconds per grid point"""
+        nk, nj = max(1, min(nk, n3)), max(1, min(nj, n2))
+        slab = np.asfortranarray(rng.uniform(-1, 1, (n1, n2, nk)))
+        t0 = time.perf_counter()
+        oracle.r2r(kfx, slab, 0)
+        oracle.r2r(kfy, slab, 1)
+        oracle.r2r(kby, slab, 1)
+        oracle.r2r(kbx, slab, 0)
+        t_xy = time.perf_counter() - t0
+        cols = np.asfortranarray(rng.uniform(-1, 1, (n1, nj, n3)))
+        lam = np.asfortranarray(s.lambdaxy[:, :nj] - 1.0e-3)          # keep every sampled column regular
+        t0 = time.perf_counter()
+        oracle.gaussel(s.a, s.b, s.c, lam, cols, periodic)
+        t_z = time.perf_counter() - t0
+        return t_xy / (n1 * n2 * nk) + t_z / (n1 * nj * n3), t_xy + t_z, nk, nj
+
+    per_pt, spent, nk, nj = run(1, 1)                                   # probe
+    scale = max(1.0, 0.8 * budget_s / max(spent, 1e-6))
+    nk2, nj2 = int(max(1, min(n3, nk * scale))), int(max(1, min(n2, nj * scale)))
+    per_pt, spent, nk, nj = run(nk2, nj2)
+    return {"gpts": 1.0e-9 / per_pt, "seconds": spent,
+            "sample": "x/y transforms on %d of %d z-planes + z solves on %d of %d y-rows of the %dx%dx%d grid, "
+                      "per-point costs summed" % (nk, n3, nj, n2, n1, n2, n3),
+            "cores": oracle.num_threads()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from flutas_b200.cases import CONFIGS, Case
+    from oracle import oracle
+    case = Case.from_config(args.workload)
+    n1, n2, n3 = case.ng
+    budget = max(1.0, min(8.0, 150.0 / (args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(case, budget)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_sample(case, budget))
+    wall = time.perf_counter() - t0
+    gpts = float(np.mean([v["gpts"] for v in vals]))
+    line = {"impl": "reference", "metric": "poisson_solve_throughput", "value": gpts, "unit": "Gpts/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * n1 * n2 * n3 / (gpts * 1e9), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(case, args.workload),
+            "cpu_baseline": {"value": gpts, "unit": "Gpts/s", "cores": vals[-1]["cores"], "kind": "port",
+                             "sample": vals[-1]["sample"],
+                             "note": "CPU restatement of solver_cpu.f90 with its own FFT (oracle/), not FluTAS+FFTW: "
+                                     "no Fortran/MPI/FFTW toolchain in this image"},
+            "e2e": {"value": gpts, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line))
+
+
+def workload_config(case, wid):
+    from flutas_b200.cases import CONFIGS
+    n1, n2, n3 = case.ng
+    return {"workload": "%s: %s" % (wid, CONFIGS[wid]["desc"]), "grid": [n1, n2, n3], "pressure_bc": "/".join(case.cbc),
+            "l2_policy": "inputs larger than L2: one FP64 field is %.2f GB vs 126 MB of L2" % (8e-9 * n1 * n2 * n3),
+            "step": "one solver call (5 kernels), in place, device resident"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from flutas_b200 import api
+    from flutas_b200.cases import Case
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pressure path has no CPU fallback")
+    if world > 1:
+        raise SystemExit("multi-GPU slab solve not wired into bench.py yet")
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank, rank, world)
+
+    case = Case.from_config(args.workload)
+    s = case.setup
+    n = case.ng
+    n1, n2, n3 = n
+    npts = n1 * n2 * n3
+    u, v, w = case.velocity()
+    ud, vd, wd = (api.device_field(f) for f in (u, v, w))
+    del u, v, w
+    pd = api.device_field(case.new_p())
+    pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
+
+    def fill():
+        api.fillps(*n, case.nh_d, case.nh_u, *s.dli, s.dzfi, case.dti, case.rho0, ud, vd, wd, pd)
+        api.updt_rhs_b(*n, case.cbc, s.rhsbx, s.rhsby, s.rhsbz, pd)
+
+    def solve():
+        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", pd)
+
+    # ---- timed region: K solver calls ----------------------------------------------------------
+    fill()
+    for _ in range(args.warmup):
+        solve()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    api.profile_enable(True)
+    api.profile_read()
+    l0 = api.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        solve()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = api.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    stages = api.profile_read()
+    api.profile_enable(False)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = npts / (ms_step * 1e-3) / 1e9
+
+    # ---- ms per pressure step (fillps + updt_rhs_b + solver + correc), device resident -----------
+    api.profile_enable(True)
+    api.profile_read()
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nps = max(3, min(args.steps, 10))
+    p0.record()
+    for _ in range(nps):
+        fill()
+        solve()
+        api.correc(*n, case.nh_d, case.nh_u, *s.dli, s.dzci, case.dt, case.rho0, pd, ud, vd, wd)
+    p1.record()
+    torch.cuda.synchronize()
+    ms_pressure_step = p0.elapsed_time(p1) / nps
+    stages_ps = api.profile_read()
+    api.profile_enable(False)
+    for k in ("fillps", "correc"):
+        if k in stages_ps:
+            stages[k] = stages_ps[k]
+
+    # ---- e2e: the same solver call with host (pinned) p ----------------------------------------
+    pcount = (n1 + 2) * (n2 + 2) * (n3 + 2)
+    ph_t = torch.empty(pcount, dtype=torch.float64).pin_memory()
+    ph = ph_t.numpy().reshape((n1 + 2, n2 + 2, n3 + 2), order="F")
+    fill()
+    torch.cuda.synchronize()
+    rhs_host = api.host_field(pd, ph.shape)
+    e2e_ms = []
+    for it in range(args.e2e_steps + 1):
+        ph[...] = rhs_host
+        t0 = time.perf_counter()
+        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", ph)    # returns after the D2H copy
+        dt = time.perf_counter() - t0
+        if it > 0:
+            e2e_ms.append(dt * 1e3)
+    e2e_val = npts / (np.mean(e2e_ms) * 1e-3) / 1e9
+
+    # ---- roofline of the slowest solver kernel ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    stage_tbl = {}
+    for name, (ms, cnt) in stages.items():
+        avg = ms / cnt
+        gbs = ALG_BYTES_PER_PT[name] * npts / (avg * 1e-3) / 1e9
+        stage_tbl[name] = {"ms": round(avg, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    solver_stages = [k for k in ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd") if k in stage_tbl]
+    dom = max(solver_stages, key=lambda k: stage_tbl[k]["ms"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": stage_tbl[dom]["GB/s"], "peak": peak, "unit": "GB/s",
+                "frac": stage_tbl[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_PT[dom] * npts,
+                "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT, "achieved": round(SOLVER_BYTES_PER_PT * value, 1),
+                           "frac": round(SOLVER_BYTES_PER_PT * value / peak, 4)},
+                "stages": stage_tbl}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        c = cpu_sample(case, 15.0)
+        cpu = {"value": round(c["gpts"], 5), "unit": "Gpts/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
+               "seconds": round(c["seconds"], 1),
+               "note": "CPU restatement of solver_cpu.f90 with its own FFT (oracle/), not FluTAS+FFTW"}
+
+    line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(case, args.workload),
+            "ms_per_pressure_step": round(ms_pressure_step, 4),
+            "pressure_step": "fillps + updt_rhs_b + solver + correc, device resident (boundp not included)",
+            "e2e": {"value": round(e2e_val, 4), "unit": "Gpts/s", "h2d_bytes_per_step": pcount * 8,
+                    "d2h_bytes_per_step": pcount * 8, "ms_per_step": round(float(np.mean(e2e_ms)), 3),
+                    "path": "flutas_b200_solver with a pinned host p (H2D + 5 kernels + D2H)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    api.fftend(pl)
+
+
+if __name__ == "__main__":
+    main()

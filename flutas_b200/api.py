@@ -128,3 +128,17 @@ def chkdiv(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzfi, u, v, w):
 
 def launch_count():
     return _lib.load().flutas_b200_launch_count()
+
+
+def profile_enable(on=True):
+    _lib.load().flutas_b200_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{stage name: (ms_sum, launches)} since the previous read (synchronises the stream)."""
+    L = _lib.load()
+    n = L.flutas_b200_profile_stage_count()
+    ms = (C.c_double * n)()
+    cnt = (C.c_long * n)()
+    _lib.check(L.flutas_b200_profile_read(ms, cnt))
+    return {L.flutas_b200_profile_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}

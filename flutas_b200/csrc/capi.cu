@@ -49,6 +49,27 @@ int fail(int code, const char* fmt, ...) {
       return fail(FLUTAS_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// optional per-stage timing with CUDA events on the library stream (bench.py's live roofline numbers)
+enum Stage { ST_XF = 0, ST_YF, ST_Z, ST_YB, ST_XB, ST_FILLPS, ST_CORREC, ST_EXCH_F, ST_EXCH_B, ST_COUNT };
+const char* const g_stage_names[ST_COUNT] = {"xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd",
+                                             "fillps", "correc", "exchange_fwd", "exchange_bwd"};
+struct StageRec { int id; cudaEvent_t e0, e1; };
+bool g_prof = false;
+std::vector<StageRec> g_prof_recs;
+struct StageTimer {
+  int id; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  explicit StageTimer(int id_) : id(id_) {
+    if (!g_prof) return;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, g_stream);
+  }
+  ~StageTimer() {
+    if (!e0) return;
+    cudaEventRecord(e1, g_stream);
+    g_prof_recs.push_back({id, e0, e1});
+  }
+};
+
 int ensure_device() {
   if (g_device >= 0) return FLUTAS_B200_OK;
   int n = 0;
@@ -264,6 +285,31 @@ const char* flutas_b200_version(void) { return "flutas_b200 0.1 (sm_100a, FP64 p
 const char* flutas_b200_last_error(void) { return g_err.c_str(); }
 long flutas_b200_launch_count(void) { return g_launches.load(); }
 
+int flutas_b200_profile_enable(int on) {
+  g_prof = (on != 0);
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_profile_stage_count(void) { return ST_COUNT; }
+const char* flutas_b200_profile_stage_name(int id) { return (id >= 0 && id < ST_COUNT) ? g_stage_names[id] : ""; }
+
+// Synchronises the stream, then returns for every stage the summed device time (ms) and the number of
+// timed launches since the last read; clears the records.
+int flutas_b200_profile_read(double* ms_sum, long* counts) {
+  if (int rc = ensure_device()) return rc;
+  CK(cudaStreamSynchronize(g_stream));
+  for (int q = 0; q < ST_COUNT; ++q) { ms_sum[q] = 0.0; counts[q] = 0; }
+  for (StageRec& r : g_prof_recs) {
+    float ms = 0.f;
+    CK(cudaEventSynchronize(r.e1));
+    CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_sum[r.id] += ms; counts[r.id] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
+  return FLUTAS_B200_OK;
+}
+
 int flutas_b200_init(int device, int rank, int nranks) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -393,9 +439,10 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
   const double* abc = sp->abc.as<double>();
   const double* lam = sp->lam_int.as<double>();
 
-  if (int rc = run_x<true>(sp->px, pd, gp, W, gw, 1.0)) return rc;          // solver_cpu.f90:59
-  if (int rc = run_y<true>(sp->py, W, n1, n3)) return rc;                    // :65
+  { StageTimer t(ST_XF); if (int rc = run_x<true>(sp->px, pd, gp, W, gw, 1.0)) return rc; }   // solver_cpu.f90:59
+  { StageTimer t(ST_YF); if (int rc = run_y<true>(sp->py, W, n1, n3)) return rc; }             // :65
   {                                                                          // :71-77
+    StageTimer t(ST_Z);
     const long ncol = (long)n1 * n2;
     bool done = false;
     if (sp->thomas_mode == 0) {
@@ -417,8 +464,8 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
       LAUNCHED();
     }
   }
-  if (int rc = run_y<false>(sp->py, W, n1, n3)) return rc;                   // :86
-  if (int rc = run_x<false>(sp->px, W, gw, pd, gp, normfft)) return rc;      // :89,93
+  { StageTimer t(ST_YB); if (int rc = run_y<false>(sp->py, W, n1, n3)) return rc; }            // :86
+  { StageTimer t(ST_XB); if (int rc = run_x<false>(sp->px, W, gw, pd, gp, normfft)) return rc; }  // :89,93
 
   if (host_p) {
     CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
@@ -445,8 +492,11 @@ int flutas_b200_fillps(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   if (int rc = g_coef.reserve(nd * sizeof(double))) return rc;
   CK(cudaMemcpyAsync(g_coef.p, dzfi, nd * sizeof(double), cudaMemcpyDefault, g_stream));
   dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
-  fillps_kernel<<<grd, blk, 0, g_stream>>>(g, dti * dxi, dti * dyi, dti, g_coef.as<double>() + (nh_d - 1), rho0,
-                                           fu.dev, fv.dev, fw.dev, fp.dev);
+  {
+    StageTimer t(ST_FILLPS);
+    fillps_kernel<<<grd, blk, 0, g_stream>>>(g, dti * dxi, dti * dyi, dti, g_coef.as<double>() + (nh_d - 1), rho0,
+                                             fu.dev, fv.dev, fw.dev, fp.dev);
+  }
   LAUNCHED();
   if (int rc = stage_out(fp)) return rc;
   if (fp.staged) CK(cudaStreamSynchronize(g_stream));
@@ -507,8 +557,11 @@ int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   CK(cudaMemcpyAsync(g_coef.p, dzci, nd * sizeof(double), cudaMemcpyDefault, g_stream));
   const double rho0i = 1.0 / rho0;
   dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
-  correc_kernel<<<grd, blk, 0, g_stream>>>(g, dt * dxi, dt * dyi, dt, g_coef.as<double>() + (nh_d - 1), rho0i,
-                                           fp.dev, fu.dev, fv.dev, fw.dev);
+  {
+    StageTimer t(ST_CORREC);
+    correc_kernel<<<grd, blk, 0, g_stream>>>(g, dt * dxi, dt * dyi, dt, g_coef.as<double>() + (nh_d - 1), rho0i,
+                                             fp.dev, fu.dev, fv.dev, fw.dev);
+  }
   LAUNCHED();
   if (int rc = stage_out(fu)) return rc;
   if (int rc = stage_out(fv)) return rc;

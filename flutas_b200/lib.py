@@ -41,6 +41,10 @@ def load():
     L.flutas_b200_updt_rhs_b.argtypes = [ci] * 3 + [cc, vp, vp, vp, vp]
     L.flutas_b200_correc.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp, vp]
     L.flutas_b200_chkdiv.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] * 4 + [_dp, _dp]
+    L.flutas_b200_profile_enable.argtypes = [ci]
+    L.flutas_b200_profile_stage_name.restype = cc
+    L.flutas_b200_profile_stage_name.argtypes = [ci]
+    L.flutas_b200_profile_read.argtypes = [_dp, C.POINTER(C.c_long)]
     _LIB = L
     return L
 
@@ -55,5 +59,6 @@ EXPORTS = [
     "flutas_b200_alloc", "flutas_b200_free", "flutas_b200_memcpy", "flutas_b200_synchronize",
     "flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_solver_invalidate",
     "flutas_b200_fillps", "flutas_b200_updt_rhs_b", "flutas_b200_correc", "flutas_b200_chkdiv",
-    "flutas_b200_launch_count",
+    "flutas_b200_launch_count", "flutas_b200_profile_enable", "flutas_b200_profile_stage_count",
+    "flutas_b200_profile_stage_name", "flutas_b200_profile_read",
 ]

@@ -93,6 +93,16 @@ int flutas_b200_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dz
                        const double *dzfi, const double *u, const double *v, const double *w,
                        double *divtot, double *divmax);
 
+/* Optional per-stage device timing (CUDA events on the library stream), the counterpart of the
+ * reference's named profiler clocks (src/profiler.f90:103-205; labels "SOLVER", "CORREC", ...).
+ * Stage ids 0..count-1 have names ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd", "fillps",
+ * "correc", "exchange_fwd", "exchange_bwd").  profile_read synchronises, fills ms_sum[count] and
+ * counts[count] with the totals since the previous read, and clears them. */
+int flutas_b200_profile_enable(int on);
+int flutas_b200_profile_stage_count(void);
+const char *flutas_b200_profile_stage_name(int id);
+int flutas_b200_profile_read(double *ms_sum, long *counts);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 long flutas_b200_launch_count(void);
 

@@ -132,7 +132,7 @@ def test_pressure_step_stencils_bit_exact_and_divergence_free(cbc, nh_u):
 def test_device_resident_step_and_linearity():
     """Size-independent properties on a larger grid: linearity of the solve and discrete residual."""
     import torch
-    case = Case((256, 128, 64), ("PP", "PP", "NN"), (6.0, 3.0, 1.0), gr=1.0, seed=5)
+    case = Case((256, 128, 64), ("PP", "PP", "NN"), (6.0, 3.0, 1.0), gr=0.0, seed=5)
     s = case.setup
     n = case.ng
     rng = np.random.default_rng(1)
@@ -151,7 +151,7 @@ def test_device_resident_step_and_linearity():
         sols.append(api.host_field(pd, p.shape))
     comb = 2.0 * sols[0] - 3.0 * sols[1]
     assert gauge_rel_err(sols[2][1:-1, 1:-1, 1:-1], comb[1:-1, 1:-1, 1:-1], True) <= 1e-11
-    # weights of the z-stretched operator are not uniform, so compare the residual, not the mean
+    # uniform grid: a zero-mean RHS is compatible, so the discrete residual must vanish
     p = case.boundp(sols[0])
     res = np.max(np.abs(case.laplacian(p) - r1)) / np.max(np.abs(r1))
     assert res <= 1e-10, res
