@@ -1,11 +1,289 @@
-// thomas_tile.cuh -- on-chip z solve (placeholder until the tiled kernel lands): reports "not done"
-// so the caller uses the generic scratch-field kernels.
+// thomas_tile.cuh -- z-direction tridiagonal solve with the whole column on chip (16 B/pt of HBM traffic).
+//
+// Replaces gaussel / gaussel_periodic (src/solver_cpu.f90:117-185) and the reference GPU versions that
+// spill 2-4 scratch fields to memory (src/solver_gpu.f90:475-638).
+//
+// A block stages TI consecutive (i,j) columns x nz levels in shared memory as [k][lane] and solves
+// them with a two-level (partition / Schur-complement) method so that nz/L threads work on one column:
+//
+//   thread (lane, s) owns levels [sL, (s+1)L); the last one is the separator X_s, the L-1 before it
+//   are interior.
+//   1. local sweeps over the interior block T_s (one UL sweep upward, one LU sweep downward, scalar
+//      carries only; the LU pivots z_l stay in registers):
+//         x_first = RU - QU X_{s-1} - GU X_s          x_last = RD - FD X_{s-1} - DD X_s
+//   2. reduced (cyclic) tridiagonal system in the S separators, solved by parallel cyclic reduction
+//      in shared memory (all TI*S threads, log2 S steps) -- this is the PCR variant the north star asks
+//      for periodic z; non-periodic z is the same code with the wrap-around couplings set to zero.
+//   3. local forward/backward substitution with the now-known X_{s-1}, X_s (re-using z_l).
+//
+// Different elimination order from dgtsv_homebrewed, same (diagonally dominant) systems: results agree
+// to round-off (tests: <= 1e-13 relative per column).  The singular (kx,ky)=(0,0) column of an
+// all-Neumann/periodic problem is pinned to x(nz)=0 -- see thomas_generic_kernel in kernels.cuh.
+//
+// Host-compilable (tests/emulate) like tile_fft.cuh.
 #pragma once
-#include <cuda_runtime.h>
+#include "tile_fft.cuh"
+
 namespace fb {
-inline int thomas_tile_run(long, int, const double*, const double*, const double*, const double*, double*, bool, int,
-                           cudaStream_t, bool* done) {
+
+// coefficient arrays az, bz, cz: a,b,c of initsolver with az[0] = 0 and cz[nz-1] = 0 unless z is periodic
+struct ThomasArgs {
+  int nz, S;              // S = nz / L segments
+  int periodic, singular;
+  const double* az;
+  const double* bz;
+  const double* cz;
+};
+
+template <int L, int TI>
+struct ThomasTile {
+  static FB_HD int prow(int k) { return k + k / L; }                   // one pad row per segment (bank parity)
+  static FB_HD int tile_rows(int nz) { return nz + nz / L; }
+  static FB_HD size_t smem_doubles(int nz) { return (size_t)tile_rows(nz) * TI + 8 * (size_t)(nz / L) * TI; }
+
+  // ---- phase 1: local sweeps; writes (RU,QU,GU) and (RD,FD,DD) of this thread to ex[6][S][TI]
+  static FB_HD void local_sweeps(const double* tile, double* ex, const ThomasArgs& T, double lam, int lane, int s,
+                                 double* z) {
+    const int S = T.S, k0 = s * L;
+    // upward (UL) sweep over interior rows L-2 .. 0
+    double q = 0.0, g = 1.0, ru = 0.0;                                   // relation of the separator itself
+    // downward (LU) sweep over interior rows 0 .. L-2
+    double d = 0.0, f = 0.0, rd = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = 0; l < L - 1; ++l) {
+      {                                                                  // up: row lu = L-2-l
+        const int k = k0 + (L - 2 - l);
+        const double ak = T.az[k], ck = T.cz[k], bk = T.bz[k] + lam;
+        const double zz = 1.0 / (bk - ck * q);
+        ru = (tile[prow(k) * TI + lane] - ck * ru) * zz;
+        g = -ck * g * zz;
+        q = ak * zz;
+      }
+      {                                                                  // down: row l
+        const int k = k0 + l;
+        const double ak = T.az[k], ck = T.cz[k], bk = T.bz[k] + lam;
+        const double zz = 1.0 / (bk - ak * d);
+        rd = (tile[prow(k) * TI + lane] - ak * rd) * zz;
+        f = (l == 0) ? ak * zz : -ak * f * zz;
+        d = ck * zz;
+        z[l] = zz;
+      }
+    }
+    const int o = s * TI + lane, st = S * TI;
+    ex[o] = ru; ex[st + o] = q; ex[2 * st + o] = g;
+    ex[3 * st + o] = rd; ex[4 * st + o] = f; ex[5 * st + o] = d;
+  }
+
+  // ---- phase 2a: reduced row of separator s from own (RD,FD,DD) and the next segment's (RU,QU,GU)
+  static FB_HD void reduced_row(const double* tile, const double* ex, double* red, const ThomasArgs& T, double lam,
+                                int lane, int s, bool pin) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    const int ks = s * L + L - 1;
+    const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
+    const double ak = T.az[ks], ck = T.cz[ks], bk = T.bz[ks] + lam;     // ck = 0 on the last row unless periodic
+    double A, B, C, R;
+    if (L > 1) {
+      const double ru = ex[on], qu = ex[st + on], gu = ex[2 * st + on];
+      const double rd = ex[3 * st + o], fd = ex[4 * st + o], dd = ex[5 * st + o];
+      A = -ak * fd;
+      B = bk - ak * dd - ck * qu;
+      C = -ck * gu;
+      R = tile[prow(ks) * TI + lane] - ak * rd - ck * ru;
+    } else {
+      A = ak; B = bk; C = ck; R = tile[prow(ks) * TI + lane];
+    }
+    if (pin && s == S - 1) { A = 0.0; B = 1.0; C = 0.0; R = 0.0; }       // gauge: x(nz) = 0
+    red[o] = A; red[st + o] = B; red[2 * st + o] = C; red[3 * st + o] = R;
+  }
+
+  // ---- phase 2b: one PCR step with stride h, src -> dst (each 4 arrays [S][TI])
+  static FB_HD void pcr_step(const double* src, double* dst, const ThomasArgs& T, int lane, int s, int h) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    int sm = s - h, sp = s + h;
+    bool hm = true, hp = true;
+    if (T.periodic) { sm = (sm % S + S) % S; sp = sp % S; }
+    else { hm = (sm >= 0); hp = (sp < S); }
+    const double A = src[o], B = src[st + o], C = src[2 * st + o], R = src[3 * st + o];
+    double Am = 0.0, Bm = 1.0, Cm = 0.0, Rm = 0.0, Ap = 0.0, Bp = 1.0, Cp = 0.0, Rp = 0.0;
+    if (hm) { const int q = sm * TI + lane; Am = src[q]; Bm = src[st + q]; Cm = src[2 * st + q]; Rm = src[3 * st + q]; }
+    if (hp) { const int q = sp * TI + lane; Ap = src[q]; Bp = src[st + q]; Cp = src[2 * st + q]; Rp = src[3 * st + q]; }
+    const double al = -A / Bm, ga = -C / Bp;
+    dst[o] = al * Am;
+    dst[st + o] = B + al * Cm + ga * Ap;
+    dst[2 * st + o] = ga * Cp;
+    dst[3 * st + o] = R + al * Rm + ga * Rp;
+  }
+
+  // ---- phase 2c: after the PCR steps every row is decoupled (non-periodic) or coupled only to row
+  // s + S/2 (periodic, S a power of two): write X_s
+  static FB_HD void pcr_finish(const double* src, double* X, const ThomasArgs& T, int lane, int s) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    const double B = src[st + o], R = src[3 * st + o];
+    if (T.periodic && S >= 2) {
+      const int t = (s + S / 2) % S, q = t * TI + lane;
+      const double K = src[o] + src[2 * st + o], Kt = src[q] + src[2 * st + q];
+      const double Bt = src[st + q], Rt = src[3 * st + q];
+      X[o] = (R * Bt - K * Rt) / (B * Bt - K * Kt);
+    } else {
+      X[o] = R / B;
+    }
+  }
+
+  // ---- phase 3: substitution inside the segment with known separators
+  static FB_HD void substitute(double* tile, const double* X, const ThomasArgs& T, int lane, int s, const double* z) {
+    const int S = T.S, k0 = s * L;
+    const int spv = (s == 0) ? S - 1 : s - 1;
+    const double xs = X[s * TI + lane];
+    const double xp = X[spv * TI + lane];                                // multiplied by az[k0] (= 0 at k0 = 0 if not periodic)
+    tile[prow(k0 + L - 1) * TI + lane] = xs;
+    if (L == 1) return;
+    double pp = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = 0; l < L - 1; ++l) {
+      const int k = k0 + l;
+      double r = tile[prow(k) * TI + lane];
+      if (l == 0) r -= T.az[k] * xp; else r -= T.az[k] * pp;
+      if (l == L - 2) r -= T.cz[k] * xs;
+      pp = r * z[l];
+      tile[prow(k) * TI + lane] = pp;
+    }
+    double x = pp;                                                       // x_{L-2} = p'_{L-2}
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = L - 3; l >= 0; --l) {
+      const int k = k0 + l;
+      x = tile[prow(k) * TI + lane] - T.cz[k] * z[l] * x;
+      tile[prow(k) * TI + lane] = x;
+    }
+  }
+};
+
+}  // namespace fb
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+
+namespace fb {
+
+template <int L, int TI>
+__global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasArgs T, const double* __restrict__ lam,
+                                                              double* __restrict__ W) {
+  using TT = ThomasTile<L, TI>;
+  extern __shared__ double smem[];
+  const int nz = T.nz, S = T.S;
+  double* tile = smem;
+  double* exa = smem + (size_t)TT::tile_rows(nz) * TI;     // 4*S*TI
+  double* exb = exa + 4 * (size_t)S * TI;                   // 4*S*TI  (exa..exb+.. also hold the 6 local-sweep arrays)
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid % TI, s = tid / TI;
+  const long col0 = (long)blockIdx.x * TI;
+  const bool live = (col0 + lane) < ncol;
+  double* base = W + col0 + lane;
+
+  for (int k = s; k < nz; k += S) tile[TT::prow(k) * TI + lane] = live ? base[(long)k * ncol] : 0.0;
+  const double l = live ? lam[col0 + lane] : -1.0;
+  const bool pin = T.singular && live && (l == 0.0);
+  __syncthreads();
+
+  double z[L > 1 ? L - 1 : 1];
+  if (L > 1) TT::local_sweeps(tile, exa, T, l, lane, s, z);
+  __syncthreads();
+  // reduced rows go to a private register set first: `exa` still holds the sweep results others read
+  double* red = exb + 2 * (size_t)S * TI;                   // 4 arrays fit behind the 6 sweep arrays? no: use registers
+  (void)red;
+  double rA, rB, rC, rR;
+  {
+    // same arithmetic as ThomasTile::reduced_row, kept in registers until every thread has read `exa`
+    const int st = S * TI, o = s * TI + lane;
+    const int ks = s * L + L - 1;
+    const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
+    const double ak = T.az[ks], ck = T.cz[ks], bk = T.bz[ks] + l;
+    if (L > 1) {
+      const double ru = exa[on], qu = exa[st + on], gu = exa[2 * st + on];
+      const double rd = exa[3 * st + o], fd = exa[4 * st + o], dd = exa[5 * st + o];
+      rA = -ak * fd; rB = bk - ak * dd - ck * qu; rC = -ck * gu;
+      rR = tile[TT::prow(ks) * TI + lane] - ak * rd - ck * ru;
+    } else {
+      rA = ak; rB = bk; rC = ck; rR = tile[TT::prow(ks) * TI + lane];
+    }
+    if (pin && s == S - 1) { rA = 0.0; rB = 1.0; rC = 0.0; rR = 0.0; }
+  }
+  __syncthreads();
+  {
+    const int st = S * TI, o = s * TI + lane;
+    exa[o] = rA; exa[st + o] = rB; exa[2 * st + o] = rC; exa[3 * st + o] = rR;
+  }
+  __syncthreads();
+  double* src = exa;
+  double* dst = exb;
+  const int hmax = T.periodic ? S / 2 : S;
+  for (int h = 1; h < hmax; h *= 2) {
+    TT::pcr_step(src, dst, T, lane, s, h);
+    __syncthreads();
+    double* t = src; src = dst; dst = t;
+  }
+  TT::pcr_finish(src, dst, T, lane, s);                     // X in dst[0 .. S*TI)
+  __syncthreads();
+  TT::substitute(tile, dst, T, lane, s, z);
+  __syncthreads();
+  if (live)
+    for (int k = s; k < nz; k += S) base[(long)k * ncol] = tile[TT::prow(k) * TI + lane];
+  (void)nthr;
+}
+
+template <int L, int TI>
+inline cudaError_t thomas_tile_launch(long ncol, const ThomasArgs& T, const double* lam, double* W, cudaStream_t st) {
+  using TT = ThomasTile<L, TI>;
+  auto kern = thomas_tile_kernel<L, TI>;
+  const size_t smem = TT::smem_doubles(T.nz) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long nblk = (ncol + TI - 1) / TI;
+  kern<<<(unsigned)nblk, TI * T.S, smem, st>>>(ncol, T, lam, W);
+  return cudaGetLastError();
+}
+
+// Picks a segment length; *done = false if this nz is not served (caller falls back to the generic kernels).
+inline bool thomas_tile_pick(int nz, bool periodic, int* Lout) {
+  const int cand[5] = {16, 8, 32, 4, 2};
+  for (int q = 0; q < 5; ++q) {
+    const int L = cand[q];
+    if (nz % L) continue;
+    const int S = nz / L;
+    if (S < 2 || S > 64) continue;
+    if (periodic && (S & (S - 1))) continue;              // cyclic PCR needs a power-of-two number of separators
+    const size_t smem = ((size_t)(nz + S) * 8 + 8 * (size_t)S * 8) * sizeof(double);
+    if (smem > 200 * 1024) continue;
+    *Lout = L;
+    return true;
+  }
+  return false;
+}
+
+inline int thomas_tile_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam,
+                           double* W, bool periodic, int singular, cudaStream_t st, bool* done) {
   *done = false;
+  int L = 0;
+  if (!thomas_tile_pick(nz, periodic, &L)) return 0;
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
+  cudaError_t e = cudaSuccess;
+  switch (L) {
+    case 2: e = thomas_tile_launch<2, 8>(ncol, T, lam, W, st); break;
+    case 4: e = thomas_tile_launch<4, 8>(ncol, T, lam, W, st); break;
+    case 8: e = thomas_tile_launch<8, 8>(ncol, T, lam, W, st); break;
+    case 16: e = thomas_tile_launch<16, 8>(ncol, T, lam, W, st); break;
+    default: e = thomas_tile_launch<32, 8>(ncol, T, lam, W, st); break;
+  }
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
   return 0;
 }
+
 }  // namespace fb
+#endif
