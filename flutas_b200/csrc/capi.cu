@@ -131,9 +131,9 @@ struct DevLinePlan {
     const size_t kb = 1024;
     if ((size_t)h.N * 16 * 8 <= 64 * kb) tb = 16;
     else if ((size_t)h.N * 8 * 8 <= 128 * kb) tb = 8;
-    else if ((size_t)h.N * 4 * 8 <= 224 * kb) tb = 4;
+    else if (fft_smem_bytes<4>(h.N) <= 220 * kb) tb = 4;
     else return fail(FLUTAS_B200_ERR_UNSUPPORTED, "transform length %d does not fit a shared-memory tile", h.N);
-    smem = (size_t)h.N * tb * sizeof(double);
+    smem = (tb == 16) ? fft_smem_bytes<16>(h.N) : (tb == 8) ? fft_smem_bytes<8>(h.N) : fft_smem_bytes<4>(h.N);
     return 0;
   }
 };
@@ -149,6 +149,7 @@ struct SolverPlan {
   // cached coefficients
   DevBuf lam_int, abc, maps, lam_raw;
   int cached_nz = 0;
+  bool cached_periodic = false;
   const double* key_lam = nullptr;
   std::vector<double> key_a, key_b, key_c;
   double key_lam_samples[3] = {0, 0, 0};
@@ -204,10 +205,11 @@ int run_y(const DevLinePlan& lp, double* W, int n1, long n3) {
   }
 }
 
-int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const double* a, const double* b, const double* c) {
+int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const double* a, const double* b, const double* c,
+                       bool periodic) {
   const int n1 = sp->n1, n2 = sp->n2;
   const bool lam_dev = on_device(lambdaxy), abc_dev = on_device(a);
-  bool same = sp->cache_valid && sp->cached_nz == nz && sp->key_lam == lambdaxy;
+  bool same = sp->cache_valid && sp->cached_nz == nz && sp->key_lam == lambdaxy && sp->cached_periodic == periodic;
   if (same && !abc_dev) {
     same = (int)sp->key_a.size() == nz && !memcmp(sp->key_a.data(), a, sizeof(double) * nz) &&
            !memcmp(sp->key_b.data(), b, sizeof(double) * nz) && !memcmp(sp->key_c.data(), c, sizeof(double) * nz);
@@ -222,13 +224,19 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
   const size_t nl = (size_t)n1 * n2;
   if (int rc = sp->lam_raw.reserve(nl * sizeof(double))) return rc;
   if (int rc = sp->lam_int.reserve(nl * sizeof(double))) return rc;
-  if (int rc = sp->abc.reserve(3 * (size_t)nz * sizeof(double))) return rc;
+  if (int rc = sp->abc.reserve(6 * (size_t)nz * sizeof(double))) return rc;
   if (int rc = sp->maps.reserve((size_t)(n1 + n2) * sizeof(int))) return rc;
   CK(cudaMemcpyAsync(sp->lam_raw.p, lambdaxy, nl * sizeof(double), cudaMemcpyDefault, g_stream));
   double* abc = sp->abc.as<double>();
   CK(cudaMemcpyAsync(abc, a, nz * sizeof(double), cudaMemcpyDefault, g_stream));
   CK(cudaMemcpyAsync(abc + nz, b, nz * sizeof(double), cudaMemcpyDefault, g_stream));
   CK(cudaMemcpyAsync(abc + 2 * nz, c, nz * sizeof(double), cudaMemcpyDefault, g_stream));
+  // second copy for the on-chip z solve: couplings that leave the system are zero unless z is periodic
+  CK(cudaMemcpyAsync(abc + 3 * nz, abc, 3 * (size_t)nz * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  if (!periodic) {
+    CK(cudaMemsetAsync(abc + 3 * nz, 0, sizeof(double), g_stream));                  // az[0]
+    CK(cudaMemsetAsync(abc + 5 * nz + (nz - 1), 0, sizeof(double), g_stream));       // cz[nz-1]
+  }
   int* maps = sp->maps.as<int>();
   CK(cudaMemcpyAsync(maps, sp->px.h.mode.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(maps + n1, sp->py.h.mode.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
@@ -237,6 +245,7 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
   LAUNCHED();
   CK(cudaStreamSynchronize(g_stream));
   sp->cached_nz = nz;
+  sp->cached_periodic = periodic;
   sp->key_lam = lambdaxy;
   if (!abc_dev) { sp->key_a.assign(a, a + nz); sp->key_b.assign(b, b + nz); sp->key_c.assign(c, c + nz); }
   else { sp->key_a.clear(); sp->key_b.clear(); sp->key_c.clear(); }
@@ -419,7 +428,7 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
   const bool xysing = (sp->bcxy[0] != 'D' && sp->bcxy[2] != 'D');   // PP or NN in both x and y
   const int singular = (zsing && xysing) ? 1 : 0;
 
-  if (int rc = cache_coefficients(sp, n3, lambdaxy, a, b, c)) return rc;
+  if (int rc = cache_coefficients(sp, n3, lambdaxy, a, b, c, periodic)) return rc;
   const size_t npts = (size_t)n1 * n2 * n3;
   if (int rc = sp->work.reserve(npts * sizeof(double))) return rc;
   double* W = sp->work.as<double>();
@@ -446,7 +455,7 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
     const long ncol = (long)n1 * n2;
     bool done = false;
     if (sp->thomas_mode == 0) {
-      int rc = thomas_tile_run(ncol, n3, abc, abc + n3, abc + 2 * n3, lam, W, periodic, singular, g_stream, &done);
+      int rc = thomas_tile_run(ncol, n3, abc + 3 * n3, abc + 4 * n3, abc + 5 * n3, lam, W, periodic, singular, g_stream, &done);
       if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_tile launch failed: %s", cudaGetErrorString((cudaError_t)rc));
       if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
     }

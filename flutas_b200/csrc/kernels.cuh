@@ -26,108 +26,150 @@ __device__ __forceinline__ long line_offset(const LineGeom& g, long line) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// shared-memory layout of the transform kernels: [tile: N*TB doubles][wM: M cpx][line offsets: TB longs]
+// The pass twiddles wM are staged in shared memory (they are read 7x per radix-8 butterfly and global
+// loads of them were the top stall in the first profile); wN/wQ/pos stay in global memory (L1/L2 hits).
+template <int TB>
+__host__ __device__ inline size_t fft_smem_bytes(int N) {
+  return (size_t)N * TB * sizeof(double) + (size_t)(N / 2) * sizeof(cpx) + TB * sizeof(long);
+}
+
+__device__ __forceinline__ void stage_twiddles(cpx* s_w, const cpx* __restrict__ g_w, int M, int tid, int nthr) {
+  const double2* g = reinterpret_cast<const double2*>(g_w);
+  double2* d = reinterpret_cast<double2*>(s_w);
+  for (int q = tid; q < M; q += nthr) d[q] = __ldg(g + q);
+}
+
+template <int TB, bool ROT, bool FWD>
+__device__ __forceinline__ void tile_transform(double* tile, const LinePlan& P, const cpx* wM, int lane, int worker,
+                                               int nworkers) {
+  if (FWD) {
+    for (int q = 0; q < P.npass; ++q) {
+      fft_pass<TB, ROT, true>(tile, P, wM, q, lane, worker, nworkers);
+      __syncthreads();
+    }
+    split_fwd<TB, ROT>(tile, P, lane, worker, nworkers);
+  } else {
+    merge_bwd<TB, ROT>(tile, P, lane, worker, nworkers);
+    for (int q = P.npass - 1; q >= 0; --q) {
+      __syncthreads();
+      fft_pass<TB, ROT, false>(tile, P, wM, q, lane, worker, nworkers);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // x direction.  One block = TB consecutive lines.  FWD: physical -> spectral rows, BWD: the reverse
 // (times `scale`, = normfft on the last stage, solver_cpu.f90:93).
+// Load/store: a warp handles 32 consecutive elements e of every line; the slot of e is computed once
+// and reused for the TB lines, whose TB loads are all in flight together.
 template <int TB, bool FWD>
-__global__ void __launch_bounds__(256) xfft_kernel(LinePlan P, const double* __restrict__ src, LineGeom gs,
+__global__ void __launch_bounds__(256, 3) xfft_kernel(LinePlan P, const double* __restrict__ src, LineGeom gs,
                                                    double* __restrict__ dst, LineGeom gd, double scale) {
   extern __shared__ double tile[];
   const int N = P.N, M = P.M, kind = P.kind;
+  cpx* s_w = reinterpret_cast<cpx*>(tile + (size_t)N * TB);
+  long* s_off = reinterpret_cast<long*>(s_w + M);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const long line0 = (long)blockIdx.x * TB;
+  const int nlive = (int)min((long)TB, gs.nlines - line0);
 
-  for (int L = 0; L < TB; ++L) {
-    const long line = line0 + L;
-    const bool live = line < gs.nlines;
-    const double* s = src + (live ? line_offset(gs, line) : 0);
-    for (int e = tid; e < N; e += nthr) {
-      int m, part;
-      double sgn = 1.0;
-      if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
-      else { part = (e >= M); m = e - part * M; }
-      const double v = live ? __ldg(s + e) : 0.0;
-      tile[taddr<TB, true>(m, part, M, L)] = sgn * v;
-    }
+  if (tid < TB) s_off[tid] = line_offset(gs, min(line0 + tid, gs.nlines - 1));
+  stage_twiddles(s_w, P.wM, M, tid, nthr);
+  __syncthreads();
+
+  for (int e = tid; e < N; e += nthr) {
+    int m, part;
+    double sgn = 1.0;
+    if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
+    else { part = (e >= M); m = e - part * M; }
+    double v[TB];
+#pragma unroll
+    for (int L = 0; L < TB; ++L) v[L] = __ldcs(src + s_off[L] + e);
+#pragma unroll
+    for (int L = 0; L < TB; ++L) tile[taddr<TB, true>(m, part, M, L)] = (L < nlive) ? sgn * v[L] : 0.0;
   }
   __syncthreads();
 
   const int lane = tid & (TB - 1), worker = tid / TB, nworkers = nthr / TB;
-  if (FWD) {
-    for (int q = 0; q < P.npass; ++q) {
-      fft_pass<TB, true, true>(tile, P, q, lane, worker, nworkers);
-      __syncthreads();
-    }
-    split_fwd<TB, true>(tile, P, lane, worker, nworkers);
-  } else {
-    merge_bwd<TB, true>(tile, P, lane, worker, nworkers);
-    for (int q = P.npass - 1; q >= 0; --q) {
-      __syncthreads();
-      fft_pass<TB, true, false>(tile, P, q, lane, worker, nworkers);
-    }
-  }
-  __syncthreads();
+  tile_transform<TB, true, FWD>(tile, P, s_w, lane, worker, nworkers);
 
-  for (int L = 0; L < TB; ++L) {
-    const long line = line0 + L;
-    if (line >= gd.nlines) break;
-    double* d = dst + line_offset(gd, line);
-    for (int e = tid; e < N; e += nthr) {
-      int m, part;
-      double sgn = 1.0;
-      if (!FWD) elem_to_slot(kind, N, e, m, part, sgn);
-      else { part = (e >= M); m = e - part * M; }
-      d[e] = sgn * scale * tile[taddr<TB, true>(m, part, M, L)];
-    }
+  if (tid < TB) s_off[tid] = line_offset(gd, min(line0 + tid, gd.nlines - 1));
+  __syncthreads();
+  for (int e = tid; e < N; e += nthr) {
+    int m, part;
+    double sgn = 1.0;
+    if (!FWD) elem_to_slot(kind, N, e, m, part, sgn);
+    else { part = (e >= M); m = e - part * M; }
+    const double f = sgn * scale;
+    double v[TB];
+#pragma unroll
+    for (int L = 0; L < TB; ++L) v[L] = tile[taddr<TB, true>(m, part, M, L)];
+#pragma unroll
+    for (int L = 0; L < TB; ++L)
+      if (L < nlive) __stcs(dst + s_off[L] + e, f * v[L]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // y direction, in place on the dense work array W(n1, N, n3).  One block = lanes i0..i0+TB-1 of one
-// k plane, all N rows.  Global accesses are TB*8 contiguous bytes per row.
+// k plane, all N rows.  Global accesses are TB*8 contiguous bytes per row, YU rows in flight per thread.
 template <int TB, bool FWD>
-__global__ void __launch_bounds__(256) yfft_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
+__global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
+  constexpr int YU = 8;
   extern __shared__ double tile[];
   const int N = P.N, M = P.M, kind = P.kind;
+  cpx* s_w = reinterpret_cast<cpx*>(tile + (size_t)N * TB);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int ti = blockIdx.x % ntile_i;
   const long k = blockIdx.x / ntile_i;
   const int i0 = ti * TB;
   const int lane = tid & (TB - 1), worker = tid / TB, nworkers = nthr / TB;
   const bool live = (i0 + lane) < n1;
-  double* base = W + (long)n1 * N * k + i0 + lane;
+  double* base = W + (long)n1 * N * k + i0 + (live ? lane : 0);
 
-  for (int e = worker; e < N; e += nworkers) {
-    int m, part;
-    double sgn = 1.0;
-    if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
-    else { part = (e >= M); m = e - part * M; }
-    const double v = live ? base[(long)e * n1] : 0.0;
-    tile[taddr<TB, false>(m, part, M, lane)] = sgn * v;
-  }
-  __syncthreads();
-
-  if (FWD) {
-    for (int q = 0; q < P.npass; ++q) {
-      fft_pass<TB, false, true>(tile, P, q, lane, worker, nworkers);
-      __syncthreads();
+  stage_twiddles(s_w, P.wM, M, tid, nthr);
+  for (int e0 = worker; e0 < N; e0 += YU * nworkers) {
+    double v[YU];
+#pragma unroll
+    for (int u = 0; u < YU; ++u) {
+      const int e = e0 + u * nworkers;
+      v[u] = (e < N) ? __ldcs(base + (long)e * n1) : 0.0;
     }
-    split_fwd<TB, false>(tile, P, lane, worker, nworkers);
-  } else {
-    merge_bwd<TB, false>(tile, P, lane, worker, nworkers);
-    for (int q = P.npass - 1; q >= 0; --q) {
-      __syncthreads();
-      fft_pass<TB, false, false>(tile, P, q, lane, worker, nworkers);
+#pragma unroll
+    for (int u = 0; u < YU; ++u) {
+      const int e = e0 + u * nworkers;
+      if (e < N) {
+        int m, part;
+        double sgn = 1.0;
+        if (FWD) elem_to_slot(kind, N, e, m, part, sgn);
+        else { part = (e >= M); m = e - part * M; }
+        tile[taddr<TB, false>(m, part, M, lane)] = live ? sgn * v[u] : 0.0;
+      }
     }
   }
   __syncthreads();
+
+  tile_transform<TB, false, FWD>(tile, P, s_w, lane, worker, nworkers);
 
   if (!live) return;
-  for (int e = worker; e < N; e += nworkers) {
-    int m, part;
-    double sgn = 1.0;
-    if (!FWD) elem_to_slot(kind, N, e, m, part, sgn);
-    else { part = (e >= M); m = e - part * M; }
-    base[(long)e * n1] = sgn * tile[taddr<TB, false>(m, part, M, lane)];
+  for (int e0 = worker; e0 < N; e0 += YU * nworkers) {
+    double v[YU];
+#pragma unroll
+    for (int u = 0; u < YU; ++u) {
+      const int e = e0 + u * nworkers;
+      int m, part;
+      double sgn = 1.0;
+      if (!FWD) elem_to_slot(kind, N, min(e, N - 1), m, part, sgn);
+      else { const int ee = min(e, N - 1); part = (ee >= M); m = ee - part * M; }
+      v[u] = sgn * tile[taddr<TB, false>(m, part, M, lane)];
+    }
+#pragma unroll
+    for (int u = 0; u < YU; ++u) {
+      const int e = e0 + u * nworkers;
+      if (e < N) __stcs(base + (long)e * n1, v[u]);
+    }
   }
 }
 

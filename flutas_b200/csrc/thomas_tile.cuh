@@ -46,7 +46,7 @@ struct ThomasTile {
                                  double* z) {
     const int S = T.S, k0 = s * L;
     // upward (UL) sweep over interior rows L-2 .. 0
-    double q = 0.0, g = 1.0, ru = 0.0;                                   // relation of the separator itself
+    double q = 0.0, g = -1.0, ru = 0.0;                                  // x = ru - q x_below - g X_s holds for the separator itself
     // downward (LU) sweep over interior rows 0 .. L-2
     double d = 0.0, f = 0.0, rd = 0.0;
 #if defined(__CUDACC__)

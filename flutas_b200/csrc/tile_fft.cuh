@@ -157,7 +157,7 @@ template <int R, int SIGN> FB_HD void bfly(double* re, double* im) {
 // one radix-R pass over the tile.  FWD: DIF (butterfly, then twiddle).  !FWD: DIT (conj twiddle, then
 // inverse butterfly) -- exactly undoes the FWD pass up to the factor R.
 template <int TB, bool ROT, int R, bool FWD>
-FB_HD void pass_R(double* tile, const LinePlan& P, int q, int lane, int worker, int nworkers) {
+FB_HD void pass_R(double* tile, const LinePlan& P, const cpx* wM, int q, int lane, int worker, int nworkers) {
   const int M = P.M, s = P.sub[q], Lc = s * R;
   const int tstep = M / Lc;
   const int nb = M / R;
@@ -179,7 +179,7 @@ FB_HD void pass_R(double* tile, const LinePlan& P, int q, int lane, int worker, 
 #pragma unroll
 #endif
       for (int t = 1; t < R; ++t) {
-        const cpx w = P.wM[n * t * tstep];
+        const cpx w = wM[n * t * tstep];
         const double xr = re[t] * w.x - im[t] * w.y, xi = re[t] * w.y + im[t] * w.x;
         re[t] = xr; im[t] = xi;
       }
@@ -188,7 +188,7 @@ FB_HD void pass_R(double* tile, const LinePlan& P, int q, int lane, int worker, 
 #pragma unroll
 #endif
       for (int t = 1; t < R; ++t) {
-        const cpx w = P.wM[n * t * tstep];          // multiply by conj(w)
+        const cpx w = wM[n * t * tstep];            // multiply by conj(w)
         const double xr = re[t] * w.x + im[t] * w.y, xi = im[t] * w.x - re[t] * w.y;
         re[t] = xr; im[t] = xi;
       }
@@ -206,13 +206,13 @@ FB_HD void pass_R(double* tile, const LinePlan& P, int q, int lane, int worker, 
 }
 
 template <int TB, bool ROT, bool FWD>
-FB_HD void fft_pass(double* tile, const LinePlan& P, int q, int lane, int worker, int nworkers) {
+FB_HD void fft_pass(double* tile, const LinePlan& P, const cpx* wM, int q, int lane, int worker, int nworkers) {
   switch (P.radix[q]) {
-    case 2: pass_R<TB, ROT, 2, FWD>(tile, P, q, lane, worker, nworkers); break;
-    case 3: pass_R<TB, ROT, 3, FWD>(tile, P, q, lane, worker, nworkers); break;
-    case 4: pass_R<TB, ROT, 4, FWD>(tile, P, q, lane, worker, nworkers); break;
-    case 5: pass_R<TB, ROT, 5, FWD>(tile, P, q, lane, worker, nworkers); break;
-    default: pass_R<TB, ROT, 8, FWD>(tile, P, q, lane, worker, nworkers); break;
+    case 2: pass_R<TB, ROT, 2, FWD>(tile, P, wM, q, lane, worker, nworkers); break;
+    case 3: pass_R<TB, ROT, 3, FWD>(tile, P, wM, q, lane, worker, nworkers); break;
+    case 4: pass_R<TB, ROT, 4, FWD>(tile, P, wM, q, lane, worker, nworkers); break;
+    case 5: pass_R<TB, ROT, 5, FWD>(tile, P, wM, q, lane, worker, nworkers); break;
+    default: pass_R<TB, ROT, 8, FWD>(tile, P, wM, q, lane, worker, nworkers); break;
   }
 }
 

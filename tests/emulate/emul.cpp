@@ -33,12 +33,12 @@ static void run(const HostLinePlan& hp, int nworkers, int fwd, const double* in,
   };
   if (fwd) {
     for (int q = 0; q < P.npass; ++q)
-      phase([&](int lane, int w) { fft_pass<TB, ROT, true>(tile.data(), P, q, lane, w, nworkers); });
+      phase([&](int lane, int w) { fft_pass<TB, ROT, true>(tile.data(), P, P.wM, q, lane, w, nworkers); });
     phase([&](int lane, int w) { split_fwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
   } else {
     phase([&](int lane, int w) { merge_bwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
     for (int q = P.npass - 1; q >= 0; --q)
-      phase([&](int lane, int w) { fft_pass<TB, ROT, false>(tile.data(), P, q, lane, w, nworkers); });
+      phase([&](int lane, int w) { fft_pass<TB, ROT, false>(tile.data(), P, P.wM, q, lane, w, nworkers); });
   }
   // store phase
   for (int L = 0; L < TB; ++L)
@@ -65,5 +65,69 @@ extern "C" int emul_mode_index(int N, int kind, int* mode) {
   HostLinePlan hp = make_line_plan(N, kind);
   if (!hp.ok) return 1;
   std::memcpy(mode, hp.mode.data(), sizeof(int) * (size_t)N);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// on-chip Thomas (flutas_b200/csrc/thomas_tile.cuh): same phases as thomas_tile_kernel, serial over threads
+#include "../../flutas_b200/csrc/thomas_tile.cuh"
+
+template <int L, int TI>
+static void thomas_emul(long ncol, ThomasArgs T, const double* lam, double* W) {
+  using TT = ThomasTile<L, TI>;
+  const int nz = T.nz, S = T.S;
+  const long nblk = (ncol + TI - 1) / TI;
+  std::vector<double> smem(TT::smem_doubles(nz));
+  std::vector<double> zreg((size_t)S * TI * (L > 1 ? L - 1 : 1));
+  for (long blk = 0; blk < nblk; ++blk) {
+    double* tile = smem.data();
+    double* exa = tile + (size_t)TT::tile_rows(nz) * TI;
+    double* exb = exa + 4 * (size_t)S * TI;
+    const long col0 = blk * TI;
+    auto live = [&](int lane) { return col0 + lane < ncol; };
+    auto lamof = [&](int lane) { return live(lane) ? lam[col0 + lane] : -1.0; };
+    auto zof = [&](int lane, int s) { return zreg.data() + ((size_t)s * TI + lane) * (L > 1 ? L - 1 : 1); };
+    for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
+      for (int k = s; k < nz; k += S) tile[TT::prow(k) * TI + lane] = live(lane) ? W[col0 + lane + (long)k * ncol] : 0.0;
+    if (L > 1)
+      for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
+        TT::local_sweeps(tile, exa, T, lamof(lane), lane, s, zof(lane, s));
+    // reduced rows: computed by every thread from exa, then written over exa (kernel keeps them in registers)
+    std::vector<double> red(4 * (size_t)S * TI);
+    for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane) {
+      const bool pin = T.singular && live(lane) && lamof(lane) == 0.0;
+      TT::reduced_row(tile, exa, red.data(), T, lamof(lane), lane, s, pin);
+    }
+    std::memcpy(exa, red.data(), sizeof(double) * red.size());
+    double* src = exa; double* dst = exb;
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) {
+      for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane) TT::pcr_step(src, dst, T, lane, s, h);
+      double* t = src; src = dst; dst = t;
+    }
+    for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane) TT::pcr_finish(src, dst, T, lane, s);
+    for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane) TT::substitute(tile, dst, T, lane, s, zof(lane, s));
+    for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
+      if (live(lane)) for (int k = s; k < nz; k += S) W[col0 + lane + (long)k * ncol] = tile[TT::prow(k) * TI + lane];
+  }
+}
+
+extern "C" int emul_thomas_tile(int L, int nz, long ncol, int periodic, int singular, const double* a, const double* b,
+                                const double* c, const double* lam, double* W) {
+  if (nz % L) return 1;
+  std::vector<double> az(a, a + nz), cz(c, c + nz);
+  if (!periodic) { az[0] = 0.0; cz[nz - 1] = 0.0; }
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / L; T.periodic = periodic; T.singular = singular; T.az = az.data(); T.bz = b; T.cz = cz.data();
+  if (periodic && (T.S & (T.S - 1))) return 2;
+  switch (L) {
+    case 1: thomas_emul<1, 8>(ncol, T, lam, W); break;
+    case 2: thomas_emul<2, 8>(ncol, T, lam, W); break;
+    case 4: thomas_emul<4, 8>(ncol, T, lam, W); break;
+    case 8: thomas_emul<8, 8>(ncol, T, lam, W); break;
+    case 16: thomas_emul<16, 8>(ncol, T, lam, W); break;
+    case 32: thomas_emul<32, 8>(ncol, T, lam, W); break;
+    default: return 3;
+  }
   return 0;
 }

@@ -73,3 +73,56 @@ def test_unsupported_lengths_are_rejected(emul):
     out = np.zeros(14)
     assert emul.emul_line_transform(14, 0, 16, 0, 1, 1, out.ctypes.data_as(_dp), out.ctypes.data_as(_dp), 1.0) == 1
     assert emul.emul_line_transform(9, 0, 16, 0, 1, 1, out.ctypes.data_as(_dp), out.ctypes.data_as(_dp), 1.0) == 1
+
+
+# ---- on-chip Thomas (thomas_tile.cuh) -------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emul_t(emul):
+    emul.emul_thomas_tile.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    return emul
+
+
+@pytest.mark.parametrize("periodic", [0, 1])
+@pytest.mark.parametrize("nz,L", [(8, 2), (16, 4), (32, 8), (64, 8), (72, 8), (40, 8), (64, 16), (128, 16), (512, 16),
+                                  (256, 32), (1024, 32), (12, 2), (24, 4)])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched):
+    S = nz // L
+    if periodic and (S & (S - 1)):
+        pytest.skip("cyclic PCR needs a power-of-two number of separators (falls back to the generic kernel)")
+    if periodic and stretched:
+        pytest.skip("periodic z implies a uniform grid")
+    from flutas_b200 import initsolver
+    rng = np.random.default_rng(nz + L)
+    dzc, dzf = initsolver.initgrid(nz, 2.0 if stretched else 0.0, 1.0, 1)
+    bcz = "PP" if periodic else "NN"
+    a, b, c = initsolver.tridmatrix(bcz, nz, 1, 1.0 / dzc, 1.0 / dzf)
+    nx, ny = 7, 3                                        # 21 columns: exercises the ragged last tile
+    lam = -rng.uniform(0.0, 4.0 * nz * nz, (nx, ny))
+    lam[0, 0] = 0.0                                      # singular column
+    lam[1, 0] = -1.0e-3                                  # nearly singular column
+    rhs = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz)))
+    rhs[0, 0, :] -= (rhs[0, 0, :] * dzf[1:-1]).sum() / dzf[1:-1].sum()    # compatible RHS for the singular column
+    ref = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bool(periodic))
+    got = rhs.copy(order="F")
+    rc = emul_t.emul_thomas_tile(L, nz, nx * ny, periodic, 1, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
+                                 c.ctypes.data_as(_dp), np.asfortranarray(lam).ctypes.data_as(_dp),
+                                 got.ctypes.data_as(_dp))
+    assert rc == 0
+    for i in range(nx):
+        for j in range(ny):
+            g, r = got[i, j, :], ref[i, j, :]
+            if i == 0 and j == 0:
+                # pinned gauge x(nz) = 0.  The reference leaves this column's constant to round-off (and returns
+                # NaN when its closure denominator is exactly 0), so check the residual of the singular system.
+                assert g[-1] == 0.0
+                A = np.diag(b) + np.diag(a[1:], -1) + np.diag(c[:-1], 1)
+                if periodic:
+                    A[0, nz - 1] += a[0]
+                    A[nz - 1, 0] += c[nz - 1]
+                assert np.max(np.abs(A @ g - rhs[i, j, :])) <= 1e-11 * np.max(np.abs(a))
+                continue
+            else:
+                # forward error of any stable elimination order ~ cond * eps; cond ~ 4 max(a) / |lambda|
+                tol = max(2e-13, 4.0 * a.max() / abs(lam[i, j]) * 2e-15)
+            assert np.max(np.abs(g - r)) <= tol * max(np.max(np.abs(r)), 1e-300), (i, j, lam[i, j])
