@@ -5,10 +5,10 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SO = os.path.join(CSRC, "libflutas_b200.so")
-SOURCES = ["capi.cu"]
-HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh"]
+SOURCES = ["capi.cu", "fft_p2_x.cu", "fft_p2_y.cu"]
+HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -30,13 +30,22 @@ def is_stale():
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    env = dict(os.environ)
-    for cc in ("/usr/bin/g++",):
-        if os.path.exists(cc):
-            cmd[1:1] = ["-ccbin", cc]
-            break
-    subprocess.check_call(cmd, cwd=CSRC, env=env)
+    nvcc = [_nvcc()]
+    if os.path.exists("/usr/bin/g++"):
+        nvcc += ["-ccbin", "/usr/bin/g++"]
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        subprocess.check_call(nvcc + flags + ["-c", "-o", obj, src], cwd=CSRC)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call(nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs, cwd=CSRC)
     return SO
 
 

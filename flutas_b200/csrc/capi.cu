@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/flutas_b200.h"
+#include "fft_p2.h"
 #include "kernels.cuh"
 #include "line_plan.h"
 #include "thomas_tile.cuh"
@@ -179,8 +180,16 @@ int launch_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst,
   LAUNCHED();
   return 0;
 }
+bool g_force_generic_fft = false;   // test hook: bypass the power-of-two kernels
+
 template <bool FWD>
 int run_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale) {
+  if (!g_force_generic_fft && p2_tile_width(lp.d.N)) {
+    cudaError_t e = p2_run_x(FWD, lp.d, src, gs, dst, gd, scale, g_stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "xfft_p2 launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   switch (lp.tb) {
     case 16: return launch_x<16, FWD>(lp, src, gs, dst, gd, scale);
     case 8: return launch_x<8, FWD>(lp, src, gs, dst, gd, scale);
@@ -198,6 +207,12 @@ int launch_y(const DevLinePlan& lp, double* W, int n1, long n3) {
 }
 template <bool FWD>
 int run_y(const DevLinePlan& lp, double* W, int n1, long n3) {
+  if (!g_force_generic_fft && p2_tile_width(lp.d.N)) {
+    cudaError_t e = p2_run_y(FWD, lp.d, W, n1, n3, g_stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_p2 launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   switch (lp.tb) {
     case 16: return launch_y<16, FWD>(lp, W, n1, n3);
     case 8: return launch_y<8, FWD>(lp, W, n1, n3);
@@ -401,6 +416,12 @@ int flutas_b200_solver_invalidate(void* const arrplan[4]) {
   SolverPlan* sp = plan_of(arrplan);
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "not a flutas_b200 plan");
   sp->cache_valid = false;
+  return FLUTAS_B200_OK;
+}
+
+// test hook: 1 = always use the run-time-radix transform kernels (skip the power-of-two specialisations)
+int flutas_b200_debug_generic_fft(int on) {
+  g_force_generic_fft = (on != 0);
   return FLUTAS_B200_OK;
 }
 

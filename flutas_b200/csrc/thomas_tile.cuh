@@ -185,7 +185,18 @@ __global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasA
   const bool live = (col0 + lane) < ncol;
   double* base = W + col0 + lane;
 
-  for (int k = s; k < nz; k += S) tile[TT::prow(k) * TI + lane] = live ? base[(long)k * ncol] : 0.0;
+  {
+    // coalesced load, LU loads in flight per thread (a warp covers 32/TI rows of 8*TI contiguous bytes)
+    constexpr int LU = 8;
+    const double* src = W + col0 + (live ? lane : 0);
+    for (int k0 = s; k0 < nz; k0 += LU * S) {
+      double v[LU];
+#pragma unroll
+      for (int u = 0; u < LU; ++u) { const int k = k0 + u * S; v[u] = (k < nz) ? __ldcs(src + (long)k * ncol) : 0.0; }
+#pragma unroll
+      for (int u = 0; u < LU; ++u) { const int k = k0 + u * S; if (k < nz) tile[TT::prow(k) * TI + lane] = live ? v[u] : 0.0; }
+    }
+  }
   const double l = live ? lam[col0 + lane] : -1.0;
   const bool pin = T.singular && live && (l == 0.0);
   __syncthreads();
@@ -231,8 +242,16 @@ __global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasA
   __syncthreads();
   TT::substitute(tile, dst, T, lane, s, z);
   __syncthreads();
-  if (live)
-    for (int k = s; k < nz; k += S) base[(long)k * ncol] = tile[TT::prow(k) * TI + lane];
+  if (live) {
+    constexpr int LU = 8;
+    for (int k0 = s; k0 < nz; k0 += LU * S) {
+      double v[LU];
+#pragma unroll
+      for (int u = 0; u < LU; ++u) { const int k = min(k0 + u * S, nz - 1); v[u] = tile[TT::prow(k) * TI + lane]; }
+#pragma unroll
+      for (int u = 0; u < LU; ++u) { const int k = k0 + u * S; if (k < nz) __stcs(base + (long)k * ncol, v[u]); }
+    }
+  }
   (void)nthr;
 }
 

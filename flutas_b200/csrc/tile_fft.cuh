@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define FB_HD __host__ __device__ __forceinline__
+#define FB_CX __host__ __device__ constexpr
 #else
 #define FB_HD inline
+#define FB_CX constexpr
 #endif
 
 namespace fb {
@@ -154,11 +156,94 @@ template <int R, int SIGN> FB_HD void bfly(double* re, double* im) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// one radix-R pass over the tile.  FWD: DIF (butterfly, then twiddle).  !FWD: DIT (conj twiddle, then
-// inverse butterfly) -- exactly undoes the FWD pass up to the factor R.
-template <int TB, bool ROT, int R, bool FWD>
-FB_HD void pass_R(double* tile, const LinePlan& P, const cpx* wM, int q, int lane, int worker, int nworkers) {
-  const int M = P.M, s = P.sub[q], Lc = s * R;
+// accessors: where a pass / split step reads and writes complex element m (re, im).
+//   TileAcc  : the shared-memory tile.
+//   LineAcc  : a strided line in global memory (y lines: element e at base[e*stride]), with the
+//              physical <-> packed mapping (Makhoul permutation, DST sign) applied on the fly; used to
+//              fuse the first pass with the global load and the last pass with the global store.
+//   SpecAcc  : the spectral layout in global memory (row r at base[r*stride]), for the fused split/merge.
+template <int TB, bool ROT>
+struct TileAcc {
+  double* tile; int M, lane;
+  FB_HD void ld(int m, double& re, double& im) const {
+    re = tile[taddr<TB, ROT>(m, 0, M, lane)];
+    im = tile[taddr<TB, ROT>(m, 1, M, lane)];
+  }
+  FB_HD void st(int m, double re, double im) const {
+    tile[taddr<TB, ROT>(m, 0, M, lane)] = re;
+    tile[taddr<TB, ROT>(m, 1, M, lane)] = im;
+  }
+};
+
+// packed index v -> physical element e and sign (inverse of elem_to_slot)
+FB_HD void slot_to_elem(int kind, int N, int v, int& e, double& sgn) {
+  e = v;
+  sgn = 1.0;
+  if (kind != KIND_PP) {
+    e = (2 * v < N) ? 2 * v : 2 * (N - 1 - v) + 1;
+    if (kind == KIND_DD && (e & 1)) sgn = -1.0;
+  }
+}
+
+struct LineAcc {
+  double* base; long stride; int kind, N; bool live; double scale;
+  FB_HD void ld(int m, double& re, double& im) const {
+    int e0, e1; double s0, s1;
+    slot_to_elem(kind, N, 2 * m, e0, s0);
+    slot_to_elem(kind, N, 2 * m + 1, e1, s1);
+#if defined(__CUDA_ARCH__)
+    re = live ? s0 * __ldcs(base + (long)e0 * stride) : 0.0;
+    im = live ? s1 * __ldcs(base + (long)e1 * stride) : 0.0;
+#else
+    re = live ? s0 * base[(long)e0 * stride] : 0.0;
+    im = live ? s1 * base[(long)e1 * stride] : 0.0;
+#endif
+  }
+  FB_HD void st(int m, double re, double im) const {
+    if (!live) return;
+    int e0, e1; double s0, s1;
+    slot_to_elem(kind, N, 2 * m, e0, s0);
+    slot_to_elem(kind, N, 2 * m + 1, e1, s1);
+#if defined(__CUDA_ARCH__)
+    __stcs(base + (long)e0 * stride, s0 * scale * re);
+    __stcs(base + (long)e1 * stride, s1 * scale * im);
+#else
+    base[(long)e0 * stride] = s0 * scale * re;
+    base[(long)e1 * stride] = s1 * scale * im;
+#endif
+  }
+};
+
+struct SpecAcc {
+  double* base; long stride; int M; bool live;
+  FB_HD void ld(int m, double& re, double& im) const {
+#if defined(__CUDA_ARCH__)
+    re = live ? __ldcs(base + (long)m * stride) : 0.0;
+    im = live ? __ldcs(base + (long)(M + m) * stride) : 0.0;
+#else
+    re = live ? base[(long)m * stride] : 0.0;
+    im = live ? base[(long)(M + m) * stride] : 0.0;
+#endif
+  }
+  FB_HD void st(int m, double re, double im) const {
+    if (!live) return;
+#if defined(__CUDA_ARCH__)
+    __stcs(base + (long)m * stride, re);
+    __stcs(base + (long)(M + m) * stride, im);
+#else
+    base[(long)m * stride] = re;
+    base[(long)(M + m) * stride] = im;
+#endif
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// one radix-R pass.  FWD: DIF (butterfly, then twiddle).  !FWD: DIT (conj twiddle, then inverse
+// butterfly) -- exactly undoes the FWD pass up to the factor R.  M and s may be compile-time constants
+// at the call site (power-of-two kernels): everything here is force-inlined so they fold.
+template <int R, bool FWD, class LD, class ST>
+FB_HD void pass_core(int M, int s, const cpx* wM, int worker, int nworkers, const LD& src, const ST& dst) {
+  const int Lc = s * R;
   const int tstep = M / Lc;
   const int nb = M / R;
   for (int b = worker; b < nb; b += nworkers) {
@@ -168,11 +253,7 @@ FB_HD void pass_R(double* tile, const LinePlan& P, const cpx* wM, int q, int lan
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int t = 0; t < R; ++t) {
-      const int m = base + t * s;
-      re[t] = tile[taddr<TB, ROT>(m, 0, M, lane)];
-      im[t] = tile[taddr<TB, ROT>(m, 1, M, lane)];
-    }
+    for (int t = 0; t < R; ++t) src.ld(base + t * s, re[t], im[t]);
     if (FWD) {
       bfly<R, -1>(re, im);
 #if defined(__CUDACC__)
@@ -197,12 +278,14 @@ FB_HD void pass_R(double* tile, const LinePlan& P, const cpx* wM, int q, int lan
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int t = 0; t < R; ++t) {
-      const int m = base + t * s;
-      tile[taddr<TB, ROT>(m, 0, M, lane)] = re[t];
-      tile[taddr<TB, ROT>(m, 1, M, lane)] = im[t];
-    }
+    for (int t = 0; t < R; ++t) dst.st(base + t * s, re[t], im[t]);
   }
+}
+
+template <int TB, bool ROT, int R, bool FWD>
+FB_HD void pass_R(double* tile, const LinePlan& P, const cpx* wM, int q, int lane, int worker, int nworkers) {
+  const TileAcc<TB, ROT> acc{tile, P.M, lane};
+  pass_core<R, FWD>(P.M, P.sub[q], wM, worker, nworkers, acc, acc);
 }
 
 template <int TB, bool ROT, bool FWD>
@@ -221,92 +304,121 @@ FB_HD void fft_pass(double* tile, const LinePlan& P, const cpx* wM, int q, int l
 //   PP : slot(pos k) <- (Re X_k, Im X_k), k=1..M-1 ; slot(0) <- (X_0, X_M)        [R2HC content]
 //   NN : slot(pos k) <- (Y_k, Y_{N-k}) ; slot(0) <- (Y_0, Y_M)                    [REDFT10 content]
 //   DD : as NN on the sign-flipped input; row holding DCT mode q holds DST mode N-1-q (fft.f90:537-560)
-template <int TB, bool ROT>
-FB_HD void split_fwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
-  const int M = P.M;
-  const bool mk = (P.kind != KIND_PP);
+template <class LD, class ST>
+FB_HD void split_core(int M, int kind, const cpx* wN, const cpx* wQ, const int* pos, int worker, int nworkers,
+                      const LD& src, const ST& dst) {
+  const bool mk = (kind != KIND_PP);
   for (int k = worker; 2 * k <= M; k += nworkers) {
     if (k == 0) {
-      const int a0 = taddr<TB, ROT>(0, 0, M, lane), a1 = taddr<TB, ROT>(0, 1, M, lane);
-      const double zr = tile[a0], zi = tile[a1];
+      double zr, zi;
+      src.ld(0, zr, zi);
       double x0 = zr + zi, xm = zr - zi;
-      if (mk) { x0 = 2.0 * x0; xm = 2.0 * P.wQ[M].x * xm; }
-      tile[a0] = x0; tile[a1] = xm;
+      if (mk) { x0 = 2.0 * x0; xm = 2.0 * wQ[M].x * xm; }
+      dst.st(0, x0, xm);
       continue;
     }
-    const int pk = P.pos[k];
-    const int akr = taddr<TB, ROT>(pk, 0, M, lane), aki = taddr<TB, ROT>(pk, 1, M, lane);
+    const int pk = pos[k];
     if (2 * k == M) {                                   // X = conj(Z)
-      double xr = tile[akr], xi = -tile[aki];
+      double xr, xi;
+      src.ld(pk, xr, xi);
+      xi = -xi;
       if (mk) {
-        const cpx q = P.wQ[k];
+        const cpx q = wQ[k];
         const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
         xr = 2.0 * tr; xi = -2.0 * ti;
       }
-      tile[akr] = xr; tile[aki] = xi;
+      dst.st(pk, xr, xi);
       continue;
     }
-    const int pj = P.pos[M - k];
-    const int ajr = taddr<TB, ROT>(pj, 0, M, lane), aji = taddr<TB, ROT>(pj, 1, M, lane);
-    const double zkr = tile[akr], zki = tile[aki], zjr = tile[ajr], zji = tile[aji];
+    const int pj = pos[M - k];
+    double zkr, zki, zjr, zji;
+    src.ld(pk, zkr, zki);
+    src.ld(pj, zjr, zji);
     // E = (Z_k + conj Z_j)/2 ; O = -(i/2)(Z_k - conj Z_j) ; X_k = E + w^k O ; X_j = conj(E - w^k O)
     const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
     const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
-    const cpx w = P.wN[k];
+    const cpx w = wN[k];
     const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
     double xkr = er + wor, xki = ei + woi, xjr = er - wor, xji = -(ei - woi);
     if (mk) {
-      const cpx qk = P.wQ[k], qj = P.wQ[M - k];
+      const cpx qk = wQ[k], qj = wQ[M - k];
       const double tkr = xkr * qk.x - xki * qk.y, tki = xkr * qk.y + xki * qk.x;
       const double tjr = xjr * qj.x - xji * qj.y, tji = xjr * qj.y + xji * qj.x;
       xkr = 2.0 * tkr; xki = -2.0 * tki; xjr = 2.0 * tjr; xji = -2.0 * tji;
     }
-    tile[akr] = xkr; tile[aki] = xki; tile[ajr] = xjr; tile[aji] = xji;
+    dst.st(pk, xkr, xki);
+    dst.st(pj, xjr, xji);
   }
 }
 
-// backward merge: inverse of split_fwd up to the FFTW scale (HC2R: N, REDFT01/RODFT01: 2N)
-template <int TB, bool ROT>
-FB_HD void merge_bwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
-  const int M = P.M;
-  const bool mk = (P.kind != KIND_PP);
+// backward merge: inverse of split_core up to the FFTW scale (HC2R: N, REDFT01/RODFT01: 2N)
+template <class LD, class ST>
+FB_HD void merge_core(int M, int kind, const cpx* wN, const cpx* wQ, const int* pos, int worker, int nworkers,
+                      const LD& src, const ST& dst) {
+  const bool mk = (kind != KIND_PP);
   for (int k = worker; 2 * k <= M; k += nworkers) {
     if (k == 0) {
-      const int a0 = taddr<TB, ROT>(0, 0, M, lane), a1 = taddr<TB, ROT>(0, 1, M, lane);
-      double x0 = tile[a0], xm = tile[a1];
-      if (mk) xm = 2.0 * P.wQ[M].x * xm;               // V'_M = sqrt(2) Y_M
-      tile[a0] = x0 + xm; tile[a1] = x0 - xm;
+      double x0, xm;
+      src.ld(0, x0, xm);
+      if (mk) xm = 2.0 * wQ[M].x * xm;                  // V'_M = sqrt(2) Y_M
+      dst.st(0, x0 + xm, x0 - xm);
       continue;
     }
-    const int pk = P.pos[k];
-    const int akr = taddr<TB, ROT>(pk, 0, M, lane), aki = taddr<TB, ROT>(pk, 1, M, lane);
+    const int pk = pos[k];
     if (2 * k == M) {                                   // Z' = 2 conj(X)
-      double xr = tile[akr], xi = tile[aki];
+      double xr, xi;
+      src.ld(pk, xr, xi);
       if (mk) {                                         // V' = conj(q) (Y_k - i Y_{N-k})
-        const cpx q = P.wQ[k];
+        const cpx q = wQ[k];
         const double vr = xr * q.x - xi * q.y, vi = -xi * q.x - xr * q.y;
         xr = vr; xi = vi;
       }
-      tile[akr] = 2.0 * xr; tile[aki] = -2.0 * xi;
+      dst.st(pk, 2.0 * xr, -2.0 * xi);
       continue;
     }
-    const int pj = P.pos[M - k];
-    const int ajr = taddr<TB, ROT>(pj, 0, M, lane), aji = taddr<TB, ROT>(pj, 1, M, lane);
-    double xkr = tile[akr], xki = tile[aki], xjr = tile[ajr], xji = tile[aji];
+    const int pj = pos[M - k];
+    double xkr, xki, xjr, xji;
+    src.ld(pk, xkr, xki);
+    src.ld(pj, xjr, xji);
     if (mk) {
-      const cpx qk = P.wQ[k], qj = P.wQ[M - k];
+      const cpx qk = wQ[k], qj = wQ[M - k];
       const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
       const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
       xkr = vkr; xki = vki; xjr = vjr; xji = vji;
     }
     // S = X_k + conj X_j ; D = X_k - conj X_j ; T = i conj(w^k) D ; Z'_k = S + T ; Z'_j = conj(S - T)
     const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
-    const cpx w = P.wN[k];
+    const cpx w = wN[k];
     const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
     const double tr = -ci, ti = cr;                                       // i * (.)
-    tile[akr] = sr + tr; tile[aki] = si + ti;
-    tile[ajr] = sr - tr; tile[aji] = -(si - ti);
+    dst.st(pk, sr + tr, si + ti);
+    dst.st(pj, sr - tr, -(si - ti));
   }
+}
+
+template <int TB, bool ROT>
+FB_HD void split_fwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
+  const TileAcc<TB, ROT> acc{tile, P.M, lane};
+  split_core(P.M, P.kind, P.wN, P.wQ, P.pos, worker, nworkers, acc, acc);
+}
+
+template <int TB, bool ROT>
+FB_HD void merge_bwd(double* tile, const LinePlan& P, int lane, int worker, int nworkers) {
+  const TileAcc<TB, ROT> acc{tile, P.M, lane};
+  merge_core(P.M, P.kind, P.wN, P.wQ, P.pos, worker, nworkers, acc, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// power-of-two lengths: the radix schedule is a compile-time function of M (identical to the one
+// make_line_plan builds at run time: 8,8,...,then 4 or 2), so strides/twiddle steps fold to constants.
+FB_CX int p2_first_radix(int Lc) { return (Lc % 8 == 0) ? 8 : (Lc % 4 == 0) ? 4 : 2; }
+FB_CX int p2_npass(int M) { int n = 0; while (M > 1) { M /= p2_first_radix(M); ++n; } return n; }
+FB_CX int p2_lc(int M, int q) { while (q-- > 0) M /= p2_first_radix(M); return M; }   // sub-length before pass q
+
+template <int M, int Q, bool FWD, class LD, class ST>
+FB_HD void p2_pass(const cpx* wM, int worker, int nworkers, const LD& src, const ST& dst) {
+  constexpr int Lc = p2_lc(M, Q), R = p2_first_radix(Lc), s = Lc / R;
+  pass_core<R, FWD>(M, s, wM, worker, nworkers, src, dst);
 }
 
 }  // namespace fb

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _solve_gpu(case, rhs, device=False, generic_z=False):
+def _solve_gpu(case, rhs, device=False, generic_z=False, generic_fft=False):
     s = case.setup
     n = case.ng
+    lib.load().flutas_b200_debug_generic_fft(1 if generic_fft else 0)
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
     assert nf == s.normfft
     if generic_z:
@@ -69,12 +70,19 @@ CASES = [
     ("wide", (1024, 16, 8), ("PP", "NN", "NN"), (4.0, 1.0, 1.0), 0.0),
     ("tall", (16, 2048, 4), ("DD", "PP", "NN"), (1.0, 4.0, 1.0), 0.0),
     ("deep", (16, 16, 256), ("PP", "PP", "PP"), (1.0, 1.0, 4.0), 0.0),
+    ("p2a", (512, 256, 8), ("NN", "DD", "NN"), (2.0, 1.0, 1.0), 0.0),
+    ("p2b", (256, 512, 8), ("DD", "NN", "DD"), (2.0, 1.0, 1.0), 0.0),
+    ("p2c", (128, 1024, 4), ("PP", "DD", "NN"), (2.0, 1.0, 1.0), 0.0),
+    ("p2d", (2048, 64, 4), ("NN", "PP", "NN"), (2.0, 1.0, 1.0), 0.0),
+    ("p2e", (72, 2048, 4), ("PP", "NN", "NN"), (2.0, 1.0, 1.0), 0.0),
+    ("p2f", (1000, 128, 6), ("DD", "PP", "PP"), (2.0, 1.0, 1.0), 0.0),
 ]
 
 
 @pytest.mark.parametrize("name,ng,cbc,lengths,gr", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("device", [False, True], ids=["hostptr", "devptr"])
-def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device):
+@pytest.mark.parametrize("device,generic_fft", [(False, False), (True, False), (True, True)],
+                         ids=["hostptr", "devptr", "devptr-genericfft"])
+def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device, generic_fft):
     case = Case(ng, cbc, lengths, gr=gr, seed=4242 + len(name), name=name)
     s = case.setup
     u, v, w = case.velocity()
@@ -83,7 +91,7 @@ def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device):
     rhs = rhs_p[1:-1, 1:-1, 1:-1].copy(order="F")
     pref = rhs_p.copy(order="F")
     oracle.Solver(ng, cbc[0], cbc[1]).solve(s.lambdaxy, s.a, s.b, s.c, cbc[2], pref)
-    p = _solve_gpu(case, rhs, device=device)
+    p = _solve_gpu(case, rhs, device=device, generic_fft=generic_fft)
     err = gauge_rel_err(p[1:-1, 1:-1, 1:-1], pref[1:-1, 1:-1, 1:-1], case.singular)
     assert err <= TOL, err
 
