@@ -26,20 +26,41 @@
 
 namespace fb {
 
+// 1/x for the (well-scaled, diagonally dominant) pivots.  On the device: MUFU.RCP64H-class approximation
+// (rel. error <= 2^-23) + two Newton steps = full double precision without the slow-path branches of the
+// IEEE division sequence; on the host (tests/emulate) plain division.
+FB_HD double fb_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 // coefficient arrays az, bz, cz: a,b,c of initsolver with az[0] = 0 and cz[nz-1] = 0 unless z is periodic
 struct ThomasArgs {
   int nz, S;              // S = nz / L segments
   int periodic, singular;
-  const double* az;
+  const double* az;       // indexed by cidx(k): k itself, or the padded row k + k/L once staged in shared memory
   const double* bz;
   const double* cz;
+  int padded;             // 1: coefficient arrays use the padded (shared-memory) index
 };
 
 template <int L, int TI>
 struct ThomasTile {
   static FB_HD int prow(int k) { return k + k / L; }                   // one pad row per segment (bank parity)
+  static FB_HD int cidx(const ThomasArgs& T, int k) { return T.padded ? prow(k) : k; }
   static FB_HD int tile_rows(int nz) { return nz + nz / L; }
-  static FB_HD size_t smem_doubles(int nz) { return (size_t)tile_rows(nz) * TI + 8 * (size_t)(nz / L) * TI; }
+  static FB_HD size_t smem_doubles(int nz) {                          // tile | 8 exchange arrays | az,bz,cz (padded)
+    return (size_t)tile_rows(nz) * TI + 8 * (size_t)(nz / L) * TI + 3 * (size_t)tile_rows(nz);
+  }
 
   // ---- phase 1: local sweeps; writes (RU,QU,GU) and (RD,FD,DD) of this thread to ex[6][S][TI]
   static FB_HD void local_sweeps(const double* tile, double* ex, const ThomasArgs& T, double lam, int lane, int s,
@@ -54,17 +75,17 @@ struct ThomasTile {
 #endif
     for (int l = 0; l < L - 1; ++l) {
       {                                                                  // up: row lu = L-2-l
-        const int k = k0 + (L - 2 - l);
-        const double ak = T.az[k], ck = T.cz[k], bk = T.bz[k] + lam;
-        const double zz = 1.0 / (bk - ck * q);
+        const int k = k0 + (L - 2 - l), kc = cidx(T, k);
+        const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + lam;
+        const double zz = fb_rcp(bk - ck * q);
         ru = (tile[prow(k) * TI + lane] - ck * ru) * zz;
         g = -ck * g * zz;
         q = ak * zz;
       }
       {                                                                  // down: row l
-        const int k = k0 + l;
-        const double ak = T.az[k], ck = T.cz[k], bk = T.bz[k] + lam;
-        const double zz = 1.0 / (bk - ak * d);
+        const int k = k0 + l, kc = cidx(T, k);
+        const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + lam;
+        const double zz = fb_rcp(bk - ak * d);
         rd = (tile[prow(k) * TI + lane] - ak * rd) * zz;
         f = (l == 0) ? ak * zz : -ak * f * zz;
         d = ck * zz;
@@ -82,7 +103,8 @@ struct ThomasTile {
     const int S = T.S, st = S * TI, o = s * TI + lane;
     const int ks = s * L + L - 1;
     const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
-    const double ak = T.az[ks], ck = T.cz[ks], bk = T.bz[ks] + lam;     // ck = 0 on the last row unless periodic
+    const int kc = cidx(T, ks);
+    const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + lam;     // ck = 0 on the last row unless periodic
     double A, B, C, R;
     if (L > 1) {
       const double ru = ex[on], qu = ex[st + on], gu = ex[2 * st + on];
@@ -103,13 +125,13 @@ struct ThomasTile {
     const int S = T.S, st = S * TI, o = s * TI + lane;
     int sm = s - h, sp = s + h;
     bool hm = true, hp = true;
-    if (T.periodic) { sm = (sm % S + S) % S; sp = sp % S; }
+    if (T.periodic) { sm &= (S - 1); sp &= (S - 1); }          // cyclic PCR runs with S a power of two
     else { hm = (sm >= 0); hp = (sp < S); }
     const double A = src[o], B = src[st + o], C = src[2 * st + o], R = src[3 * st + o];
     double Am = 0.0, Bm = 1.0, Cm = 0.0, Rm = 0.0, Ap = 0.0, Bp = 1.0, Cp = 0.0, Rp = 0.0;
     if (hm) { const int q = sm * TI + lane; Am = src[q]; Bm = src[st + q]; Cm = src[2 * st + q]; Rm = src[3 * st + q]; }
     if (hp) { const int q = sp * TI + lane; Ap = src[q]; Bp = src[st + q]; Cp = src[2 * st + q]; Rp = src[3 * st + q]; }
-    const double al = -A / Bm, ga = -C / Bp;
+    const double al = -A * fb_rcp(Bm), ga = -C * fb_rcp(Bp);
     dst[o] = al * Am;
     dst[st + o] = B + al * Cm + ga * Ap;
     dst[2 * st + o] = ga * Cp;
@@ -122,12 +144,12 @@ struct ThomasTile {
     const int S = T.S, st = S * TI, o = s * TI + lane;
     const double B = src[st + o], R = src[3 * st + o];
     if (T.periodic && S >= 2) {
-      const int t = (s + S / 2) % S, q = t * TI + lane;
+      const int t = (s + S / 2) & (S - 1), q = t * TI + lane;
       const double K = src[o] + src[2 * st + o], Kt = src[q] + src[2 * st + q];
       const double Bt = src[st + q], Rt = src[3 * st + q];
-      X[o] = (R * Bt - K * Rt) / (B * Bt - K * Kt);
+      X[o] = (R * Bt - K * Rt) * fb_rcp(B * Bt - K * Kt);
     } else {
-      X[o] = R / B;
+      X[o] = R * fb_rcp(B);
     }
   }
 
@@ -144,10 +166,10 @@ struct ThomasTile {
 #pragma unroll
 #endif
     for (int l = 0; l < L - 1; ++l) {
-      const int k = k0 + l;
+      const int k = k0 + l, kc = cidx(T, k);
       double r = tile[prow(k) * TI + lane];
-      if (l == 0) r -= T.az[k] * xp; else r -= T.az[k] * pp;
-      if (l == L - 2) r -= T.cz[k] * xs;
+      if (l == 0) r -= T.az[kc] * xp; else r -= T.az[kc] * pp;
+      if (l == L - 2) r -= T.cz[kc] * xs;
       pp = r * z[l];
       tile[prow(k) * TI + lane] = pp;
     }
@@ -157,7 +179,7 @@ struct ThomasTile {
 #endif
     for (int l = L - 3; l >= 0; --l) {
       const int k = k0 + l;
-      x = tile[prow(k) * TI + lane] - T.cz[k] * z[l] * x;
+      x = tile[prow(k) * TI + lane] - T.cz[cidx(T, k)] * z[l] * x;
       tile[prow(k) * TI + lane] = x;
     }
   }
@@ -170,8 +192,11 @@ struct ThomasTile {
 
 namespace fb {
 
+#ifndef FB_THOMAS_MINB
+#define FB_THOMAS_MINB 2
+#endif
 template <int L, int TI>
-__global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasArgs T, const double* __restrict__ lam,
+__global__ void __launch_bounds__(TI * 32, (L <= 16) ? FB_THOMAS_MINB : 2) thomas_tile_kernel(long ncol, ThomasArgs T, const double* __restrict__ lam,
                                                               double* __restrict__ W) {
   using TT = ThomasTile<L, TI>;
   extern __shared__ double smem[];
@@ -179,6 +204,7 @@ __global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasA
   double* tile = smem;
   double* exa = smem + (size_t)TT::tile_rows(nz) * TI;     // 4*S*TI
   double* exb = exa + 4 * (size_t)S * TI;                   // 4*S*TI  (exa..exb+.. also hold the 6 local-sweep arrays)
+  double* coef = exb + 4 * (size_t)S * TI;                  // 3 * tile_rows: az | bz | cz at padded rows
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int lane = tid % TI, s = tid / TI;
   const long col0 = (long)blockIdx.x * TI;
@@ -186,8 +212,16 @@ __global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasA
   double* base = W + col0 + lane;
 
   {
+    const int tr = TT::tile_rows(nz);
+    for (int k = tid; k < nz; k += nthr) {
+      const int r = TT::prow(k);
+      coef[r] = __ldg(T.az + k); coef[tr + r] = __ldg(T.bz + k); coef[2 * tr + r] = __ldg(T.cz + k);
+    }
+    T.az = coef; T.bz = coef + tr; T.cz = coef + 2 * tr; T.padded = 1;
+  }
+  {
     // coalesced load, LU loads in flight per thread (a warp covers 32/TI rows of 8*TI contiguous bytes)
-    constexpr int LU = 8;
+    constexpr int LU = (L < 16) ? L : 16;
     const double* src = W + col0 + (live ? lane : 0);
     for (int k0 = s; k0 < nz; k0 += LU * S) {
       double v[LU];
@@ -211,9 +245,9 @@ __global__ void __launch_bounds__(TI * 64) thomas_tile_kernel(long ncol, ThomasA
   {
     // same arithmetic as ThomasTile::reduced_row, kept in registers until every thread has read `exa`
     const int st = S * TI, o = s * TI + lane;
-    const int ks = s * L + L - 1;
+    const int ks = s * L + L - 1, kc = TT::cidx(T, ks);
     const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
-    const double ak = T.az[ks], ck = T.cz[ks], bk = T.bz[ks] + l;
+    const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + l;
     if (L > 1) {
       const double ru = exa[on], qu = exa[st + on], gu = exa[2 * st + on];
       const double rd = exa[3 * st + o], fd = exa[4 * st + o], dd = exa[5 * st + o];
@@ -269,14 +303,14 @@ inline cudaError_t thomas_tile_launch(long ncol, const ThomasArgs& T, const doub
 
 // Picks a segment length; *done = false if this nz is not served (caller falls back to the generic kernels).
 inline bool thomas_tile_pick(int nz, bool periodic, int* Lout) {
-  const int cand[5] = {16, 8, 32, 4, 2};
+  const int cand[5] = {16, 32, 8, 4, 2};
   for (int q = 0; q < 5; ++q) {
     const int L = cand[q];
     if (nz % L) continue;
     const int S = nz / L;
-    if (S < 2 || S > 64) continue;
+    if (S < 2 || S > 32) continue;                       // block = 8*S threads, launch bounds assume <= 256
     if (periodic && (S & (S - 1))) continue;              // cyclic PCR needs a power-of-two number of separators
-    const size_t smem = ((size_t)(nz + S) * 8 + 8 * (size_t)S * 8) * sizeof(double);
+    const size_t smem = ((size_t)(nz + S) * 8 + 8 * (size_t)S * 8 + 3 * (size_t)(nz + S)) * sizeof(double);
     if (smem > 200 * 1024) continue;
     *Lout = L;
     return true;
@@ -291,6 +325,7 @@ inline int thomas_tile_run(long ncol, int nz, const double* az, const double* bz
   if (!thomas_tile_pick(nz, periodic, &L)) return 0;
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
+  T.padded = 0;
   cudaError_t e = cudaSuccess;
   switch (L) {
     case 2: e = thomas_tile_launch<2, 8>(ncol, T, lam, W, st); break;

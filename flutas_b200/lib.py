@@ -17,7 +17,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = _build.SO
+    so = os.environ.get("FLUTAS_B200_LIB") or _build.SO      # override: A/B runs of kernel variants
     if not os.path.exists(so):
         so = _build.build()
     L = C.CDLL(so)

@@ -119,6 +119,7 @@ extern "C" int emul_thomas_tile(int L, int nz, long ncol, int periodic, int sing
   if (!periodic) { az[0] = 0.0; cz[nz - 1] = 0.0; }
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic; T.singular = singular; T.az = az.data(); T.bz = b; T.cz = cz.data();
+  T.padded = 0;
   if (periodic && (T.S & (T.S - 1))) return 2;
   switch (L) {
     case 1: thomas_emul<1, 8>(ncol, T, lam, W); break;
