@@ -156,6 +156,18 @@ struct SolverPlan {
   double key_lam_samples[3] = {0, 0, 0};
   bool cache_valid = false;
   int thomas_mode = 0;           // 0 = auto, 1 = force generic (tests)
+  // slab (multi-GPU) state
+  DevBuf sendrecv, pencil, lam_win;
+  bool p2p = false;
+  void* p2p_alloc = nullptr;                 // [pencil | recv | flags], published through CUDA IPC
+  size_t p2p_bytes = 0, p2p_chunk = 0;
+  double* peer_pencil[FB_MAX_RANKS] = {};
+  double* peer_recv[FB_MAX_RANKS] = {};
+  unsigned long long* peer_flags[FB_MAX_RANKS] = {};
+  void* peer_base[FB_MAX_RANKS] = {};
+  unsigned long long** d_peer_flags = nullptr;
+  int* d_err = nullptr;
+  unsigned long long epoch = 0;
 };
 
 struct PlanHandle {
@@ -197,28 +209,37 @@ int run_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst, Li
   }
 }
 template <int TB, bool FWD>
-int launch_y(const DevLinePlan& lp, double* W, int n1, long n3) {
+int launch_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& sg) {
   auto kern = yfft_kernel<TB, FWD>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem));
   const int nti = (n1 + TB - 1) / TB;
-  kern<<<(unsigned)(nti * n3), 256, lp.smem, g_stream>>>(lp.d, W, n1, nti);
+  kern<<<(unsigned)(nti * n3), 256, lp.smem, g_stream>>>(lp.d, W, n1, nti, sg);
   LAUNCHED();
   return 0;
 }
 template <bool FWD>
-int run_y(const DevLinePlan& lp, double* W, int n1, long n3) {
+int run_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& sg) {
   if (!g_force_generic_fft && p2_tile_width(lp.d.N)) {
-    cudaError_t e = p2_run_y(FWD, lp.d, W, n1, n3, g_stream);
+    cudaError_t e = p2_run_y(FWD, lp.d, W, n1, n3, sg, g_stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_p2 launch failed: %s", cudaGetErrorString(e));
     return 0;
   }
   switch (lp.tb) {
-    case 16: return launch_y<16, FWD>(lp, W, n1, n3);
-    case 8: return launch_y<8, FWD>(lp, W, n1, n3);
-    default: return launch_y<4, FWD>(lp, W, n1, n3);
+    case 16: return launch_y<16, FWD>(lp, W, n1, n3, sg);
+    case 8: return launch_y<8, FWD>(lp, W, n1, n3, sg);
+    default: return launch_y<4, FWD>(lp, W, n1, n3, sg);
   }
 }
+
+SpecGeom local_spec(double* W, int n1) {
+  SpecGeom sg;
+  for (int q = 0; q < FB_MAX_RANKS; ++q) sg.ptr[q] = W;
+  sg.n1l = n1; sg.koff = 0;
+  return sg;
+}
+
+int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular);
 
 int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const double* a, const double* b, const double* c,
                        bool periodic) {
@@ -270,6 +291,73 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
   }
   sp->cache_valid = true;
   return 0;
+}
+
+
+// z stage (solver_cpu.f90:71-77): on-chip partition/PCR kernel when nz allows it, else the generic
+// scratch-field kernels (in place; a ColGeom output then needs the scatter kernel).
+__global__ void scatter_cols_kernel(long ncol, int nz, const double* __restrict__ W, ColGeom og) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ncol * nz) return;
+  const int k = (int)(idx / ncol);
+  const long col = idx - (long)k * ncol;
+  const int q = k / og.n3l;
+  og.ptr[q][og.koff + col + ncol * (long)(k - q * og.n3l)] = W[idx];
+}
+
+int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
+  const double* abc = sp->abc.as<double>();
+  bool done = false;
+  if (sp->thomas_mode == 0) {
+    int rc = thomas_tile_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, out, periodic, singular, g_stream, &done);
+    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_tile launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (done) return 0;
+  const size_t npts = (size_t)ncol * nz;
+  if (int rc = sp->scratchD.reserve(npts * sizeof(double))) return rc;
+  const unsigned nb = (unsigned)((ncol + 127) / 128);
+  if (periodic) {
+    if (int rc = sp->scratchP2.reserve(npts * sizeof(double))) return rc;
+    thomas_periodic_generic_kernel<<<nb, 128, 0, g_stream>>>(ncol, nz, abc, abc + nz, abc + 2 * nz, lam, W,
+                                                             sp->scratchD.as<double>(), sp->scratchP2.as<double>(), singular);
+  } else {
+    thomas_generic_kernel<<<nb, 128, 0, g_stream>>>(ncol, nz, abc, abc + nz, abc + 2 * nz, lam, W,
+                                                    sp->scratchD.as<double>(), singular);
+  }
+  LAUNCHED();
+  if (out) {
+    scatter_cols_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, g_stream>>>(ncol, nz, W, *out);
+    LAUNCHED();
+  }
+  return 0;
+}
+
+// ---- multi-GPU slab exchange ------------------------------------------------------------------
+flutas_b200_alltoall_fn g_a2a = nullptr;
+void* g_a2a_ctx = nullptr;
+
+struct P2PBlob {                       // what one rank publishes to the others
+  cudaIpcMemHandle_t handle;
+  unsigned long long bytes;
+  unsigned long long chunk_doubles;
+};
+
+// cross-GPU barrier through flag words in peer memory: rank r stores `epoch` into slot r of every
+// peer's flag array, then waits until all slots of its own array have reached `epoch`.
+__global__ void p2p_barrier_kernel(int rank, int nranks, unsigned long long epoch, unsigned long long* own,
+                                   unsigned long long* const* peers, int* err) {
+  const int q = threadIdx.x;
+  if (q >= nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers[q] + rank), "l"(epoch) : "memory");
+  const long long t0 = clock64();
+  unsigned long long v = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(own + q) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 4000000000LL) { atomicAdd(err, 1); break; }   // ~2 s: never hang the GPU
+  } while (true);
 }
 
 StencilGeom stencil_geom(int nx, int ny, int nz, int nh_u) {
@@ -406,6 +494,12 @@ int flutas_b200_fftend(void* arrplan[4]) {
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "fftend: not a flutas_b200 plan");
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
+  for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
+  for (int q = 0; q < FB_MAX_RANKS; ++q)
+    if (sp->peer_base[q] && sp->peer_base[q] != sp->p2p_alloc) cudaIpcCloseMemHandle(sp->peer_base[q]);
+  if (sp->p2p_alloc) cudaFree(sp->p2p_alloc);
+  if (sp->d_peer_flags) cudaFree(sp->d_peer_flags);
+  if (sp->d_err) cudaFree(sp->d_err);
   sp->magic = 0;
   delete sp;
   for (int q = 0; q < 4; ++q) { delete (PlanHandle*)arrplan[q]; arrplan[q] = nullptr; }
@@ -470,32 +564,185 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
   const double* lam = sp->lam_int.as<double>();
 
   { StageTimer t(ST_XF); if (int rc = run_x<true>(sp->px, pd, gp, W, gw, 1.0)) return rc; }   // solver_cpu.f90:59
-  { StageTimer t(ST_YF); if (int rc = run_y<true>(sp->py, W, n1, n3)) return rc; }             // :65
-  {                                                                          // :71-77
-    StageTimer t(ST_Z);
-    const long ncol = (long)n1 * n2;
-    bool done = false;
-    if (sp->thomas_mode == 0) {
-      int rc = thomas_tile_run(ncol, n3, abc + 3 * n3, abc + 4 * n3, abc + 5 * n3, lam, W, periodic, singular, g_stream, &done);
-      if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_tile launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-      if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-    if (!done) {
-      if (int rc = sp->scratchD.reserve(npts * sizeof(double))) return rc;
-      const unsigned nb = (unsigned)((ncol + 127) / 128);
-      if (periodic) {
-        if (int rc = sp->scratchP2.reserve(npts * sizeof(double))) return rc;
-        thomas_periodic_generic_kernel<<<nb, 128, 0, g_stream>>>(ncol, n3, abc, abc + n3, abc + 2 * n3, lam, W,
-                                                                 sp->scratchD.as<double>(), sp->scratchP2.as<double>(), singular);
-      } else {
-        thomas_generic_kernel<<<nb, 128, 0, g_stream>>>(ncol, n3, abc, abc + n3, abc + 2 * n3, lam, W,
-                                                        sp->scratchD.as<double>(), singular);
-      }
-      LAUNCHED();
-    }
-  }
-  { StageTimer t(ST_YB); if (int rc = run_y<false>(sp->py, W, n1, n3)) return rc; }            // :86
+  const SpecGeom sg = local_spec(W, n1);
+  { StageTimer t(ST_YF); if (int rc = run_y<true>(sp->py, W, n1, n3, sg)) return rc; }         // :65
+  { StageTimer t(ST_Z); if (int rc = run_z(sp, (long)n1 * n2, n3, lam, W, nullptr, periodic, singular)) return rc; }   // :71-77
+  { StageTimer t(ST_YB); if (int rc = run_y<false>(sp->py, W, n1, n3, sg)) return rc; }        // :86
   { StageTimer t(ST_XB); if (int rc = run_x<false>(sp->px, W, gw, pd, gp, normfft)) return rc; }  // :89,93
+
+  if (host_p) {
+    CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_set_alltoall(flutas_b200_alltoall_fn fn, void* ctx) {
+  g_a2a = fn;
+  g_a2a_ctx = ctx;
+  return FLUTAS_B200_OK;
+}
+
+size_t flutas_b200_p2p_handle_bytes(void) { return sizeof(P2PBlob); }
+
+// Allocates this rank's exchange memory [pencil | recv | flags] and returns its IPC handle in `blob`.
+int flutas_b200_p2p_export(void* const arrplan[4], const int n_local[3], void* blob) {
+  SolverPlan* sp = plan_of(arrplan);
+  if (!sp || !n_local || !blob) return fail(FLUTAS_B200_ERR_ARG, "p2p_export: bad arguments");
+  const int P = g_nranks;
+  if (P < 2 || P > FB_MAX_RANKS) return fail(FLUTAS_B200_ERR_ARG, "p2p needs 2..%d ranks (flutas_b200_init)", FB_MAX_RANKS);
+  if (sp->n1 % P) return fail(FLUTAS_B200_ERR_ARG, "ng1 = %d is not divisible by %d ranks", sp->n1, P);
+  const size_t chunk = (size_t)(sp->n1 / P) * sp->n2 * n_local[2];
+  const size_t field = chunk * P * sizeof(double);
+  const size_t bytes = 2 * field + 4096;
+  if (sp->p2p_alloc) { cudaFree(sp->p2p_alloc); sp->p2p_alloc = nullptr; }
+  CK(cudaMalloc(&sp->p2p_alloc, bytes));
+  CK(cudaMemset(sp->p2p_alloc, 0, bytes));
+  sp->p2p_bytes = bytes; sp->p2p_chunk = chunk;
+  P2PBlob b;
+  memset(&b, 0, sizeof(b));
+  CK(cudaIpcGetMemHandle(&b.handle, sp->p2p_alloc));
+  b.bytes = bytes; b.chunk_doubles = chunk;
+  memcpy(blob, &b, sizeof(b));
+  return FLUTAS_B200_OK;
+}
+
+// `blobs`: the nranks blobs in rank order (all-gathered by the host).  Maps every peer's exchange memory.
+int flutas_b200_p2p_attach(void* const arrplan[4], const void* blobs) {
+  SolverPlan* sp = plan_of(arrplan);
+  if (!sp || !blobs || !sp->p2p_alloc) return fail(FLUTAS_B200_ERR_ARG, "p2p_attach: call p2p_export first");
+  const int P = g_nranks;
+  const P2PBlob* bl = (const P2PBlob*)blobs;
+  const size_t field = sp->p2p_chunk * P * sizeof(double);
+  for (int q = 0; q < P; ++q) {
+    if (bl[q].chunk_doubles != sp->p2p_chunk) return fail(FLUTAS_B200_ERR_ARG, "rank %d has a different chunk size", q);
+    void* base = sp->p2p_alloc;
+    if (q != g_rank) {
+      cudaIpcMemHandle_t h = bl[q].handle;
+      cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+    }
+    sp->peer_base[q] = base;
+    sp->peer_pencil[q] = (double*)base;
+    sp->peer_recv[q] = (double*)((char*)base + field);
+    sp->peer_flags[q] = (unsigned long long*)((char*)base + 2 * field);
+  }
+  if (!sp->d_peer_flags) CK(cudaMalloc(&sp->d_peer_flags, FB_MAX_RANKS * sizeof(void*)));
+  CK(cudaMemcpy(sp->d_peer_flags, sp->peer_flags, FB_MAX_RANKS * sizeof(void*), cudaMemcpyHostToDevice));
+  if (!sp->d_err) { CK(cudaMalloc(&sp->d_err, sizeof(int))); CK(cudaMemset(sp->d_err, 0, sizeof(int))); }
+  sp->epoch = 0;
+  sp->p2p = true;
+  return FLUTAS_B200_OK;
+}
+
+// number of barrier time-outs seen so far (0 = healthy); synchronises the stream
+int flutas_b200_p2p_errors(void* const arrplan[4]) {
+  SolverPlan* sp = plan_of(arrplan);
+  if (!sp || !sp->d_err) return 0;
+  int v = 0;
+  cudaStreamSynchronize(g_stream);
+  cudaMemcpy(&v, sp->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+static int p2p_barrier(SolverPlan* sp) {
+  sp->epoch += 1;
+  p2p_barrier_kernel<<<1, 32, 0, g_stream>>>(g_rank, g_nranks, sp->epoch, sp->peer_flags[g_rank], sp->d_peer_flags, sp->d_err);
+  LAUNCHED();
+  return 0;
+}
+
+int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normfft, const double* lambdaxy_global,
+                            const double* a, const double* b, const double* c, const char bcz[2],
+                            const char c_or_f[3], double* p) {
+  SolverPlan* sp = plan_of(arrplan);
+  if (!sp) return fail(FLUTAS_B200_ERR_ARG, "solver_slab: arrplan was not created by flutas_b200_fftini");
+  if (!n || !lambdaxy_global || !a || !b || !c || !bcz || !c_or_f || !p) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (c_or_f[2] != 'c') return fail(FLUTAS_B200_ERR_UNSUPPORTED, "c_or_f(3) must be 'c'");
+  const int P = g_nranks, r = g_rank;
+  if (P == 1) return flutas_b200_solver(n, arrplan, normfft, lambdaxy_global, a, b, c, bcz, c_or_f, p);
+  if (P > FB_MAX_RANKS) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "at most %d ranks (one NVSwitch box)", FB_MAX_RANKS);
+  const int n1 = n[0], n2 = n[1], n3l = n[2], ng3 = n3l * P;
+  if (n1 != sp->n1 || n2 != sp->n2) return fail(FLUTAS_B200_ERR_ARG, "n = (%d,%d,%d) does not match the plan (%d,%d)", n1, n2, n3l, sp->n1, sp->n2);
+  if (n1 % P) return fail(FLUTAS_B200_ERR_ARG, "ng1 = %d is not divisible by %d ranks (sanity.f90:159-167)", n1, P);
+  if (!sp->p2p && !g_a2a) return fail(FLUTAS_B200_ERR_ARG, "multi-rank solve needs flutas_b200_set_alltoall or flutas_b200_p2p_attach");
+  const int n1l = n1 / P;
+  const bool periodic = (bcz[0] == 'P' && bcz[1] == 'P');
+  if (ng3 < 4) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "ng3 = %d too small", ng3);
+  const bool zsing = periodic || (bcz[0] == 'N' && bcz[1] == 'N');
+  const bool xysing = (sp->bcxy[0] != 'D' && sp->bcxy[2] != 'D');
+  const int singular = (zsing && xysing) ? 1 : 0;
+
+  const bool was_valid = sp->cache_valid;
+  if (int rc = cache_coefficients(sp, ng3, lambdaxy_global, a, b, c, periodic)) return rc;
+  const size_t chunk = (size_t)n1l * n2 * n3l, nloc = chunk * P;
+  if (!was_valid || !sp->cache_valid || sp->lam_win.cap < (size_t)n1l * n2 * sizeof(double)) {
+    if (int rc = sp->lam_win.reserve((size_t)n1l * n2 * sizeof(double))) return rc;
+  }
+  // this rank's x rows of the permuted eigenvalues: lam_win(i_l, ry) = lam_int(r*n1l + i_l, ry)
+  CK(cudaMemcpy2DAsync(sp->lam_win.p, (size_t)n1l * sizeof(double), sp->lam_int.as<double>() + (size_t)r * n1l,
+                       (size_t)n1 * sizeof(double), (size_t)n1l * sizeof(double), n2, cudaMemcpyDeviceToDevice, g_stream));
+  if (int rc = sp->work.reserve(nloc * sizeof(double))) return rc;
+  double* W1 = sp->work.as<double>();
+  double *S = nullptr, *W2 = nullptr, *R = nullptr;
+  if (sp->p2p) {
+    if (chunk != sp->p2p_chunk) return fail(FLUTAS_B200_ERR_ARG, "local size changed since p2p_export");
+    W2 = sp->peer_pencil[r]; R = sp->peer_recv[r];
+  } else {
+    if (int rc = sp->sendrecv.reserve(nloc * sizeof(double))) return rc;
+    if (int rc = sp->pencil.reserve(nloc * sizeof(double))) return rc;
+    S = sp->sendrecv.as<double>(); R = S; W2 = sp->pencil.as<double>();
+  }
+
+  const size_t pcount = (size_t)(n1 + 2) * (n2 + 2) * (n3l + 2);
+  double* pd = p;
+  const bool host_p = !on_device(p);
+  if (host_p) {
+    if (int rc = sp->pstage.reserve(pcount * sizeof(double))) return rc;
+    pd = sp->pstage.as<double>();
+    CK(cudaMemcpyAsync(pd, p, pcount * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  }
+  const long s1 = n1 + 2, s2 = n2 + 2;
+  LineGeom gp{1 + s1 * (1 + s2), s1, s1 * s2, n2, (long)n2 * n3l};
+  LineGeom gw{0, (long)n1, (long)n1 * n2, n2, (long)n2 * n3l};
+
+  { StageTimer t(ST_XF); if (int rc = run_x<true>(sp->px, pd, gp, W1, gw, 1.0)) return rc; }
+  {
+    // y transform whose store IS the pack (NCCL) or the exchange itself (direct stores into peer pencils)
+    SpecGeom sg;
+    for (int q = 0; q < FB_MAX_RANKS; ++q) sg.ptr[q] = nullptr;
+    for (int q = 0; q < P; ++q) sg.ptr[q] = sp->p2p ? sp->peer_pencil[q] : S + (size_t)q * chunk;
+    sg.n1l = n1l; sg.koff = sp->p2p ? (long)r * (long)chunk : 0;
+    StageTimer t(ST_YF);
+    if (int rc = run_y<true>(sp->py, W1, n1, n3l, sg)) return rc;
+  }
+  {
+    StageTimer t(ST_EXCH_F);
+    if (sp->p2p) { if (int rc = p2p_barrier(sp)) return rc; }
+    else if (g_a2a(g_a2a_ctx, S, W2, chunk * sizeof(double), (void*)g_stream)) return fail(FLUTAS_B200_ERR_CUDA, "all-to-all callback failed");
+  }
+  {
+    ColGeom og;
+    for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = nullptr;
+    for (int q = 0; q < P; ++q) og.ptr[q] = sp->peer_recv[q];
+    og.n3l = n3l; og.koff = (long)r * (long)chunk;
+    StageTimer t(ST_Z);
+    if (int rc = run_z(sp, (long)n1l * n2, ng3, sp->lam_win.as<double>(), W2, sp->p2p ? &og : nullptr, periodic, singular)) return rc;
+  }
+  {
+    StageTimer t(ST_EXCH_B);
+    if (sp->p2p) { if (int rc = p2p_barrier(sp)) return rc; }
+    else if (g_a2a(g_a2a_ctx, W2, R, chunk * sizeof(double), (void*)g_stream)) return fail(FLUTAS_B200_ERR_CUDA, "all-to-all callback failed");
+  }
+  {
+    SpecGeom sg;
+    for (int q = 0; q < FB_MAX_RANKS; ++q) sg.ptr[q] = nullptr;
+    for (int q = 0; q < P; ++q) sg.ptr[q] = R + (size_t)q * chunk;
+    sg.n1l = n1l; sg.koff = 0;
+    StageTimer t(ST_YB);
+    if (int rc = run_y<false>(sp->py, W1, n1, n3l, sg)) return rc;
+  }
+  { StageTimer t(ST_XB); if (int rc = run_x<false>(sp->px, W1, gw, pd, gp, normfft)) return rc; }
 
   if (host_p) {
     CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));

@@ -98,7 +98,7 @@ xfft_p2_kernel(LinePlan P, const double* __restrict__ src, LineGeom gs, double* 
 
 template <int N, int TB, bool FWD>
 __global__ void __launch_bounds__(256, (N * TB * 8 <= 72 * 1024) ? 3 : 1)
-yfft_p2_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
+yfft_p2_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i, SpecGeom sg) {
   constexpr int M = N / 2, NP = p2_npass(M);
   extern __shared__ double tile[];
   const int kind = P.kind;
@@ -110,7 +110,9 @@ yfft_p2_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
   const int i0 = ti * TB;
   const int lane = tid & (TB - 1), worker = tid / TB;
   const bool live = (i0 + lane) < n1;
-  double* base = W + (long)n1 * N * k + i0 + (live ? lane : 0);
+  const int il = i0 + (live ? lane : 0);
+  double* base = W + (long)n1 * N * k + il;               // physical side
+  double* sbase = spec_base(sg, il, N, k);                 // spectral side (pencil chunk of the exchange)
 
   stage_twiddles(s_w, P.wM, M, tid, nthr);
   __syncthreads();
@@ -122,10 +124,10 @@ yfft_p2_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
     p2_tile_pass<M, 1, true, TB, false>(tile, s_w, lane, worker, NW);
     p2_tile_pass<M, 2, true, TB, false>(tile, s_w, lane, worker, NW);
     p2_tile_pass<M, 3, true, TB, false>(tile, s_w, lane, worker, NW);
-    const SpecAcc gout{base, (long)n1, M, live};
+    const SpecAcc gout{sbase, (long)sg.n1l, M, live};
     split_core(M, kind, P.wN, P.wQ, P.pos, worker, NW, acc, gout);   // smem -> split -> global
   } else {
-    const SpecAcc gin{base, (long)n1, M, live};
+    const SpecAcc gin{sbase, (long)sg.n1l, M, live};
     merge_core(M, kind, P.wN, P.wQ, P.pos, worker, NW, gin, acc);    // global -> merge -> smem
     __syncthreads();
     p2_tile_pass<M, 3, false, TB, false>(tile, s_w, lane, worker, NW);
@@ -156,18 +158,19 @@ inline cudaError_t p2_launch_x(bool fwd, const LinePlan& P, const double* src, L
 }
 
 template <int N, int TB>
-inline cudaError_t p2_launch_y(bool fwd, const LinePlan& P, double* W, int n1, long n3, cudaStream_t st) {
+inline cudaError_t p2_launch_y(bool fwd, const LinePlan& P, double* W, int n1, long n3, const SpecGeom& sg,
+                               cudaStream_t st) {
   const size_t smem = fft_smem_bytes<TB>(N);
   const int nti = (n1 + TB - 1) / TB;
   cudaError_t e;
   if (fwd) {
     e = cudaFuncSetAttribute(yfft_p2_kernel<N, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    yfft_p2_kernel<N, TB, true><<<(unsigned)(nti * n3), 256, smem, st>>>(P, W, n1, nti);
+    yfft_p2_kernel<N, TB, true><<<(unsigned)(nti * n3), 256, smem, st>>>(P, W, n1, nti, sg);
   } else {
     e = cudaFuncSetAttribute(yfft_p2_kernel<N, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    yfft_p2_kernel<N, TB, false><<<(unsigned)(nti * n3), 256, smem, st>>>(P, W, n1, nti);
+    yfft_p2_kernel<N, TB, false><<<(unsigned)(nti * n3), 256, smem, st>>>(P, W, n1, nti, sg);
   }
   return cudaGetLastError();
 }

@@ -15,5 +15,5 @@ inline int p2_tile_width(int N) {
 }
 cudaError_t p2_run_x(bool fwd, const LinePlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                      cudaStream_t st);
-cudaError_t p2_run_y(bool fwd, const LinePlan& P, double* W, int n1, long n3, cudaStream_t st);
+cudaError_t p2_run_y(bool fwd, const LinePlan& P, double* W, int n1, long n3, const SpecGeom& sg, cudaStream_t st);
 }  // namespace fb

@@ -18,6 +18,31 @@ __device__ __forceinline__ long line_offset(const LineGeom& g, long line) {
   return g.off0 + j * g.sj + k * g.sk;
 }
 
+// Spectral side of the y stage.  On one GPU this is the work array itself; on a z-slab decomposition
+// it is the x-split "pencil" layout of the exchange: element (i, row, k) of the slab lives in chunk
+// q = i / n1l at ptr[q][koff + (i - q*n1l) + n1l*(row + N*k)].  ptr[q] is a send/receive buffer (NCCL
+// path) or rank q's pencil buffer mapped through CUDA IPC (direct NVLink stores/loads).
+// Reference counterpart: the pack/unpack loops of transpose_x_to_z / transpose_z_to_x
+// (src/2decomp/transpose_x_to_z.f90:45-142, transpose_z_to_x.f90:15-163), fused here into the kernels.
+enum { FB_MAX_RANKS = 8 };
+struct SpecGeom {
+  double* ptr[FB_MAX_RANKS];
+  int n1l;       // x rows per chunk (n1 on one GPU)
+  long koff;     // offset of this rank's k-range inside the destination chunk
+};
+__device__ __forceinline__ double* spec_base(const SpecGeom& g, int i, int N, long k) {
+  const int q = i / g.n1l;
+  return g.ptr[q] + g.koff + (i - q * g.n1l) + (long)g.n1l * N * k;
+}
+
+// Output side of the z stage: column `col`, level k goes to chunk q = k / n3l at
+// ptr[q][koff + col + ncol*(k - q*n3l)] (one GPU: ptr[0] = the work array, n3l = nz, koff = 0).
+struct ColGeom {
+  double* ptr[FB_MAX_RANKS];
+  int n3l;
+  long koff;
+};
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout of the transform kernels: [tile: N*TB doubles][wM: M cpx][line offsets: TB longs]
 // The pass twiddles wM are staged in shared memory (they are read 7x per radix-8 butterfly and global

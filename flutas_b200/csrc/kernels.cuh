@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(256, 3) xfft_kernel(LinePlan P, const double* 
 // y direction, in place on the dense work array W(n1, N, n3).  One block = lanes i0..i0+TB-1 of one
 // k plane, all N rows.  Global accesses are TB*8 contiguous bytes per row, YU rows in flight per thread.
 template <int TB, bool FWD>
-__global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i) {
+__global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __restrict__ W, int n1, int ntile_i,
+                                                      SpecGeom sg) {
   constexpr int YU = 8;
   extern __shared__ double tile[];
   const int N = P.N, M = P.M, kind = P.kind;
@@ -101,7 +102,11 @@ __global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __rest
   const int i0 = ti * TB;
   const int lane = tid & (TB - 1), worker = tid / TB, nworkers = nthr / TB;
   const bool live = (i0 + lane) < n1;
-  double* base = W + (long)n1 * N * k + i0 + (live ? lane : 0);
+  const int il = i0 + (live ? lane : 0);
+  double* pbase = W + (long)n1 * N * k + il;            // physical side: element e at pbase[e*n1]
+  double* sbase = spec_base(sg, il, N, k);              // spectral side: row r at sbase[r*sg.n1l]
+  const double* base = FWD ? pbase : sbase;
+  const long ldi = FWD ? (long)n1 : (long)sg.n1l;
 
   stage_twiddles(s_w, P.wM, M, tid, nthr);
   for (int e0 = worker; e0 < N; e0 += YU * nworkers) {
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __rest
 #pragma unroll
     for (int u = 0; u < YU; ++u) {
       const int e = e0 + u * nworkers;
-      v[u] = (e < N) ? __ldcs(base + (long)e * n1) : 0.0;
+      v[u] = (e < N) ? __ldcs(base + (long)e * ldi) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < YU; ++u) {
@@ -128,6 +133,8 @@ __global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __rest
   tile_transform<TB, false, FWD>(tile, P, s_w, lane, worker, nworkers);
 
   if (!live) return;
+  double* obase = FWD ? sbase : pbase;
+  const long ldo = FWD ? (long)sg.n1l : (long)n1;
   for (int e0 = worker; e0 < N; e0 += YU * nworkers) {
     double v[YU];
 #pragma unroll
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(256, 3) yfft_kernel(LinePlan P, double* __rest
 #pragma unroll
     for (int u = 0; u < YU; ++u) {
       const int e = e0 + u * nworkers;
-      if (e < N) __stcs(base + (long)e * n1, v[u]);
+      if (e < N) __stcs(obase + (long)e * ldo, v[u]);
     }
   }
 }

@@ -190,6 +190,8 @@ struct ThomasTile {
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 
+#include "geom.cuh"
+
 namespace fb {
 
 #ifndef FB_THOMAS_MINB
@@ -197,7 +199,7 @@ namespace fb {
 #endif
 template <int L, int TI>
 __global__ void __launch_bounds__(TI * 32, (L <= 16) ? FB_THOMAS_MINB : 2) thomas_tile_kernel(long ncol, ThomasArgs T, const double* __restrict__ lam,
-                                                              double* __restrict__ W) {
+                                                              double* __restrict__ W, ColGeom og) {
   using TT = ThomasTile<L, TI>;
   extern __shared__ double smem[];
   const int nz = T.nz, S = T.S;
@@ -283,21 +285,28 @@ __global__ void __launch_bounds__(TI * 32, (L <= 16) ? FB_THOMAS_MINB : 2) thoma
 #pragma unroll
       for (int u = 0; u < LU; ++u) { const int k = min(k0 + u * S, nz - 1); v[u] = tile[TT::prow(k) * TI + lane]; }
 #pragma unroll
-      for (int u = 0; u < LU; ++u) { const int k = k0 + u * S; if (k < nz) __stcs(base + (long)k * ncol, v[u]); }
+      for (int u = 0; u < LU; ++u) {
+        const int k = k0 + u * S;
+        if (k < nz) {
+          const int q = k / og.n3l;
+          __stcs(og.ptr[q] + og.koff + col0 + lane + ncol * (long)(k - q * og.n3l), v[u]);
+        }
+      }
     }
   }
   (void)nthr;
 }
 
 template <int L, int TI>
-inline cudaError_t thomas_tile_launch(long ncol, const ThomasArgs& T, const double* lam, double* W, cudaStream_t st) {
+inline cudaError_t thomas_tile_launch(long ncol, const ThomasArgs& T, const double* lam, double* W, const ColGeom& og,
+                                      cudaStream_t st) {
   using TT = ThomasTile<L, TI>;
   auto kern = thomas_tile_kernel<L, TI>;
   const size_t smem = TT::smem_doubles(T.nz) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long nblk = (ncol + TI - 1) / TI;
-  kern<<<(unsigned)nblk, TI * T.S, smem, st>>>(ncol, T, lam, W);
+  kern<<<(unsigned)nblk, TI * T.S, smem, st>>>(ncol, T, lam, W, og);
   return cudaGetLastError();
 }
 
@@ -319,20 +328,23 @@ inline bool thomas_tile_pick(int nz, bool periodic, int* Lout) {
 }
 
 inline int thomas_tile_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam,
-                           double* W, bool periodic, int singular, cudaStream_t st, bool* done) {
+                           double* W, const ColGeom* out, bool periodic, int singular, cudaStream_t st, bool* done) {
   *done = false;
   int L = 0;
   if (!thomas_tile_pick(nz, periodic, &L)) return 0;
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
   T.padded = 0;
+  ColGeom og;
+  if (out) og = *out;
+  else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = W; og.n3l = nz; og.koff = 0; }
   cudaError_t e = cudaSuccess;
   switch (L) {
-    case 2: e = thomas_tile_launch<2, 8>(ncol, T, lam, W, st); break;
-    case 4: e = thomas_tile_launch<4, 8>(ncol, T, lam, W, st); break;
-    case 8: e = thomas_tile_launch<8, 8>(ncol, T, lam, W, st); break;
-    case 16: e = thomas_tile_launch<16, 8>(ncol, T, lam, W, st); break;
-    default: e = thomas_tile_launch<32, 8>(ncol, T, lam, W, st); break;
+    case 2: e = thomas_tile_launch<2, 8>(ncol, T, lam, W, og, st); break;
+    case 4: e = thomas_tile_launch<4, 8>(ncol, T, lam, W, og, st); break;
+    case 8: e = thomas_tile_launch<8, 8>(ncol, T, lam, W, og, st); break;
+    case 16: e = thomas_tile_launch<16, 8>(ncol, T, lam, W, og, st); break;
+    default: e = thomas_tile_launch<32, 8>(ncol, T, lam, W, og, st); break;
   }
   if (e != cudaSuccess) return (int)e;
   *done = true;

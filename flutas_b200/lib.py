@@ -42,6 +42,12 @@ def load():
     L.flutas_b200_updt_rhs_b.argtypes = [ci] * 3 + [cc, vp, vp, vp, vp]
     L.flutas_b200_correc.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp, vp]
     L.flutas_b200_chkdiv.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] * 4 + [_dp, _dp]
+    L.flutas_b200_set_alltoall.argtypes = [vp, vp]
+    L.flutas_b200_p2p_handle_bytes.restype = C.c_size_t
+    L.flutas_b200_p2p_export.argtypes = [C.POINTER(vp), ip, vp]
+    L.flutas_b200_p2p_attach.argtypes = [C.POINTER(vp), vp]
+    L.flutas_b200_p2p_errors.argtypes = [C.POINTER(vp)]
+    L.flutas_b200_solver_slab.argtypes = [ip, C.POINTER(vp), cd, vp, vp, vp, vp, cc, cc, vp]
     L.flutas_b200_profile_enable.argtypes = [ci]
     L.flutas_b200_profile_stage_name.restype = cc
     L.flutas_b200_profile_stage_name.argtypes = [ci]
@@ -61,5 +67,7 @@ EXPORTS = [
     "flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_solver_invalidate",
     "flutas_b200_fillps", "flutas_b200_updt_rhs_b", "flutas_b200_correc", "flutas_b200_chkdiv",
     "flutas_b200_launch_count", "flutas_b200_profile_enable", "flutas_b200_profile_stage_count",
-    "flutas_b200_profile_stage_name", "flutas_b200_profile_read",
+    "flutas_b200_profile_stage_name", "flutas_b200_profile_read", "flutas_b200_set_alltoall",
+    "flutas_b200_p2p_handle_bytes", "flutas_b200_p2p_export", "flutas_b200_p2p_attach", "flutas_b200_p2p_errors",
+    "flutas_b200_solver_slab",
 ]

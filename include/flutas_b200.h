@@ -71,6 +71,37 @@ int flutas_b200_solver(const int n[3], void *const arrplan[4], double normfft, c
                        const char c_or_f[3], double *p);
 int flutas_b200_solver_invalidate(void *const arrplan[4]);
 
+/* ---- multi-GPU: z-slab decomposition over the GPUs of one NVSwitch box ------------------------------
+ * Layout = the reference's _DECOMP_X with dims_in = (1, nranks): every rank holds p(0:ng1+1, 0:ng2+1,
+ * 0:ng3/nranks+1).  x and y transforms are rank-local; the two exchanges of the reference GPU slab
+ * path (transpose_xc_to_z / transpose_z_to_xc, src/2decomp/transpose_x_to_z.f90:15-166,
+ * transpose_z_to_x.f90:15-163, called at src/solver_gpu.f90:150-153,179-182) are either
+ *   (a) a host-supplied all-to-all on device buffers (NCCL / CUDA-aware MPI) -- the pack is fused into
+ *       the y-transform store and the unpack into the inverse y-transform load, or
+ *   (b) direct NVLink stores into the peers' buffers (CUDA IPC mappings) from inside the y-transform
+ *       and Thomas kernels, ordered by two flag barriers per solve: no collective call on the data path.
+ * The all-to-all callback moves `bytes_per_peer` bytes from sendbuf + q*bytes_per_peer to rank q and
+ * receives rank q's block at recvbuf + q*bytes_per_peer, enqueued on `cuda_stream`; returns 0 on success. */
+typedef int (*flutas_b200_alltoall_fn)(void *ctx, const void *sendbuf, void *recvbuf, size_t bytes_per_peer,
+                                       void *cuda_stream);
+int flutas_b200_set_alltoall(flutas_b200_alltoall_fn fn, void *ctx);
+
+/* (b): export allocates this rank's exchange memory for the plan and writes an opaque blob of
+ * flutas_b200_p2p_handle_bytes() bytes; the host all-gathers the blobs (MPI_Allgather / torch.distributed)
+ * and passes all nranks of them, in rank order, to attach.  p2p_errors returns the number of barrier
+ * time-outs observed (0 when healthy). */
+size_t flutas_b200_p2p_handle_bytes(void);
+int flutas_b200_p2p_export(void *const arrplan[4], const int n_local[3], void *blob);
+int flutas_b200_p2p_attach(void *const arrplan[4], const void *blobs);
+int flutas_b200_p2p_errors(void *const arrplan[4]);
+
+/* solver on a z-slab: as flutas_b200_solver, with n = the LOCAL interior size (ng1, ng2, ng3/nranks) and
+ * lambdaxy_global = lambdaxy(ng1, ng2) for the whole x-y plane (the shim all-gathers the (ng1, ng2/nranks)
+ * windows initsolver produces on each rank, src/initsolver.f90:87-93; done once).  Collective. */
+int flutas_b200_solver_slab(const int n[3], void *const arrplan[4], double normfft, const double *lambdaxy_global,
+                            const double *a, const double *b, const double *c, const char bcz[2],
+                            const char c_or_f[3], double *p);
+
 /* fillps, src/fillps.f90:16-69 (with _CONSTANT_COEFFS_POISSON: the result is multiplied by rho0). */
 int flutas_b200_fillps(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, double dyi, double dzi,
                        const double *dzfi, double dti, double rho0, const double *u, const double *v,

@@ -1,0 +1,82 @@
+"""Launched by torchrun (one process per GPU): multi-GPU slab solve vs the single-rank oracle.
+usage: torchrun --nproc-per-node N tests/slab_gpu_worker.py [nccl|p2p] """
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from flutas_b200 import api, slab  # noqa: E402
+from flutas_b200.cases import Case  # noqa: E402
+from oracle import oracle  # noqa: E402
+from util import gauge_rel_err  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lrank)
+    dist.init_process_group("nccl")
+    api.init(lrank, rank, world)
+    comm = slab.SlabComm()
+    ok = True
+    for name, ng, cbc, gr in (("chan", (128, 64, 32), ("PP", "PP", "NN"), 1.0), ("hit", (64, 64, 64), ("PP", "PP", "PP"), 0.0),
+                              ("rb", (64, 48, 40), ("NN", "NN", "NN"), 0.0), ("dd72", (32, 40, 72), ("DD", "NN", "DD"), 0.0)):
+        if ng[0] % world or ng[2] % world or ng[1] % world:
+            continue
+        case = Case(ng, cbc, (2.0, 1.0, 1.0), gr=gr, seed=77)
+        s = case.setup
+        n1, n2, n3 = ng
+        n3l = n3 // world
+        k0, k1 = slab.local_levels(n3, rank, world)
+        u, v, w = case.velocity()
+        pg = case.new_p()
+        oracle.fillps(ng, case.nh_d, case.nh_u, s.dli, s.dzfi, case.dti, case.rho0, u, v, w, pg)
+        pref = pg.copy(order="F")
+        oracle.Solver(ng, cbc[0], cbc[1]).solve(s.lambdaxy, s.a, s.b, s.c, cbc[2], pref)
+        pl = np.zeros((n1 + 2, n2 + 2, n3l + 2), order="F")
+        pl[1:-1, 1:-1, 1:-1] = pg[1:-1, 1:-1, 1 + k0:1 + k1]
+        nl = (n1, n2, n3l)
+        plan, nf = api.fftini(nl, nl, (cbc[0], cbc[1]))
+        if mode == "p2p":
+            comm.use_p2p(plan, nl)
+        else:
+            comm.use_nccl_alltoall()
+        j0, j1 = rank * (n2 // world), (rank + 1) * (n2 // world)
+        lam_win = np.asfortranarray(s.lambdaxy[:, j0:j1])
+        pd = api.device_field(pl)
+        for _ in range(3):                                   # repeated solves exercise the barrier epochs
+            pd.copy_(api.device_field(pl))
+            comm.solver(nl, plan, nf, lam_win, s.a, s.b, s.c, cbc[2], "ccc", pd)
+        torch.cuda.synchronize()
+        got = api.host_field(pd, pl.shape)[1:-1, 1:-1, 1:-1]
+        # gauge: compare after removing the GLOBAL mean (all-reduce of the local sums)
+        ref = pref[1:-1, 1:-1, 1 + k0:1 + k1]
+        if case.singular:
+            sums = torch.tensor([got.sum(), ref.sum()], dtype=torch.float64, device="cuda")
+            dist.all_reduce(sums)
+            got = got - sums[0].item() / (n1 * n2 * n3)
+            ref = ref - sums[1].item() / (n1 * n2 * n3)
+        errs = torch.tensor([np.max(np.abs(got - ref)), np.max(np.abs(ref))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        err = errs[0].item() / errs[1].item()
+        nerr = comm.p2p_errors(plan) if mode == "p2p" else 0
+        if rank == 0:
+            print("slab %s x%d %-5s %s %s: max|dp|/max|p| = %.2e barrier_timeouts=%d" % (mode, world, name, ng, "/".join(cbc), err, nerr),
+                  flush=True)
+        ok = ok and err <= 1e-12 and nerr == 0
+        api.fftend(plan)
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+    if rank == 0:
+        print("SLAB_OK", mode, world, flush=True)
+
+
+if __name__ == "__main__":
+    main()

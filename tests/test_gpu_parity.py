@@ -164,3 +164,22 @@ def test_device_resident_step_and_linearity():
     res = np.max(np.abs(case.laplacian(p) - r1)) / np.max(np.abs(r1))
     assert res <= 1e-10, res
     api.fftend(pl)
+
+
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_multi_gpu_slab_solver(mode):
+    """N>1: z-slab decomposition, one process per GPU (torchrun), both exchange implementations."""
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 4 if ngpu >= 4 else 2
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "slab_gpu_worker.py"), mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0 and "SLAB_OK" in out.stdout
