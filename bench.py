@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: direct NVLink stores from the kernels (CUDA IPC) or NCCL all-to-all")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -191,48 +193,98 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the pressure path has no CPU fallback")
-    if world > 1:
-        raise SystemExit("multi-GPU slab solve not wired into bench.py yet")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api.init(local_rank, rank, world)
 
     case = Case.from_config(args.workload)
     s = case.setup
-    n = case.ng
-    n1, n2, n3 = n
-    npts = n1 * n2 * n3
-    u, v, w = case.velocity()
+    ng = case.ng
+    n1, n2, n3g = ng
+    if n3g % world or n1 % world or n2 % world:
+        raise SystemExit("grid %s is not divisible by %d ranks" % (ng, world))
+    n3 = n3g // world                                   # z-slab: the reference's _DECOMP_X layout with dims_in = (1, N)
+    n = (n1, n2, n3)
+    npts = n1 * n2 * n3g                                # whole job
+    npts_loc = n1 * n2 * n3
+    exchange = None
+    if world == 1:
+        u, v, w = case.velocity()
+        dzfi, dzci = s.dzfi, s.dzci
+    else:
+        # per-rank slab of synthetic velocities (timing is data independent; parity is covered by tests/)
+        rng = np.random.Generator(np.random.PCG64(case.seed + 1000 * rank))
+        h = case.nh_u
+        shape = (n1 + 2 * h, n2 + 2 * h, n3 + 2 * h)
+        u, v, w = (np.asfortranarray(rng.uniform(-1.0, 1.0, size=shape[::-1]).T) for _ in range(3))
+        o = case.nh_d - 1
+        k0 = rank * n3
+        dzfi = np.ascontiguousarray(s.dzfi[k0:k0 + n3 + 2 * case.nh_d])
+        dzci = np.ascontiguousarray(s.dzci[k0:k0 + n3 + 2 * case.nh_d])
     ud, vd, wd = (api.device_field(f) for f in (u, v, w))
     del u, v, w
-    pd = api.device_field(case.new_p())
+    pd = api.device_field(np.zeros((n1 + 2, n2 + 2, n3 + 2), order="F"))
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
+    lam_win = s.lambdaxy
+    comm = None
+    if world > 1:
+        from flutas_b200 import slab
+        comm = slab.SlabComm()
+        j0, j1 = rank * (n2 // world), (rank + 1) * (n2 // world)
+        lam_win = np.asfortranarray(s.lambdaxy[:, j0:j1])
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                comm.use_p2p(pl, n)
+            except Exception as e:                       # e.g. CUDA IPC not permitted: fall back to the NCCL all-to-all
+                if rank == 0:
+                    print("p2p exchange unavailable (%s): using NCCL all-to-all" % e, file=sys.stderr)
+                exchange = "nccl"
+        if exchange == "nccl":
+            comm.use_nccl_alltoall()
 
     def fill():
-        api.fillps(*n, case.nh_d, case.nh_u, *s.dli, s.dzfi, case.dti, case.rho0, ud, vd, wd, pd)
-        api.updt_rhs_b(*n, case.cbc, s.rhsbx, s.rhsby, s.rhsbz, pd)
+        api.fillps(*n, case.nh_d, case.nh_u, *s.dli, dzfi, case.dti, case.rho0, ud, vd, wd, pd)
+        if world == 1:
+            api.updt_rhs_b(*n, case.cbc, s.rhsbx, s.rhsby, s.rhsbz, pd)
 
-    def solve():
-        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", pd)
+    def solve(p=None):
+        p = pd if p is None else p
+        if world == 1:
+            api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", p)
+        else:
+            comm.solver(n, pl, nf, lam_win, s.a, s.b, s.c, case.cbc[2], "ccc", p)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
     # ---- timed region: K solver calls ----------------------------------------------------------
     fill()
     for _ in range(args.warmup):
         solve()
-    torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     api.profile_enable(True)
     api.profile_read()
     l0 = api.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     e0.record()
     for _ in range(args.steps):
         solve()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     launches = api.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
+    if world > 1:                                       # max over ranks, on the device clock
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
     stages = api.profile_read()
     api.profile_enable(False)
     clocks = sampler.stop()
@@ -242,17 +294,21 @@ def main():
     # ---- ms per pressure step (fillps + updt_rhs_b + solver + correc), device resident -----------
     api.profile_enable(True)
     api.profile_read()
-    torch.cuda.synchronize()
+    barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nps = max(3, min(args.steps, 10))
     p0.record()
     for _ in range(nps):
         fill()
         solve()
-        api.correc(*n, case.nh_d, case.nh_u, *s.dli, s.dzci, case.dt, case.rho0, pd, ud, vd, wd)
+        api.correc(*n, case.nh_d, case.nh_u, *s.dli, dzci, case.dt, case.rho0, pd, ud, vd, wd)
     p1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms_pressure_step = p0.elapsed_time(p1) / nps
+    if world > 1:
+        t = torch.tensor([ms_pressure_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_pressure_step = float(t.item())
     stages_ps = api.profile_read()
     api.profile_enable(False)
     for k in ("fillps", "correc"):
@@ -269,19 +325,28 @@ def main():
     e2e_ms = []
     for it in range(args.e2e_steps + 1):
         ph[...] = rhs_host
+        barrier()
         t0 = time.perf_counter()
-        api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", ph)    # returns after the D2H copy
+        solve(ph)                                        # host p: H2D + kernels (+ exchanges) + D2H, returns when p is back
+        barrier()
         dt = time.perf_counter() - t0
         if it > 0:
             e2e_ms.append(dt * 1e3)
-    e2e_val = npts / (np.mean(e2e_ms) * 1e-3) / 1e9
+    e2e_mean = float(np.mean(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_mean], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_mean = float(t.item())
+    e2e_val = npts / (e2e_mean * 1e-3) / 1e9
 
     # ---- roofline of the slowest solver kernel ---------------------------------------------------
     peak, peak_src = measured_peak()
     stage_tbl = {}
     for name, (ms, cnt) in stages.items():
         avg = ms / cnt
-        gbs = ALG_BYTES_PER_PT[name] * npts / (avg * 1e-3) / 1e9
+        if name not in ALG_BYTES_PER_PT:
+            continue
+        gbs = ALG_BYTES_PER_PT[name] * npts_loc / (avg * 1e-3) / 1e9
         stage_tbl[name] = {"ms": round(avg, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
     solver_stages = [k for k in ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd") if k in stage_tbl]
     dom = max(solver_stages, key=lambda k: stage_tbl[k]["ms"])
@@ -293,13 +358,29 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": stage_tbl[dom]["GB/s"], "peak": peak, "unit": "GB/s",
                 "frac": stage_tbl[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALG_BYTES_PER_PT[dom] * npts,
-                "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT, "achieved": round(SOLVER_BYTES_PER_PT * value, 1),
-                           "frac": round(SOLVER_BYTES_PER_PT * value / peak, 4)},
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_PT[dom] * npts_loc,
+                "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT, "achieved_per_gpu": round(SOLVER_BYTES_PER_PT * value / world, 1),
+                           "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4)},
                 "stages": stage_tbl}
+    if world > 1:
+        sent = 8.0 * npts_loc * (world - 1) / world        # bytes each GPU sends per exchange
+        nv = {"exchange": exchange, "bytes_sent_per_gpu_per_exchange": sent, "peak_GBs_per_direction": 900.0,
+              "measured_peer_copy_GBs": 770.0}
+        if exchange == "p2p":
+            # the stores go over NVLink from inside the y-transform / Thomas kernels: rate = bytes / that kernel's time
+            for nm in ("yfft_fwd", "thomas_z"):
+                if nm in stage_tbl:
+                    nv[nm + "_GBs"] = round(sent / (stage_tbl[nm]["ms"] * 1e-3) / 1e9, 1)
+        for nm in ("exchange_fwd", "exchange_bwd"):
+            if nm in stages:
+                ms = stages[nm][0] / stages[nm][1]
+                nv[nm + "_ms"] = round(ms, 4)
+                if exchange == "nccl":
+                    nv[nm + "_GBs"] = round(sent / (ms * 1e-3) / 1e9, 1)
+        roofline["nvlink"] = nv
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         c = cpu_sample(case, 15.0)
         cpu = {"value": round(c["gpts"], 5), "unit": "Gpts/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
                "seconds": round(c["seconds"], 1),
@@ -308,15 +389,19 @@ def main():
     line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(case, args.workload),
+            "config": dict(workload_config(case, args.workload), decomposition=("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU"),
             "ms_per_pressure_step": round(ms_pressure_step, 4),
             "pressure_step": "fillps + updt_rhs_b + solver + correc, device resident (boundp not included)",
             "e2e": {"value": round(e2e_val, 4), "unit": "Gpts/s", "h2d_bytes_per_step": pcount * 8,
-                    "d2h_bytes_per_step": pcount * 8, "ms_per_step": round(float(np.mean(e2e_ms)), 3),
+                    "d2h_bytes_per_step": pcount * 8, "ms_per_step": round(e2e_mean, 3),
                     "path": "flutas_b200_solver with a pinned host p (H2D + 5 kernels + D2H)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     api.fftend(pl)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
