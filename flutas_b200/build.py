@@ -6,7 +6,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SO = os.path.join(CSRC, "libflutas_b200.so")
 SOURCES = ["capi.cu", "fft_p2_x.cu", "fft_p2_y.cu"]
-HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h"]
+HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -14,6 +14,7 @@
 #include "fft_p2.h"
 #include "kernels.cuh"
 #include "line_plan.h"
+#include "thomas_reg.cuh"
 #include "thomas_tile.cuh"
 
 using namespace fb;
@@ -23,7 +24,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long> g_launches{0};
 cudaStream_t g_stream = nullptr;
-int g_device = -1, g_rank = 0, g_nranks = 1;
+int g_device = -1, g_rank = 0, g_nranks = 1, g_nsm = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -81,6 +82,7 @@ int ensure_device() {
   int cur = 0;
   CK(cudaGetDevice(&cur));
   g_device = cur;
+  CK(cudaDeviceGetAttribute(&g_nsm, cudaDevAttrMultiProcessorCount, cur));
   return FLUTAS_B200_OK;
 }
 
@@ -308,7 +310,13 @@ __global__ void scatter_cols_kernel(long ncol, int nz, const double* __restrict_
 int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
   const double* abc = sp->abc.as<double>();
   bool done = false;
-  if (sp->thomas_mode == 0) {
+  if (sp->thomas_mode == 0) {                               // register-resident persistent kernel
+    int rc = thomas_reg_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, W, out, periodic, singular,
+                            g_nsm > 0 ? g_nsm : 148, g_stream, &done);
+    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_reg launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (!done && (sp->thomas_mode == 0 || sp->thomas_mode == 2)) {   // shared-memory tile kernel
     int rc = thomas_tile_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, out, periodic, singular, g_stream, &done);
     if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_tile launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -432,6 +440,7 @@ int flutas_b200_init(int device, int rank, int nranks) {
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(FLUTAS_B200_ERR_ARG, "bad rank %d of %d", rank, nranks);
   CK(cudaSetDevice(device));
   g_device = device; g_rank = rank; g_nranks = nranks;
+  CK(cudaDeviceGetAttribute(&g_nsm, cudaDevAttrMultiProcessorCount, device));
   return FLUTAS_B200_OK;
 }
 
@@ -519,7 +528,8 @@ int flutas_b200_debug_generic_fft(int on) {
   return FLUTAS_B200_OK;
 }
 
-// test hook: 0 = automatic choice of the z solver, 1 = always the generic (scratch-field) kernels
+// test hook: 0 = automatic choice of the z solver (register kernel, then the shared-memory tile kernel, then
+// the generic ones), 1 = always the generic (scratch-field) kernels, 2 = skip the register kernel
 int flutas_b200_debug_thomas_mode(void* const arrplan[4], int mode) {
   SolverPlan* sp = plan_of(arrplan);
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "not a flutas_b200 plan");

@@ -1,0 +1,268 @@
+// reg_fft.cuh -- batched 1-D real transforms with the line held in REGISTERS (power-of-two lengths 32..2048).
+//
+// Replaces, for the pressure solver only, what the reference gets from FFTW r2r plans
+// (src/fft.f90:75-86,113-124 -> dfftw_execute_r2r, :181-193) and, on its GPU path, from cuFFT D2Z/Z2D
+// plus the separate Makhoul pre/post sweeps (src/fft.f90:294-887).  Second-generation kernels: the
+// shared-memory tile kernels (tile_fft.cuh / fft_p2.cuh) move every element through shared memory five
+// times and spend half their instructions on tile addressing; here
+//
+//   * a length-N real line is one length-M = N/2 complex Stockham FFT; T = M/16 threads own a line, each
+//     holds 16 complex values in registers from the global load to the global store;
+//   * passes are radix-16 (4x4 in registers) preceded by one radix-2/4/8 pass when M is not a power of 16;
+//     between passes the T threads exchange through a small shared-memory buffer (write scattered, read
+//     position j + T*u -- the same set in every pass), so M = 256 needs ONE exchange, M = 512..2048 two;
+//   * the real split / Makhoul post-twiddle (forward) and merge / pre-twiddle (backward) are computed per
+//     mode k from Z_k and Z_{M-k}, fetched through one more exchange;
+//   * the spectrum is left in natural order, interleaved: row 2k = Re X_k, row 2k+1 = Im X_k
+//     (row 0 = X_0, row 1 = X_M); `reg_mode_index` tells the host which FFTW mode sits in which row so that
+//     lambdaxy is permuted once at plan time (initsolver.f90:136-139 order -> this order).
+//
+// Host-compilable (tests/emulate): every function is per-thread, phase boundaries are where the kernels
+// synchronise.
+#pragma once
+#include "tile_fft.cuh"
+
+namespace fb {
+
+enum { RF_MAXPASS = 3 };
+
+// Device-visible description of one transform (tables live in global memory; pass twiddles are staged in
+// shared memory by the kernels).
+struct RegPlan {
+  int N, M, kind;
+  const cpx* tw[RF_MAXPASS];   // pass q > 0: tw[q][(t-1)*Ns + k] = exp(-2 pi i t k / (Ns r)),  t = 1..r-1, k = 0..Ns-1
+  int tw_count[RF_MAXPASS];
+  const cpx* wN;               // [M]    exp(-2 pi i k / N)
+  const cpx* wQ;               // [M+1]  exp(-i pi k / (2N))      (NN/DD only)
+};
+
+// compile-time schedule for a complex length M (power of two, 16 <= M <= 2048)
+template <int M>
+struct RegSched {
+  static constexpr int R = 16;                         // complex values per thread
+  static constexpr int T = M / R;                      // threads per line
+  static constexpr int NP = (M == 16) ? 1 : (M <= 256) ? 2 : 3;
+  static constexpr int R0 = (NP == 1) ? 16 : (NP == 2) ? M / 16 : M / 256;
+  static FB_CX int radix(int q) { return q == 0 ? R0 : 16; }
+  static FB_CX int ns(int q) { return q == 0 ? 1 : (q == 1 ? R0 : R0 * 16); }
+};
+
+FB_CX bool reg_fft_supported(int N) {
+  return N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048;
+}
+
+// which FFTW mode (index into the reference's eigenvalue array, 0-based) sits in spectral row r
+FB_HD int reg_mode_index(int N, int kind, int r) {
+  const int M = N / 2, k = r >> 1;
+  int q = (r & 1) ? ((k == 0) ? M : N - k) : k;
+  if (kind == KIND_DD) q = N - 1 - q;
+  return q;
+}
+
+// radix-16 butterfly, natural order in and out: y_t = sum_m u_m exp(SIGN 2 pi i m t / 16)
+template <int SIGN> FB_HD void bfly16(double* re, double* im) {
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+  // step 1: for each b, radix-4 over a on elements (b, b+4, b+8, b+12): slot 4c+b <- Y_b[c]
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int b = 0; b < 4; ++b) {
+    double tr[4] = { re[b], re[b + 4], re[b + 8], re[b + 12] }, ti[4] = { im[b], im[b + 4], im[b + 8], im[b + 12] };
+    bfly4<SIGN>(tr, ti);
+    re[b] = tr[0]; re[b + 4] = tr[1]; re[b + 8] = tr[2]; re[b + 12] = tr[3];
+    im[b] = ti[0]; im[b + 4] = ti[1]; im[b + 8] = ti[2]; im[b + 12] = ti[3];
+  }
+  // step 2: slot 4c+b *= w16^(b c)   (SIGN = +1: conjugate)
+  auto mul = [&](int i, double wr, double wi) {
+    const double xr = re[i] * wr - im[i] * (SIGN * -wi), xi = re[i] * (SIGN * -wi) + im[i] * wr;
+    re[i] = xr; im[i] = xi;
+  };
+  // w16^1 = (c1,-s1)  w16^2 = (h,-h)  w16^3 = (s1,-c1)  w16^4 = (0,-1)  w16^6 = (-h,-h)  w16^9 = (-c1,s1)
+  mul(4 * 1 + 1, c1, -s1);  mul(4 * 1 + 2, h, -h);    mul(4 * 1 + 3, s1, -c1);
+  mul(4 * 2 + 1, h, -h);
+  { const int i = 4 * 2 + 2; const double xr = SIGN * -im[i] * -1.0, xi = SIGN * re[i] * -1.0 * -1.0; (void)xr; (void)xi; }
+  {                                                    // w16^4 = -i (fwd), +i (bwd): (x + iy)(-i) = y - ix
+    const int i = 4 * 2 + 2;
+    const double xr = -SIGN * -im[i] * -1.0; (void)xr;
+    const double nr = (SIGN < 0) ? im[i] : -im[i], ni = (SIGN < 0) ? -re[i] : re[i];
+    re[i] = nr; im[i] = ni;
+  }
+  mul(4 * 2 + 3, -h, -h);
+  mul(4 * 3 + 1, s1, -c1);  mul(4 * 3 + 2, -h, -h);   mul(4 * 3 + 3, -c1, s1);
+  // step 3: for each c, radix-4 over b on the contiguous group 4c..4c+3: slot 4c+d <- X[c + 4d]
+  double outr[16], outi[16];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int c = 0; c < 4; ++c) {
+    double tr[4] = { re[4 * c], re[4 * c + 1], re[4 * c + 2], re[4 * c + 3] };
+    double ti[4] = { im[4 * c], im[4 * c + 1], im[4 * c + 2], im[4 * c + 3] };
+    bfly4<SIGN>(tr, ti);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int d = 0; d < 4; ++d) { outr[c + 4 * d] = tr[d]; outi[c + 4 * d] = ti[d]; }
+  }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 16; ++i) { re[i] = outr[i]; im[i] = outi[i]; }
+}
+
+template <int R, int SIGN> FB_HD void rbfly(double* re, double* im) {
+  if (R == 16) bfly16<SIGN>(re, im);
+  else bfly<R, SIGN>(re, im);
+}
+
+// One Stockham pass of the T threads owning a line.  Thread j holds element j + T*u in (re[u], im[u]).
+// Not the last pass: results go to the exchange buffer (scattered), the caller synchronises and gathers.
+// Last pass: results stay in registers, again as element (= mode) j + T*u.
+template <int M, int Q, int SIGN, class XB>
+FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) {
+  using S = RegSched<M>;
+  constexpr int r = S::radix(Q), Ns = S::ns(Q), NB = S::R / r, T = S::T;
+  constexpr bool last = (Q == S::NP - 1);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int b = 0; b < NB; ++b) {
+    const int jb = j + T * b;
+    const int k = jb & (Ns - 1);
+    double vr[r], vi[r];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) { vr[t] = re[b + t * NB]; vi[t] = im[b + t * NB]; }
+    if (Ns > 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 1; t < r; ++t) {
+        const cpx w = tw[(t - 1) * Ns + k];
+        const double wy = (SIGN < 0) ? w.y : -w.y;
+        const double xr = vr[t] * w.x - vi[t] * wy, xi = vr[t] * wy + vi[t] * w.x;
+        vr[t] = xr; vi[t] = xi;
+      }
+    }
+    rbfly<r, SIGN>(vr, vi);
+    if (last) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 0; t < r; ++t) { re[b + t * NB] = vr[t]; im[b + t * NB] = vi[t]; }
+    } else {
+      const int base = (jb - k) * r + k;               // (jb / Ns) * Ns * r + k
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 0; t < r; ++t) xb.st(base + t * Ns, vr[t], vi[t]);
+    }
+  }
+}
+
+template <int M, class XB>
+FB_HD void reg_gather(double* re, double* im, int j, const XB& xb) {
+  using S = RegSched<M>;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) xb.ld(j + S::T * u, re[u], im[u]);
+}
+
+template <int M, class XB>
+FB_HD void reg_scatter_modes(const double* re, const double* im, int j, const XB& xb) {
+  using S = RegSched<M>;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) xb.st(j + S::T * u, re[u], im[u]);
+}
+
+// forward split for this thread's modes k = j + T*u: (re,im)[u] <- the two spectral rows of mode k.
+// The exchange buffer holds Z (all modes of the line).  Same arithmetic as split_core (tile_fft.cuh).
+template <int M, class XB>
+FB_HD void reg_split(double* re, double* im, int j, int kind, const cpx* wN, const cpx* wQ, const XB& xb) {
+  using S = RegSched<M>;
+  const bool mk = (kind != KIND_PP);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) {
+    const int k = j + S::T * u;
+    const int kj = (M - k) & (M - 1);                  // partner mode (0 -> 0)
+    const double zkr = re[u], zki = im[u];
+    double zjr, zji;
+    xb.ld(kj, zjr, zji);
+    const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
+    const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
+    const cpx w = wN[k];
+    const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
+    double xr = er + wor, xi = ei + woi;
+    if (k == 0) xi = zkr - zki;                        // row 1 holds X_M = Re Z_0 - Im Z_0
+    if (mk) {
+      if (k == 0) { xr = 2.0 * xr; xi = 2.0 * wQ[M].x * xi; }
+      else {
+        const cpx q = wQ[k];
+        const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
+        xr = 2.0 * tr; xi = -2.0 * ti;
+      }
+    }
+    re[u] = xr; im[u] = xi;
+  }
+}
+
+// backward merge: (re,im)[u] holds this thread's spectral rows of mode k = j + T*u, the exchange buffer
+// holds all modes of the line; result: Z'_k (input of the inverse complex FFT).  Same arithmetic as merge_core.
+template <int M, class XB>
+FB_HD void reg_merge(double* re, double* im, int j, int kind, const cpx* wN, const cpx* wQ, const XB& xb) {
+  using S = RegSched<M>;
+  const bool mk = (kind != KIND_PP);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) {
+    const int k = j + S::T * u;
+    const int kj = (M - k) & (M - 1);
+    double xkr = re[u], xki = im[u], xjr, xji;
+    xb.ld(kj, xjr, xji);
+    if (k == 0) {
+      double xm = xki;
+      if (mk) xm = 2.0 * wQ[M].x * xm;
+      re[u] = xkr + xm; im[u] = xkr - xm;
+      continue;
+    }
+    if (mk) {
+      const cpx qk = wQ[k], qj = wQ[M - k];
+      const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
+      const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
+      xkr = vkr; xki = vki; xjr = vjr; xji = vji;
+    }
+    const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
+    const cpx w = wN[k];
+    const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
+    re[u] = sr - ci; im[u] = si + cr;                                     // S + i conj(w) D
+  }
+}
+
+// physical element indices (and DST sign) of packed complex element m: z_m = s0 x[e0] + i s1 x[e1]
+FB_HD void reg_phys_slots(int kind, int N, int m, int& e0, int& e1, double& s0, double& s1) {
+  slot_to_elem(kind, N, 2 * m, e0, s0);
+  slot_to_elem(kind, N, 2 * m + 1, e1, s1);
+}
+
+// complete forward / backward passes between gather points; SYNC is the caller's barrier functor
+template <int M, int SIGN, class XB, class SYNC>
+FB_HD void reg_fft_passes(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
+  using S = RegSched<M>;
+  reg_pass<M, 0, SIGN>(re, im, j, tw[0], xb);
+  if (S::NP > 1) {
+    sync(); reg_gather<M>(re, im, j, xb); sync();
+    reg_pass<M, (S::NP > 1 ? 1 : 0), SIGN>(re, im, j, tw[1], xb);
+  }
+  if (S::NP > 2) {
+    sync(); reg_gather<M>(re, im, j, xb); sync();
+    reg_pass<M, (S::NP > 2 ? 2 : 0), SIGN>(re, im, j, tw[2], xb);
+  }
+}
+
+}  // namespace fb

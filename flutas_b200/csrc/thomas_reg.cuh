@@ -1,0 +1,299 @@
+// thomas_reg.cuh -- z-direction tridiagonal solve with every column segment held in REGISTERS.
+//
+// Replaces gaussel / gaussel_periodic (src/solver_cpu.f90:117-185) and the reference GPU versions that
+// spill 2-4 scratch fields to memory (src/solver_gpu.f90:475-638).  Same two-level partition method as
+// thomas_tile.cuh (that kernel stays as the fall-back for shapes this one does not serve), re-organised
+// after the round-1 profile (3.9 warp-instructions per point, 31 % of the HBM peak):
+//
+//   * thread (lane, s) owns levels [sL, (s+1)L) of column `lane` of a TI-column tile and keeps them in
+//     registers from the global load to the global store -- the field never sits in a shared-memory tile;
+//   * ONE downward LU sweep per interior row (one reciprocal) that also carries the fill-in f_l towards the
+//     previous separator, then a division-free 3-term back substitution that yields the first interior
+//     row in terms of the two separators (the UL sweep of thomas_tile.cuh and its second reciprocal go);
+//   * (r'_l, f_l, d_l) stay in registers, so the final substitution is two FMAs per level;
+//   * the reduced (cyclic) tridiagonal system in the S separators is normalised to a unit diagonal and
+//     solved by parallel cyclic reduction in shared memory: one reciprocal per step instead of two;
+//   * persistent blocks: the next tile is fetched with cp.async into per-thread private shared-memory
+//     slots while the current one is being solved, so loads, arithmetic and stores of one block overlap.
+//
+// HBM traffic: 16 B/pt (read once, write once).  Host-compilable core (tests/emulate) like tile_fft.cuh.
+#pragma once
+#include "thomas_tile.cuh"
+
+namespace fb {
+
+template <int L>
+struct SegRegs {                 // per-thread state of the interior rows 0..L-2
+  double rp[L], f[L], d[L];
+};
+
+template <int L, int TI>
+struct ThomasReg {
+  static FB_HD int prow(int k) { return k + k / L; }
+  static FB_HD int tile_rows(int nz) { return nz + nz / L; }
+  // shared memory (doubles): fetch slots L*maxt | ex 6*S*TI | pcr 2*3*S*TI | X S*TI | coefficients 3*tile_rows
+  static FB_HD size_t smem_doubles(int nz, int maxt) {
+    const size_t S = (size_t)(nz / L), st = S * TI;
+    return (size_t)L * maxt + 13 * st + 3 * (size_t)tile_rows(nz);
+  }
+
+  // ---- phase 1: LU sweep down the interior rows + 3-term back substitution.
+  //   x_l = rp_l - f_l X_{s-1} - d_l x_{l+1}   (x_{L-1} = X_s)
+  //   ex[0..2] <- (R0, F0, G0): x_0     = R0 - F0 X_{s-1} - G0 X_s
+  //   ex[3..5] <- (RD, FD, DD): x_{L-2} = RD - FD X_{s-1} - DD X_s
+  static FB_HD void phase1(const double* v, const ThomasArgs& T, double lam, int lane, int s, SegRegs<L>& g, double* ex) {
+    const int kc0 = s * (L + 1);                                          // padded coefficient row of level sL
+    double dprev = 0.0, rprev = 0.0, fprev = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = 0; l < L - 1; ++l) {
+      const double ak = T.az[kc0 + l], ck = T.cz[kc0 + l], bk = T.bz[kc0 + l] + lam;
+      const double zz = fb_rcp(bk - ak * dprev);
+      const double azz = ak * zz;
+      rprev = v[l] * zz - azz * rprev;
+      fprev = (l == 0) ? azz : -azz * fprev;
+      dprev = ck * zz;
+      g.rp[l] = rprev; g.f[l] = fprev; g.d[l] = dprev;
+    }
+    double R = rprev, F = fprev, G = dprev;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = L - 3; l >= 0; --l) {
+      R = g.rp[l] - g.d[l] * R;
+      F = g.f[l] - g.d[l] * F;
+      G = -g.d[l] * G;
+    }
+    const int o = s * TI + lane, st = T.S * TI;
+    ex[o] = R; ex[st + o] = F; ex[2 * st + o] = G;
+    ex[3 * st + o] = rprev; ex[4 * st + o] = fprev; ex[5 * st + o] = dprev;
+  }
+
+  // ---- phase 2a: row of separator s of the reduced system, normalised to a unit diagonal: (A, C, R)
+  static FB_HD void reduced_row(double vsep, const double* ex, double* pcr, const ThomasArgs& T, double lam, int lane,
+                                int s, bool pin) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
+    const int kc = s * (L + 1) + L - 1;
+    const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + lam;       // ck = 0 on the last row unless periodic
+    const double r0 = ex[on], f0 = ex[st + on], g0 = ex[2 * st + on];
+    const double rd = ex[3 * st + o], fd = ex[4 * st + o], dd = ex[5 * st + o];
+    double A = -ak * fd;
+    double B = bk - ak * dd - ck * f0;
+    double C = -ck * g0;
+    double R = vsep - ak * rd - ck * r0;
+    if (pin && s == S - 1) { A = 0.0; B = 1.0; C = 0.0; R = 0.0; }        // gauge: x(nz) = 0
+    const double inv = fb_rcp(B);
+    pcr[o] = A * inv; pcr[st + o] = C * inv; pcr[2 * st + o] = R * inv;
+  }
+
+  // ---- phase 2b: one PCR step with stride h on unit-diagonal rows.  Out-of-range neighbours are clamped:
+  // their coupling coefficient is already zero in a non-periodic system.
+  static FB_HD void pcr_step(const double* src, double* dst, const ThomasArgs& T, int lane, int s, int h) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    int sm = s - h, sp = s + h;
+    if (T.periodic) { sm &= (S - 1); sp &= (S - 1); }
+    else { sm = sm < 0 ? 0 : sm; sp = sp >= S ? S - 1 : sp; }
+    const int qm = sm * TI + lane, qp = sp * TI + lane;
+    const double A = src[o], C = src[st + o], R = src[2 * st + o];
+    const double Am = src[qm], Cm = src[st + qm], Rm = src[2 * st + qm];
+    const double Ap = src[qp], Cp = src[st + qp], Rp = src[2 * st + qp];
+    const double inv = fb_rcp(1.0 - A * Cm - C * Ap);
+    dst[o] = -A * Am * inv;
+    dst[st + o] = -C * Cp * inv;
+    dst[2 * st + o] = (R - A * Rm - C * Rp) * inv;
+  }
+
+  // ---- phase 2c: rows are decoupled (non-periodic) or coupled only to row s + S/2 (periodic)
+  static FB_HD void pcr_finish(const double* src, double* X, const ThomasArgs& T, int lane, int s) {
+    const int S = T.S, st = S * TI, o = s * TI + lane;
+    const double R = src[2 * st + o];
+    if (T.periodic) {
+      const int t = (s + S / 2) & (S - 1), q = t * TI + lane;
+      const double K = src[o] + src[st + o], Kt = src[q] + src[st + q], Rt = src[2 * st + q];
+      X[o] = (R - K * Rt) * fb_rcp(1.0 - K * Kt);
+    } else {
+      X[o] = R;
+    }
+  }
+
+  // ---- phase 3: substitution with the known separators; v <- solution of this thread's L levels
+  static FB_HD void phase3(double* v, const double* X, const ThomasArgs& T, int lane, int s, const SegRegs<L>& g) {
+    const int S = T.S;
+    const int spv = (s == 0) ? S - 1 : s - 1;
+    const double xs = X[s * TI + lane];
+    const double xp = X[spv * TI + lane];                                  // multiplied by f = 0 in segment 0 unless periodic
+    double x = xs;
+    v[L - 1] = xs;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int l = L - 2; l >= 0; --l) {
+      x = (g.rp[l] - g.f[l] * xp) - g.d[l] * x;
+      v[l] = x;
+    }
+  }
+};
+
+// Picks a segment length for the register kernel; false if this nz is not served.
+inline bool thomas_reg_pick(int nz, bool periodic, int* Lout) {
+  const int cand[4] = {16, 8, 4, 2};
+  for (int q = 0; q < 4; ++q) {
+    const int L = cand[q];
+    if (nz % L) continue;
+    const int S = nz / L;
+    if (S < 2 || S > 64) continue;
+    if (periodic && (S & (S - 1))) continue;               // cyclic PCR needs a power-of-two number of separators
+    *Lout = L;
+    return true;
+  }
+  return false;
+}
+
+}  // namespace fb
+
+#if defined(__CUDACC__)
+namespace fb {
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// MAXT: upper bound of the block size TI*S (256 -> two blocks per SM, 512 -> one)
+template <int L, int TI, int MAXT>
+__global__ void __launch_bounds__(MAXT, 512 / MAXT)
+thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const double* W,
+                  ColGeom og) {
+  using TR = ThomasReg<L, TI>;
+  extern __shared__ double smem[];
+  const int nz = T.nz, S = T.S;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int st = S * TI;
+  double* slots = smem;                                   // [L][MAXT], private per thread
+  double* ex = slots + (size_t)L * MAXT;                  // 6 arrays
+  double* pcrA = ex + 6 * (size_t)st;                     // 3 arrays
+  double* pcrB = pcrA + 3 * (size_t)st;                   // 3 arrays
+  double* X = pcrB + 3 * (size_t)st;                      // 1 array
+  double* coef = X + st;                                  // az | bz | cz at padded rows
+  const int lane = tid % TI, s = tid / TI;
+  {
+    const int tr = TR::tile_rows(nz);
+    for (int k = tid; k < nz; k += nthr) {
+      const int r = TR::prow(k);
+      coef[r] = __ldg(T.az + k); coef[tr + r] = __ldg(T.bz + k); coef[2 * tr + r] = __ldg(T.cz + k);
+    }
+    T.az = coef; T.bz = coef + tr; T.cz = coef + 2 * tr; T.padded = 1;
+  }
+  // where this thread's levels go: chunk q of the output geometry (one GPU: the work array itself)
+  const int k0 = s * L;
+  const bool one_chunk = (og.n3l % L) == 0;
+  double* obase = nullptr;
+  if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
+
+  auto fetch = [&](long tile) {
+    const long col = min(tile * TI + lane, ncol - 1);
+    const double* src = W + col + (long)k0 * ncol;
+#pragma unroll
+    for (int l = 0; l < L; ++l) cp_async8(slots + l * MAXT + tid, src + (long)l * ncol);
+    cp_async_commit();
+  };
+
+  long tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile);
+  __syncthreads();                                        // coefficients staged
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const long col = tile * TI + lane;
+    const bool live = col < ncol;
+    const double lm = live ? __ldg(lam + col) : -1.0;
+    const bool pin = T.singular && live && (lm == 0.0);
+    double v[L];
+    cp_async_wait_all();
+#pragma unroll
+    for (int l = 0; l < L; ++l) v[l] = slots[l * MAXT + tid];
+
+    SegRegs<L> g;
+    TR::phase1(v, T, lm, lane, s, g, ex);
+    const long next = tile + gridDim.x;
+    if (next < ntiles) fetch(next);                       // v[] has been consumed: the slots are free again
+    __syncthreads();
+    TR::reduced_row(v[L - 1], ex, pcrA, T, lm, lane, s, pin);
+    __syncthreads();
+    double* src = pcrA;
+    double* dst = pcrB;
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) {
+      TR::pcr_step(src, dst, T, lane, s, h);
+      __syncthreads();
+      double* t = src; src = dst; dst = t;
+    }
+    TR::pcr_finish(src, X, T, lane, s);
+    __syncthreads();
+    TR::phase3(v, X, T, lane, s, g);
+    if (live) {
+      if (one_chunk) {
+        double* dstp = obase + col;
+#pragma unroll
+        for (int l = 0; l < L; ++l) __stcs(dstp + (long)l * ncol, v[l]);
+      } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const int k = k0 + l, q = k / og.n3l;
+          __stcs(og.ptr[q] + og.koff + col + ncol * (long)(k - q * og.n3l), v[l]);
+        }
+      }
+    }
+    // X / ex / pcr buffers are rewritten only after the next iteration's barriers
+  }
+}
+
+template <int L, int TI, int MAXT>
+inline cudaError_t thomas_reg_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
+                                     int nsm, cudaStream_t st) {
+  using TR = ThomasReg<L, TI>;
+  auto kern = thomas_reg_kernel<L, TI, MAXT>;
+  const size_t smem = TR::smem_doubles(T.nz, MAXT) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long ntiles = (ncol + TI - 1) / TI;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TI * T.S, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
+  kern<<<(unsigned)grid, TI * T.S, smem, st>>>(ncol, ntiles, T, lam, W, og);
+  return cudaGetLastError();
+}
+
+// *done = false if this nz is not served (caller falls back to thomas_tile / the generic kernels).
+inline int thomas_reg_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam,
+                          const double* W, double* Wout, const ColGeom* out, bool periodic, int singular, int nsm,
+                          cudaStream_t st, bool* done) {
+  *done = false;
+  int L = 0;
+  if (!thomas_reg_pick(nz, periodic, &L)) return 0;
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
+  T.padded = 0;
+  ColGeom og;
+  if (out) og = *out;
+  else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = Wout; og.n3l = nz; og.koff = 0; }
+  const bool big = (8 * T.S > 256);
+  cudaError_t e = cudaSuccess;
+  switch (L) {
+    case 2: e = big ? thomas_reg_launch<2, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<2, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
+    case 4: e = big ? thomas_reg_launch<4, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<4, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
+    case 8: e = big ? thomas_reg_launch<8, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<8, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
+    default: e = big ? thomas_reg_launch<16, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<16, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
+  }
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
+  return 0;
+}
+
+}  // namespace fb
+#endif

@@ -132,3 +132,65 @@ extern "C" int emul_thomas_tile(int L, int nz, long ncol, int periodic, int sing
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// register Thomas (flutas_b200/csrc/thomas_reg.cuh): same phases as thomas_reg_kernel, serial over threads
+#include "../../flutas_b200/csrc/thomas_reg.cuh"
+
+template <int L, int TI>
+static void thomas_reg_emul(long ncol, ThomasArgs T, const double* lam, double* W) {
+  using TR = ThomasReg<L, TI>;
+  const int nz = T.nz, S = T.S, st = S * TI;
+  const long ntiles = (ncol + TI - 1) / TI;
+  // padded coefficient rows, as the kernel stages them
+  const int tr = TR::tile_rows(nz);
+  std::vector<double> coef(3 * (size_t)tr, 0.0);
+  for (int k = 0; k < nz; ++k) { const int r = TR::prow(k); coef[r] = T.az[k]; coef[tr + r] = T.bz[k]; coef[2 * tr + r] = T.cz[k]; }
+  T.az = coef.data(); T.bz = coef.data() + tr; T.cz = coef.data() + 2 * tr; T.padded = 1;
+  std::vector<double> ex(6 * (size_t)st), pa(3 * (size_t)st), pb(3 * (size_t)st), X(st);
+  std::vector<SegRegs<L>> regs(st);
+  std::vector<double> v((size_t)st * L);
+  for (long tile = 0; tile < ntiles; ++tile) {
+    auto colof = [&](int lane) { return tile * TI + lane; };
+    auto live = [&](int lane) { return colof(lane) < ncol; };
+    auto lamof = [&](int lane) { return live(lane) ? lam[colof(lane)] : -1.0; };
+    auto vof = [&](int lane, int s) { return v.data() + ((size_t)s * TI + lane) * L; };
+#define ALLT for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
+    ALLT { const long col = live(lane) ? colof(lane) : ncol - 1; for (int l = 0; l < L; ++l) vof(lane, s)[l] = W[col + (long)(s * L + l) * ncol]; }
+    ALLT TR::phase1(vof(lane, s), T, lamof(lane), lane, s, regs[s * TI + lane], ex.data());
+    ALLT { const bool pin = T.singular && live(lane) && lamof(lane) == 0.0;
+           TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, lamof(lane), lane, s, pin); }
+    double* src = pa.data(); double* dst = pb.data();
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) { ALLT TR::pcr_step(src, dst, T, lane, s, h); double* t = src; src = dst; dst = t; }
+    ALLT TR::pcr_finish(src, X.data(), T, lane, s);
+    ALLT TR::phase3(vof(lane, s), X.data(), T, lane, s, regs[s * TI + lane]);
+    ALLT if (live(lane)) for (int l = 0; l < L; ++l) W[colof(lane) + (long)(s * L + l) * ncol] = vof(lane, s)[l];
+#undef ALLT
+  }
+}
+
+extern "C" int emul_thomas_reg(int L, int nz, long ncol, int periodic, int singular, const double* a, const double* b,
+                               const double* c, const double* lam, double* W) {
+  if (nz % L) return 1;
+  std::vector<double> az(a, a + nz), cz(c, c + nz);
+  if (!periodic) { az[0] = 0.0; cz[nz - 1] = 0.0; }
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / L; T.periodic = periodic; T.singular = singular; T.az = az.data(); T.bz = b; T.cz = cz.data();
+  T.padded = 0;
+  if (T.S < 2) return 2;
+  if (periodic && (T.S & (T.S - 1))) return 2;
+  switch (L) {
+    case 2: thomas_reg_emul<2, 8>(ncol, T, lam, W); break;
+    case 4: thomas_reg_emul<4, 8>(ncol, T, lam, W); break;
+    case 8: thomas_reg_emul<8, 8>(ncol, T, lam, W); break;
+    case 16: thomas_reg_emul<16, 8>(ncol, T, lam, W); break;
+    default: return 3;
+  }
+  return 0;
+}
+
+extern "C" int emul_thomas_reg_pick(int nz, int periodic) {
+  int L = 0;
+  return thomas_reg_pick(nz, periodic != 0, &L) ? L : 0;
+}

@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _solve_gpu(case, rhs, device=False, generic_z=False, generic_fft=False):
+def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
     s = case.setup
     n = case.ng
     lib.load().flutas_b200_debug_generic_fft(1 if generic_fft else 0)
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
     assert nf == s.normfft
-    if generic_z:
-        lib.check(lib.load().flutas_b200_debug_thomas_mode(pl.h, 1))
+    if z_mode:                                        # 1 = generic scratch-field kernels, 2 = shared-memory tile kernel
+        lib.check(lib.load().flutas_b200_debug_thomas_mode(pl.h, z_mode))
     p = case.new_p()
     p[...] = 7.0                                      # halos must come back untouched
     p[1:-1, 1:-1, 1:-1] = rhs
@@ -41,10 +41,10 @@ def _solve_gpu(case, rhs, device=False, generic_z=False, generic_fft=False):
 
 @pytest.mark.parametrize("path", [f for f in golden_files() if "ndp" not in f and "pdn" not in f],
                          ids=lambda p: p.split("/")[-1][:-4])
-@pytest.mark.parametrize("generic_z", [False, True], ids=["ztile", "zgeneric"])
-def test_solver_matches_golden(path, generic_z):
+@pytest.mark.parametrize("z_mode", [0, 2, 1], ids=["zreg", "ztile", "zgeneric"])
+def test_solver_matches_golden(path, z_mode):
     case, rhs, pgold = load_golden(path)
-    p = _solve_gpu(case, rhs, generic_z=generic_z)
+    p = _solve_gpu(case, rhs, z_mode=z_mode)
     err = gauge_rel_err(p[1:-1, 1:-1, 1:-1], pgold, case.singular)
     assert err <= TOL, err
     case.boundp(p)

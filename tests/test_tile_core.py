@@ -19,7 +19,8 @@ _dp = C.POINTER(C.c_double)
 def emul():
     src = os.path.join(HERE, "emulate", "emul.cpp")
     so = os.path.join(HERE, "emulate", "libemul.so")
-    deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f) for f in ("tile_fft.cuh", "line_plan.h")]
+    deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f)
+                    for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
@@ -79,14 +80,18 @@ def test_unsupported_lengths_are_rejected(emul):
 @pytest.fixture(scope="module")
 def emul_t(emul):
     emul.emul_thomas_tile.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    emul.emul_thomas_reg.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     return emul
 
 
 @pytest.mark.parametrize("periodic", [0, 1])
 @pytest.mark.parametrize("nz,L", [(8, 2), (16, 4), (32, 8), (64, 8), (72, 8), (40, 8), (64, 16), (128, 16), (512, 16),
-                                  (256, 32), (1024, 32), (12, 2), (24, 4)])
+                                  (256, 32), (1024, 32), (12, 2), (24, 4), (1024, 16), (48, 16), (4, 2)])
 @pytest.mark.parametrize("stretched", [False, True])
-def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched):
+@pytest.mark.parametrize("variant", ["tile", "reg"])
+def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched, variant):
+    if variant == "reg" and L > 16:
+        pytest.skip("the register kernel keeps at most 16 levels per thread")
     S = nz // L
     if periodic and (S & (S - 1)):
         pytest.skip("cyclic PCR needs a power-of-two number of separators (falls back to the generic kernel)")
@@ -105,7 +110,8 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
     rhs[0, 0, :] -= (rhs[0, 0, :] * dzf[1:-1]).sum() / dzf[1:-1].sum()    # compatible RHS for the singular column
     ref = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bool(periodic))
     got = rhs.copy(order="F")
-    rc = emul_t.emul_thomas_tile(L, nz, nx * ny, periodic, 1, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
+    fn = emul_t.emul_thomas_tile if variant == "tile" else emul_t.emul_thomas_reg
+    rc = fn(L, nz, nx * ny, periodic, 1, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
                                  c.ctypes.data_as(_dp), np.asfortranarray(lam).ctypes.data_as(_dp),
                                  got.ctypes.data_as(_dp))
     assert rc == 0
