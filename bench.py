@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--solver-only", action="store_true",
+                    help="time only the solver on a device-generated RHS (large shapes: no host-side velocity fields, "
+                         "no pressure-step / e2e / CPU legs); prints a reduced JSON line")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: direct NVLink stores from the kernels (CUDA IPC) or NCCL all-to-all")
     args = ap.parse_args()
@@ -209,7 +212,10 @@ def main():
     npts = n1 * n2 * n3g                                # whole job
     npts_loc = n1 * n2 * n3
     exchange = None
-    if world == 1:
+    if args.solver_only:
+        ud = vd = wd = None
+        dzfi, dzci = s.dzfi, s.dzci
+    elif world == 1:
         u, v, w = case.velocity()
         dzfi, dzci = s.dzfi, s.dzci
     else:
@@ -222,9 +228,15 @@ def main():
         k0 = rank * n3
         dzfi = np.ascontiguousarray(s.dzfi[k0:k0 + n3 + 2 * case.nh_d])
         dzci = np.ascontiguousarray(s.dzci[k0:k0 + n3 + 2 * case.nh_d])
-    ud, vd, wd = (api.device_field(f) for f in (u, v, w))
-    del u, v, w
-    pd = api.device_field(np.zeros((n1 + 2, n2 + 2, n3 + 2), order="F"))
+    if args.solver_only:
+        g = torch.Generator(device="cuda")
+        g.manual_seed(case.seed + rank)
+        pd = torch.rand((n3 + 2, n2 + 2, n1 + 2), dtype=torch.float64, device="cuda", generator=g) - 0.5
+        rhs0 = pd.clone()
+    else:
+        ud, vd, wd = (api.device_field(f) for f in (u, v, w))
+        del u, v, w
+        pd = api.device_field(np.zeros((n1 + 2, n2 + 2, n3 + 2), order="F"))
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
     lam_win = s.lambdaxy
     comm = None
@@ -245,6 +257,9 @@ def main():
             comm.use_nccl_alltoall()
 
     def fill():
+        if args.solver_only:
+            pd.copy_(rhs0)
+            return
         api.fillps(*n, case.nh_d, case.nh_u, *s.dli, dzfi, case.dti, case.rho0, ud, vd, wd, pd)
         if world == 1:
             api.updt_rhs_b(*n, case.cbc, s.rhsbx, s.rhsby, s.rhsbz, pd)
@@ -290,6 +305,34 @@ def main():
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = npts / (ms_step * 1e-3) / 1e9
+
+    if args.solver_only:
+        peak, peak_src = measured_peak()
+        tbl = {}
+        for name, (ms, cnt) in stages.items():
+            if name in ALG_BYTES_PER_PT and cnt:
+                gbs = ALG_BYTES_PER_PT[name] * npts_loc / (ms / cnt * 1e-3) / 1e9
+                tbl[name] = {"ms": round(ms / cnt, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
+            elif cnt:
+                tbl[name] = {"ms": round(ms / cnt, 4)}
+        line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+                "scaling": "strong", "dtype": "f64", "data": "synthetic (device-generated uniform RHS, solver only)",
+                "config": dict(workload_config(case, args.workload),
+                               decomposition=("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU"),
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                             "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT,
+                                        "achieved_per_gpu": round(SOLVER_BYTES_PER_PT * value / world, 1),
+                                        "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4)},
+                             "stages": tbl}}
+        if rank == 0:
+            print(json.dumps(line))
+        api.fftend(pl)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- ms per pressure step (fillps + updt_rhs_b + solver + correc), device resident -----------
     api.profile_enable(True)

@@ -6,12 +6,14 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/flutas_b200.h"
 #include "fft_p2.h"
+#include "fft_reg.h"
 #include "kernels.cuh"
 #include "line_plan.h"
 #include "thomas_reg.cuh"
@@ -115,6 +117,30 @@ struct DevLinePlan {
   LinePlan d{};
   int tb = 16;
   size_t smem = 0;
+  // register-resident kernels (power-of-two lengths): own tables and own spectral layout
+  bool use_reg = false;
+  HostRegPlan hr;
+  DevBuf rtables;
+  RegPlan r{};
+  const std::vector<int>& mode() const { return use_reg ? hr.mode : h.mode; }
+  int upload_reg() {
+    size_t n = hr.wN.size() + hr.wQ.size();
+    for (int q = 0; q < RF_MAXPASS; ++q) n += hr.tw[q].size();
+    if (int rc = rtables.reserve((n + 1) * sizeof(cpx))) return rc;
+    cpx* at = rtables.as<cpx>();
+    r.N = hr.N; r.M = hr.M; r.kind = hr.kind;
+    for (int q = 0; q < RF_MAXPASS; ++q) {
+      r.tw[q] = at; r.tw_count[q] = (int)hr.tw[q].size();
+      if (!hr.tw[q].empty()) CK(cudaMemcpy(at, hr.tw[q].data(), hr.tw[q].size() * sizeof(cpx), cudaMemcpyHostToDevice));
+      at += hr.tw[q].size();
+    }
+    r.wN = at;
+    CK(cudaMemcpy(at, hr.wN.data(), hr.wN.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    at += hr.wN.size();
+    r.wQ = at;
+    CK(cudaMemcpy(at, hr.wQ.data(), hr.wQ.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+    return 0;
+  }
   int upload() {
     const size_t nwM = h.wM.size(), nwN = h.wN.size(), nwQ = h.wQ.size(), npos = h.pos.size();
     const size_t bytes = (nwM + nwN + nwQ) * sizeof(cpx) + npos * sizeof(int);
@@ -194,11 +220,26 @@ int launch_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst,
   LAUNCHED();
   return 0;
 }
-bool g_force_generic_fft = false;   // test hook: bypass the power-of-two kernels
+int g_fft_level = 0;   // test hook: 0 = register kernels where available, 1 = run-time-radix tile kernels only,
+                       // 2 = tile kernels (power-of-two specialisations allowed) but no register kernels
+
+bool aligned16(const void* p, const LineGeom& g) {
+  return ((uintptr_t)p % 16 == 0) && (g.off0 % 2 == 0) && (g.sj % 2 == 0) && (g.sk % 2 == 0);
+}
 
 template <bool FWD>
 int run_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale) {
-  if (!g_force_generic_fft && p2_tile_width(lp.d.N)) {
+  if (lp.use_reg) {
+    if (!(FWD ? aligned16(dst, gd) : aligned16(src, gs)))
+      return fail(FLUTAS_B200_ERR_ARG, "register transform kernels need a 16-byte aligned spectral work array");
+    const int nsm = g_nsm > 0 ? g_nsm : 148;
+    cudaError_t e = FWD ? reg_run_x_fwd(lp.r, src, gs, dst, gd, scale, nsm, g_stream)
+                        : reg_run_x_bwd(lp.r, src, gs, dst, gd, scale, nsm, g_stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "xfft_reg launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (g_fft_level != 1 && p2_tile_width(lp.d.N)) {
     cudaError_t e = p2_run_x(FWD, lp.d, src, gs, dst, gd, scale, g_stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "xfft_p2 launch failed: %s", cudaGetErrorString(e));
@@ -221,7 +262,14 @@ int launch_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& 
 }
 template <bool FWD>
 int run_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& sg) {
-  if (!g_force_generic_fft && p2_tile_width(lp.d.N)) {
+  if (lp.use_reg) {
+    const int nsm = g_nsm > 0 ? g_nsm : 148;
+    cudaError_t e = FWD ? reg_run_y_fwd(lp.r, W, n1, n3, sg, nsm, g_stream) : reg_run_y_bwd(lp.r, W, n1, n3, sg, nsm, g_stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_reg launch failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (g_fft_level != 1 && p2_tile_width(lp.d.N)) {
     cudaError_t e = p2_run_y(FWD, lp.d, W, n1, n3, sg, g_stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_p2 launch failed: %s", cudaGetErrorString(e));
@@ -276,8 +324,8 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
     CK(cudaMemsetAsync(abc + 5 * nz + (nz - 1), 0, sizeof(double), g_stream));       // cz[nz-1]
   }
   int* maps = sp->maps.as<int>();
-  CK(cudaMemcpyAsync(maps, sp->px.h.mode.data(), n1 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(maps + n1, sp->py.h.mode.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(maps, sp->px.mode().data(), n1 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(maps + n1, sp->py.mode().data(), n2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
   permute_lambda_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, g_stream>>>(n1, n2, sp->lam_raw.as<double>(), maps,
                                                                              maps + n1, sp->lam_int.as<double>());
   LAUNCHED();
@@ -344,6 +392,8 @@ int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const
 // ---- multi-GPU slab exchange ------------------------------------------------------------------
 flutas_b200_alltoall_fn g_a2a = nullptr;
 void* g_a2a_ctx = nullptr;
+flutas_b200_halo_fn g_halo = nullptr;
+void* g_halo_ctx = nullptr;
 
 struct P2PBlob {                       // what one rank publishes to the others
   cudaIpcMemHandle_t handle;
@@ -488,6 +538,12 @@ int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], c
   }
   int rc = sp->px.upload();
   if (!rc) rc = sp->py.upload();
+  for (DevLinePlan* lp : {&sp->px, &sp->py}) {
+    if (rc || g_fft_level != 0 || !reg_fft_supported(lp->h.N)) continue;
+    lp->hr = make_reg_plan(lp->h.N, lp->h.kind);
+    lp->use_reg = lp->hr.ok;
+    if (lp->use_reg) rc = lp->upload_reg();
+  }
   if (rc) { delete sp; return rc; }
   // normfft exactly as src/fft.f90:71,87,125,150 (norm = (1,0) for PP, (2,0) for NN/DD; ix = iy = 0)
   double nf = 1.0;
@@ -501,6 +557,7 @@ int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], c
 int flutas_b200_fftend(void* arrplan[4]) {
   SolverPlan* sp = plan_of(arrplan);
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "fftend: not a flutas_b200 plan");
+  for (DevBuf* b : {&sp->px.rtables, &sp->py.rtables}) b->release();
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
@@ -522,9 +579,11 @@ int flutas_b200_solver_invalidate(void* const arrplan[4]) {
   return FLUTAS_B200_OK;
 }
 
-// test hook: 1 = always use the run-time-radix transform kernels (skip the power-of-two specialisations)
-int flutas_b200_debug_generic_fft(int on) {
-  g_force_generic_fft = (on != 0);
+// test hook, read by fftini (register kernels) and by every solve (tile kernels): 0 = register-resident kernels
+// for power-of-two lengths, 1 = always the run-time-radix tile kernels, 2 = tile kernels incl. their
+// power-of-two specialisations but no register kernels
+int flutas_b200_debug_generic_fft(int level) {
+  g_fft_level = level;
   return FLUTAS_B200_OK;
 }
 
@@ -854,6 +913,89 @@ int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   if (int rc = stage_out(fv)) return rc;
   if (int rc = stage_out(fw)) return rc;
   if (fu.staged || fv.staged || fw.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_set_halo_exchange(flutas_b200_halo_fn fn, void* ctx) {
+  g_halo = fn;
+  g_halo_ctx = ctx;
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_boundp(const char cbc[6], const int n[3], const double bc[6], int nh_d, int nh_p, const double dl[3],
+                       const double* dzc, const double* dzf, double* p) {
+  (void)dzf;
+  if (int rc = ensure_device()) return rc;
+  if (!cbc || !n || !bc || !dl || !dzc || !p) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (nh_p != 1) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "boundp: only nh_p = 1 (pressure halo) is on this path");
+  if (nh_d < 1) return fail(FLUTAS_B200_ERR_ARG, "nh_d must be >= 1");
+  for (int q = 0; q < 6; ++q)
+    if (cbc[q] != 'P' && cbc[q] != 'D' && cbc[q] != 'N') return fail(FLUTAS_B200_ERR_ARG, "bad boundary type '%c'", cbc[q]);
+  const int nx = n[0], ny = n[1], nz = n[2];
+  const long s1 = nx + 2, s2 = ny + 2, s3 = nz + 2;
+  const size_t pcount = (size_t)s1 * s2 * s3;
+  FieldRef fp;
+  if (int rc = stage_in(fp, 3, p, pcount, true)) return rc;
+  double* pd = fp.dev;
+  // z metric at the two walls: dzc(0), dzc(nz) (bound.f90:209-218); only needed for a non-zero Neumann value
+  double dzc_lo = 0.0, dzc_hi = 0.0;
+  if ((cbc[4] == 'N' && bc[4] != 0.0) || (cbc[5] == 'N' && bc[5] != 0.0)) {
+    CK(cudaMemcpyAsync(&dzc_lo, dzc + (nh_d - 1), sizeof(double), cudaMemcpyDefault, g_stream));
+    CK(cudaMemcpyAsync(&dzc_hi, dzc + (nh_d - 1) + nz, sizeof(double), cudaMemcpyDefault, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  const FaceGeom gx{1, s1, s1 * s2, nx, (int)s2, (int)s3};
+  const FaceGeom gy{s1, 1, s1 * s2, ny, (int)s1, (int)s3};
+  const FaceGeom gz{s1 * s2, 1, s1, nz, (int)s1, (int)s2};
+  auto nblk = [](const FaceGeom& g) { return (unsigned)(((long)g.na * g.nb + 255) / 256); };
+  auto wrap = [&](const FaceGeom& g) -> int {
+    boundp_wrap_kernel<<<nblk(g), 256, 0, g_stream>>>(g, pd);
+    LAUNCHED();
+    return 0;
+  };
+  // set_bc for one side (bound.f90:247-268): D (centred): 2 v - p_in ; N: p_in -/+ dr v
+  auto face = [&](const FaceGeom& g, int side, char type, double value, double dr) -> int {
+    double factor = value, sgn = 0.0;
+    if (type == 'D') { factor = 2.0 * factor; sgn = -1.0; }
+    if (type == 'N') { factor = (side == 0) ? -dr * factor : dr * factor; sgn = 1.0; }
+    boundp_face_kernel<<<nblk(g), 256, 0, g_stream>>>(g, side, factor, sgn, pd);
+    LAUNCHED();
+    return 0;
+  };
+  const bool py = (cbc[2] == 'P' && cbc[3] == 'P'), pz = (cbc[4] == 'P' && cbc[5] == 'P');
+  const int P = g_nranks, r = g_rank;
+  // 1. updthalo along y (the rank is its own y neighbour in the z-slab layout), bound.f90:182
+  if (py) { if (int rc = wrap(gy)) return rc; }
+  // 2. updthalo along z, bound.f90:183
+  int lo = -1, hi = -1;                                   // bottom / top neighbours (MPI_CART_SHIFT, initmpi.f90:127)
+  if (P > 1) {
+    lo = (r > 0) ? r - 1 : (pz ? P - 1 : -1);
+    hi = (r < P - 1) ? r + 1 : (pz ? 0 : -1);
+  }
+  if (P == 1) {
+    if (pz) { if (int rc = wrap(gz)) return rc; }
+  } else {
+    if (!g_halo) return fail(FLUTAS_B200_ERR_ARG, "boundp on %d ranks needs flutas_b200_set_halo_exchange", P);
+    const size_t plane = (size_t)s1 * s2;
+    if (g_halo(g_halo_ctx, pd + plane, pd + plane * nz, pd, pd + plane * (nz + 1), plane, lo, hi, (void*)g_stream))
+      return fail(FLUTAS_B200_ERR_CUDA, "halo exchange callback failed");
+  }
+  // 3.-5. set_bc on the faces this rank owns (x is never decomposed: left = right = MPI_PROC_NULL, initmpi.f90:124)
+  if (cbc[0] == 'P') { if (int rc = wrap(gx)) return rc; }
+  else {
+    if (int rc = face(gx, 0, cbc[0], bc[0], dl[0])) return rc;
+    if (int rc = face(gx, 1, cbc[1], bc[1], dl[0])) return rc;
+  }
+  if (!py) {
+    if (int rc = face(gy, 0, cbc[2], bc[2], dl[1])) return rc;
+    if (int rc = face(gy, 1, cbc[3], bc[3], dl[1])) return rc;
+  }
+  if (!pz) {
+    if (lo < 0 && (P == 1 || r == 0)) { if (int rc = face(gz, 0, cbc[4], bc[4], dzc_lo)) return rc; }
+    if (hi < 0 && (P == 1 || r == P - 1)) { if (int rc = face(gz, 1, cbc[5], bc[5], dzc_hi)) return rc; }
+  }
+  if (int rc = stage_out(fp)) return rc;
+  if (fp.staged) CK(cudaStreamSynchronize(g_stream));
   return FLUTAS_B200_OK;
 }
 

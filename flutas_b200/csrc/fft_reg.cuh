@@ -1,0 +1,272 @@
+// fft_reg.cuh -- kernels around reg_fft.cuh: x lines (contiguous) and y lines (stride n1), persistent blocks.
+//
+//   xfft_reg_kernel : T = N/32 threads per line.  T <= 32: a line lives inside one warp, so every exchange is
+//                     followed by __syncwarp() only -- warps of a block never wait for each other and their
+//                     load / compute / store phases overlap.  Physical side: 8-byte accesses (the halo'd p of
+//                     the caller is only 8-byte aligned); spectral side: 16-byte accesses, (Re,Im) interleaved.
+//   yfft_reg_kernel : lanes = TB consecutive i, so the strided y lines are read and written coalesced; the T
+//                     threads of a line sit in different warps -> block barriers.  The spectral side goes
+//                     through SpecGeom: on several GPUs its stores ARE the exchange (geom.cuh).
+//
+// Reference counterparts: fft() forward/backward on the x and y pencils (src/solver_cpu.f90:59,65,86,89) and
+// the pack/unpack loops of the transposes around them.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "geom.cuh"
+#include "reg_fft.cuh"
+
+namespace fb {
+
+template <int M>
+struct RegTw {
+  using S = RegSched<M>;
+  static constexpr int n1 = (S::NP > 1) ? 15 * S::ns(1) : 0;
+  static constexpr int n2 = (S::NP > 2) ? 15 * S::ns(2) : 0;
+};
+
+// exchange buffer of one x line: M slots of (re,im), one pad slot per 16 (scattered 16-slot strides -> all banks)
+struct XLineBuf {
+  double2* b;
+  __device__ __forceinline__ void st(int pos, double r, double i) const { b[pos + (pos >> 4)] = make_double2(r, i); }
+  __device__ __forceinline__ void ld(int pos, double& r, double& i) const {
+    const double2 v = b[pos + (pos >> 4)];
+    r = v.x; i = v.y;
+  }
+};
+
+// exchange buffer of a y tile: [slot][lane]
+template <int TB>
+struct YTileBuf {
+  double2* b;   // already offset by the lane
+  __device__ __forceinline__ void st(int pos, double r, double i) const { b[(pos + (pos >> 4)) * TB] = make_double2(r, i); }
+  __device__ __forceinline__ void ld(int pos, double& r, double& i) const {
+    const double2 v = b[(pos + (pos >> 4)) * TB];
+    r = v.x; i = v.y;
+  }
+};
+
+template <int M>
+__device__ __forceinline__ void reg_stage_tw(cpx* s1, cpx* s2, const RegPlan& P, int tid, int nthr) {
+  const double2* g1 = reinterpret_cast<const double2*>(P.tw[1]);
+  const double2* g2 = reinterpret_cast<const double2*>(P.tw[2]);
+  for (int q = tid; q < RegTw<M>::n1; q += nthr) reinterpret_cast<double2*>(s1)[q] = __ldg(g1 + q);
+  for (int q = tid; q < RegTw<M>::n2; q += nthr) reinterpret_cast<double2*>(s2)[q] = __ldg(g2 + q);
+}
+
+template <int N>
+constexpr size_t xfft_reg_smem() {
+  constexpr int M = N / 2;
+  return (size_t)(RegTw<M>::n1 + RegTw<M>::n2) * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
+}
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(256, 2)
+xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* __restrict__ dst, LineGeom gd, double scale) {
+  constexpr int M = N / 2;
+  using S = RegSched<M>;
+  constexpr int T = S::T, R = S::R;
+  constexpr bool WARP = (T <= 32);
+  constexpr int GT = WARP ? 32 : 256;                 // threads that synchronise with each other
+  constexpr int LG = GT / T;                          // lines per group
+  constexpr int BUFL = M + M / 16;
+  extern __shared__ double2 smem2[];
+  cpx* s_tw1 = reinterpret_cast<cpx*>(smem2);
+  cpx* s_tw2 = s_tw1 + RegTw<M>::n1;
+  double2* bufs = reinterpret_cast<double2*>(s_tw2 + RegTw<M>::n2);
+  const int tid = threadIdx.x;
+  reg_stage_tw<M>(s_tw1, s_tw2, P, tid, 256);
+  __syncthreads();
+  const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
+  const int gi = WARP ? (tid >> 5) : 0, tg = tid % GT;
+  const int lw = tg / T, j = tg % T;
+  const XLineBuf xb{bufs + (size_t)(gi * LG + lw) * BUFL};
+  auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
+  const int kind = P.kind;
+  const long nlines = gs.nlines;
+  const long ngroups = (nlines + LG - 1) / LG;
+  const long gstride = WARP ? (long)gridDim.x * 8 : (long)gridDim.x;
+  for (long g = WARP ? (long)blockIdx.x * 8 + gi : (long)blockIdx.x; g < ngroups; g += gstride) {
+    const long line = g * LG + lw;
+    const bool live = line < nlines;
+    const long lc = live ? line : nlines - 1;
+    double re[R], im[R];
+    if (FWD) {
+      const double* ps = src + line_offset(gs, lc);
+      if (kind == KIND_PP) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          int e0, e1; double s0, s1;
+          reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+          re[u] = s0 * ps[e0]; im[u] = s1 * ps[e1];
+        }
+      }
+      reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
+      reg_scatter_modes<M>(re, im, j, xb);
+      sync();
+      reg_split<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      if (live) {
+        double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
+#pragma unroll
+        for (int u = 0; u < R; ++u) __stcs(pd + (j + T * u), make_double2(scale * re[u], scale * im[u]));
+      }
+    } else {
+      const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
+#pragma unroll
+      for (int u = 0; u < R; ++u) { const double2 v = __ldcs(ps + (j + T * u)); re[u] = v.x; im[u] = v.y; }
+      reg_scatter_modes<M>(re, im, j, xb);
+      sync();
+      reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      sync();
+      reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
+      if (live) {
+        double* pd = dst + line_offset(gd, line);
+        if (kind == KIND_PP) {
+#pragma unroll
+          for (int u = 0; u < R; ++u) { const int m = j + T * u; pd[2 * m] = scale * re[u]; pd[2 * m + 1] = scale * im[u]; }
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            int e0, e1; double s0, s1;
+            reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+            pd[e0] = s0 * scale * re[u]; pd[e1] = s1 * scale * im[u];
+          }
+        }
+      }
+    }
+    sync();                                            // the buffer is rewritten by the next group
+  }
+}
+
+// ---- y lines ------------------------------------------------------------------------------------
+template <int N>
+struct YRegShape {
+  static constexpr int T = RegSched<N / 2>::T;
+  static constexpr int TB = (256 / T > 32) ? 32 : 256 / T;
+  static constexpr int NT = TB * T;
+  static constexpr size_t smem = (size_t)(RegTw<N / 2>::n1 + RegTw<N / 2>::n2) * sizeof(cpx) +
+                                 (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
+};
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(YRegShape<N>::NT, 2)
+yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
+  constexpr int M = N / 2;
+  using S = RegSched<M>;
+  constexpr int T = S::T, R = S::R, TB = YRegShape<N>::TB, NT = YRegShape<N>::NT;
+  extern __shared__ double2 smem2[];
+  cpx* s_tw1 = reinterpret_cast<cpx*>(smem2);
+  cpx* s_tw2 = s_tw1 + RegTw<M>::n1;
+  double2* buf = reinterpret_cast<double2*>(s_tw2 + RegTw<M>::n2);
+  const int tid = threadIdx.x;
+  reg_stage_tw<M>(s_tw1, s_tw2, P, tid, NT);
+  __syncthreads();
+  const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
+  const int lane = tid % TB, j = tid / TB;
+  const YTileBuf<TB> xb{buf + lane};
+  auto sync = [] { __syncthreads(); };
+  const int kind = P.kind;
+  const long stride = n1, sstride = sg.n1l;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ti = (int)(tile % ntile_i);
+    const long k = tile / ntile_i;
+    const int i0 = ti * TB;
+    const bool live = (i0 + lane) < n1;
+    const int il = i0 + (live ? lane : 0);
+    double* base = W + (long)n1 * N * k + il;               // physical side
+    double* sbase = spec_base(sg, il, N, k);                 // spectral side (pencil chunk of the exchange)
+    double re[R], im[R];
+    if (FWD) {
+      if (kind == KIND_PP) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = base[(long)(2 * m) * stride]; im[u] = base[(long)(2 * m + 1) * stride]; }
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          int e0, e1; double s0, s1;
+          reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+          re[u] = s0 * base[(long)e0 * stride]; im[u] = s1 * base[(long)e1 * stride];
+        }
+      }
+      reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
+      reg_scatter_modes<M>(re, im, j, xb);
+      sync();
+      reg_split<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      if (live) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int kk = j + T * u;
+          __stcs(sbase + (long)(2 * kk) * sstride, re[u]);
+          __stcs(sbase + (long)(2 * kk + 1) * sstride, im[u]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int kk = j + T * u;
+        re[u] = __ldcs(sbase + (long)(2 * kk) * sstride);
+        im[u] = __ldcs(sbase + (long)(2 * kk + 1) * sstride);
+      }
+      reg_scatter_modes<M>(re, im, j, xb);
+      sync();
+      reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      sync();
+      reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
+      if (live) {
+        if (kind == KIND_PP) {
+#pragma unroll
+          for (int u = 0; u < R; ++u) { const int m = j + T * u; base[(long)(2 * m) * stride] = re[u]; base[(long)(2 * m + 1) * stride] = im[u]; }
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            int e0, e1; double s0, s1;
+            reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+            base[(long)e0 * stride] = s0 * re[u]; base[(long)e1 * stride] = s1 * im[u];
+          }
+        }
+      }
+    }
+    sync();
+  }
+}
+
+template <int N, bool FWD>
+inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
+                                int nsm, cudaStream_t st) {
+  constexpr int M = N / 2, T = RegSched<M>::T;
+  constexpr int LPB = 256 / T;                         // lines per block per iteration
+  const size_t smem = xfft_reg_smem<N>();
+  auto kern = xfft_reg_kernel<N, FWD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const long nblk = (gs.nlines + LPB - 1) / LPB;
+  const long grid = nblk < (long)nsm * per_sm ? nblk : (long)nsm * per_sm;
+  kern<<<(unsigned)grid, 256, smem, st>>>(P, src, gs, dst, gd, scale);
+  return cudaGetLastError();
+}
+
+template <int N, bool FWD>
+inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
+  using Y = YRegShape<N>;
+  auto kern = yfft_reg_kernel<N, FWD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Y::NT, Y::smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const int nti = (n1 + Y::TB - 1) / Y::TB;
+  const long ntiles = (long)nti * n3;
+  const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
+  kern<<<(unsigned)grid, Y::NT, Y::smem, st>>>(P, W, n1, nti, ntiles, sg);
+  return cudaGetLastError();
+}
+
+}  // namespace fb

@@ -377,3 +377,40 @@ __global__ void chkdiv_final_kernel(long nparts, const double* __restrict__ part
 }
 
 }  // namespace fb
+
+// ------------------------------------------------------------------------------------------------
+// boundp (src/bound.f90:146-225): ghost cells of p, halo width 1.  One launch per step of the reference's
+// sequence (y halo, z halo, x faces, y faces, z faces) so that edges and corners come out bit-identical.
+// A "face pair" in direction d: ghost planes at index 0 and n_d+1, over the full (halo-inclusive) extent
+// of the other two directions.  sd = element stride of direction d; (na, sa), (nb, sb) span the face.
+struct FaceGeom {
+  long sd, sa, sb;
+  int nd, na, nb;      // nd = interior size along d; na, nb = full extents (with halos) of the face
+};
+
+// periodic wrap (set_bc case 'P', bound.f90:268-318; = updthalo with the rank as its own neighbour)
+__global__ void boundp_wrap_kernel(FaceGeom g, double* __restrict__ p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)g.na * g.nb) return;
+  const long b = idx / g.na, a = idx - b * g.na;
+  double* q = p + a * g.sa + b * g.sb;
+  q[0] = q[(long)g.nd * g.sd];
+  q[(long)(g.nd + 1) * g.sd] = q[g.sd];
+}
+
+// Dirichlet / Neumann ghost: p_ghost = factor + sgn * p_inner (bound.f90:320-420), side 0 or 1
+__global__ void boundp_face_kernel(FaceGeom g, int side, double factor, double sgn, double* __restrict__ p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)g.na * g.nb) return;
+  const long b = idx / g.na, a = idx - b * g.na;
+  double* q = p + a * g.sa + b * g.sb;
+  if (side == 0) q[0] = __dadd_rn(factor, __dmul_rn(sgn, q[g.sd]));
+  else q[(long)(g.nd + 1) * g.sd] = __dadd_rn(factor, __dmul_rn(sgn, q[(long)g.nd * g.sd]));
+}
+
+// z halo from neighbouring slabs: contiguous planes (rank-local copies; the inter-GPU transfer itself is the
+// caller's exchange callback or a peer copy)
+__global__ void copy_plane_kernel(long n, const double* __restrict__ src, double* __restrict__ dst) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) dst[idx] = src[idx];
+}

@@ -76,3 +76,55 @@ inline HostLinePlan make_line_plan(int N, int kind) {
 }
 
 }  // namespace fb
+
+// ---------------------------------------------------------------------------------------------
+// tables of the register-resident transforms (reg_fft.cuh)
+#include "reg_fft.cuh"
+
+namespace fb {
+
+struct HostRegPlan {
+  int N = 0, M = 0, kind = 0;
+  std::vector<cpx> tw[RF_MAXPASS];
+  std::vector<cpx> wN, wQ;
+  std::vector<int> mode;       // mode[r] : index into the reference's lambda array for spectral row r (0-based)
+  bool ok = false;
+};
+
+template <int M>
+inline void fill_reg_twiddles(HostRegPlan& hp) {
+  using S = RegSched<M>;
+  for (int q = 1; q < S::NP; ++q) {
+    const int r = S::radix(q), Ns = S::ns(q);
+    hp.tw[q].resize((size_t)(r - 1) * Ns);
+    for (int t = 1; t < r; ++t)
+      for (int k = 0; k < Ns; ++k) hp.tw[q][(size_t)(t - 1) * Ns + k] = unit_root(2.0L * t * k, (long double)Ns * r);
+  }
+}
+
+inline HostRegPlan make_reg_plan(int N, int kind) {
+  HostRegPlan hp;
+  hp.N = N; hp.M = N / 2; hp.kind = kind;
+  if (!reg_fft_supported(N)) return hp;
+  switch (hp.M) {
+    case 16: fill_reg_twiddles<16>(hp); break;
+    case 32: fill_reg_twiddles<32>(hp); break;
+    case 64: fill_reg_twiddles<64>(hp); break;
+    case 128: fill_reg_twiddles<128>(hp); break;
+    case 256: fill_reg_twiddles<256>(hp); break;
+    case 512: fill_reg_twiddles<512>(hp); break;
+    case 1024: fill_reg_twiddles<1024>(hp); break;
+    default: return hp;
+  }
+  const int M = hp.M;
+  hp.wN.resize(M);
+  for (int k = 0; k < M; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
+  hp.wQ.resize(M + 1);
+  for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  hp.mode.resize(N);
+  for (int r = 0; r < N; ++r) hp.mode[r] = reg_mode_index(N, kind, r);
+  hp.ok = true;
+  return hp;
+}
+
+}  // namespace fb

@@ -80,10 +80,8 @@ template <int SIGN> FB_HD void bfly16(double* re, double* im) {
   // w16^1 = (c1,-s1)  w16^2 = (h,-h)  w16^3 = (s1,-c1)  w16^4 = (0,-1)  w16^6 = (-h,-h)  w16^9 = (-c1,s1)
   mul(4 * 1 + 1, c1, -s1);  mul(4 * 1 + 2, h, -h);    mul(4 * 1 + 3, s1, -c1);
   mul(4 * 2 + 1, h, -h);
-  { const int i = 4 * 2 + 2; const double xr = SIGN * -im[i] * -1.0, xi = SIGN * re[i] * -1.0 * -1.0; (void)xr; (void)xi; }
   {                                                    // w16^4 = -i (fwd), +i (bwd): (x + iy)(-i) = y - ix
     const int i = 4 * 2 + 2;
-    const double xr = -SIGN * -im[i] * -1.0; (void)xr;
     const double nr = (SIGN < 0) ? im[i] : -im[i], ni = (SIGN < 0) ? -re[i] : re[i];
     re[i] = nr; im[i] = ni;
   }
@@ -255,13 +253,13 @@ template <int M, int SIGN, class XB, class SYNC>
 FB_HD void reg_fft_passes(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
   using S = RegSched<M>;
   reg_pass<M, 0, SIGN>(re, im, j, tw[0], xb);
-  if (S::NP > 1) {
+  if constexpr (S::NP > 1) {
     sync(); reg_gather<M>(re, im, j, xb); sync();
-    reg_pass<M, (S::NP > 1 ? 1 : 0), SIGN>(re, im, j, tw[1], xb);
+    reg_pass<M, 1, SIGN>(re, im, j, tw[1], xb);
   }
-  if (S::NP > 2) {
+  if constexpr (S::NP > 2) {
     sync(); reg_gather<M>(re, im, j, xb); sync();
-    reg_pass<M, (S::NP > 2 ? 2 : 0), SIGN>(re, im, j, tw[2], xb);
+    reg_pass<M, 2, SIGN>(re, im, j, tw[2], xb);
   }
 }
 

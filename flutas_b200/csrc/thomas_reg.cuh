@@ -43,17 +43,33 @@ struct ThomasReg {
   //   ex[3..5] <- (RD, FD, DD): x_{L-2} = RD - FD X_{s-1} - DD X_s
   static FB_HD void phase1(const double* v, const ThomasArgs& T, double lam, int lane, int s, SegRegs<L>& g, double* ex) {
     const int kc0 = s * (L + 1);                                          // padded coefficient row of level sL
-    double dprev = 0.0, rprev = 0.0, fprev = 0.0;
+    // Pivots without a serial division chain: the leading principal minors th_l = bb_l th_{l-1} - a_l c_{l-1} th_{l-2}
+    // cost one dependent FMA per level; z_l = 1/(bb_l - a_l c_{l-1} z_{l-1}) = th_{l-1} / th_l are then L-1
+    // independent reciprocals (same LU, the quotients are just formed at the end).
+    double z[L];
+    {
+      double thm = 1.0, th = T.bz[kc0] + lam;
+      z[0] = fb_rcp(th);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int l = 1; l < L - 1; ++l) {
+        const double gk = T.az[kc0 + l] * T.cz[kc0 + l - 1];
+        const double tn = (T.bz[kc0 + l] + lam) * th - gk * thm;
+        z[l] = th * fb_rcp(tn);
+        thm = th; th = tn;
+      }
+    }
+    double rprev = 0.0, fprev = 0.0, dprev = 0.0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int l = 0; l < L - 1; ++l) {
-      const double ak = T.az[kc0 + l], ck = T.cz[kc0 + l], bk = T.bz[kc0 + l] + lam;
-      const double zz = fb_rcp(bk - ak * dprev);
-      const double azz = ak * zz;
+      const double zz = z[l];
+      const double azz = T.az[kc0 + l] * zz;
       rprev = v[l] * zz - azz * rprev;
       fprev = (l == 0) ? azz : -azz * fprev;
-      dprev = ck * zz;
+      dprev = T.cz[kc0 + l] * zz;
       g.rp[l] = rprev; g.f[l] = fprev; g.d[l] = dprev;
     }
     double R = rprev, F = fprev, G = dprev;
@@ -202,14 +218,20 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
     cp_async_commit();
   };
 
+  auto lam_of = [&](long tile) {                           // dead lanes of a ragged last tile: any regular column
+    const long col = tile * TI + lane;
+    return (col < ncol) ? __ldg(lam + col) : -1.0;
+  };
   long tile = blockIdx.x;
-  if (tile < ntiles) fetch(tile);
+  double lm_next = 0.0;
+  if (tile < ntiles) { fetch(tile); lm_next = lam_of(tile); }
   __syncthreads();                                        // coefficients staged
 
   for (; tile < ntiles; tile += gridDim.x) {
     const long col = tile * TI + lane;
     const bool live = col < ncol;
-    const double lm = live ? __ldg(lam + col) : -1.0;
+    const double lm = lm_next;                            // loaded one tile ahead
+    if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
     const bool pin = T.singular && live && (lm == 0.0);
     double v[L];
     cp_async_wait_all();

@@ -124,6 +124,25 @@ int flutas_b200_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dz
                        const double *dzfi, const double *u, const double *v, const double *w,
                        double *divtot, double *divmax);
 
+/* boundp, src/bound.f90:146-225 (with set_bc :227-420 and updthalo :946-1110), halo width nh_p = 1:
+ * ghost cells of a cell-centred scalar (p, pold) for the reference's _DECOMP_X layout.  Same step order as
+ * the reference (y halo, z halo, x faces, y faces, z faces), so edges and corners are bit-identical.
+ * cbc(0:1,3) as six characters, bc(0:1,3) the six boundary values, dl(3), dzc(1-nh_d:) / dzf(1-nh_d:)
+ * (dzf is unused, like in the reference).  The reference's `halo` argument (MPI datatypes) has no
+ * counterpart.  On a z-slab decomposition (flutas_b200_init with nranks > 1) the z halo planes come from
+ * the neighbouring ranks through the callback registered with flutas_b200_set_halo_exchange; ranks at a
+ * non-periodic wall apply the boundary condition instead (neighbour = MPI_PROC_NULL in the reference). */
+int flutas_b200_boundp(const char cbc[6], const int n[3], const double bc[6], int nh_d, int nh_p,
+                       const double dl[3], const double *dzc, const double *dzf, double *p);
+
+/* z-halo exchange for flutas_b200_boundp on several ranks: send `count` doubles from send_lo to rank `lo`
+ * and from send_hi to rank `hi`, receive the same amounts into recv_lo (from lo) and recv_hi (from hi),
+ * all device pointers, ordered on `stream`; lo / hi = -1 means no neighbour (skip that pair).
+ * Must return 0 on success.  Counterpart of the MPI_SENDRECV pair of updthalo (src/bound.f90:1098-1103). */
+typedef int (*flutas_b200_halo_fn)(void *ctx, const double *send_lo, const double *send_hi, double *recv_lo,
+                                   double *recv_hi, size_t count, int lo, int hi, void *stream);
+int flutas_b200_set_halo_exchange(flutas_b200_halo_fn fn, void *ctx);
+
 /* Optional per-stage device timing (CUDA events on the library stream), the counterpart of the
  * reference's named profiler clocks (src/profiler.f90:103-205; labels "SOLVER", "CORREC", ...).
  * Stage ids 0..count-1 have names ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd", "fillps",

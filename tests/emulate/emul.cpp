@@ -5,6 +5,7 @@
 // checked against the oracle without a GPU.  Nothing in the product links this file.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../flutas_b200/csrc/line_plan.h"
@@ -193,4 +194,85 @@ extern "C" int emul_thomas_reg(int L, int nz, long ncol, int periodic, int singu
 extern "C" int emul_thomas_reg_pick(int nz, int periodic) {
   int L = 0;
   return thomas_reg_pick(nz, periodic != 0, &L) ? L : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// register-resident transforms (flutas_b200/csrc/reg_fft.cuh): the per-thread functions the kernels call, run
+// serially over the T threads of one line with the phase boundaries where the kernels synchronise.
+struct EmulXB {                          // exchange buffer of one line (the kernels add padding / lanes)
+  double* re; double* im;
+  void st(int pos, double r, double i) const { re[pos] = r; im[pos] = i; }
+  void ld(int pos, double& r, double& i) const { r = re[pos]; i = im[pos]; }
+};
+
+template <int M>
+static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
+  using S = RegSched<M>;
+  constexpr int T = S::T, R = S::R, N = 2 * M;
+  std::vector<double> bre(M), bim(M);
+  EmulXB xb{bre.data(), bim.data()};
+  std::vector<double> re((size_t)T * R), im((size_t)T * R);
+  auto RE = [&](int j) { return re.data() + (size_t)j * R; };
+  auto IM = [&](int j) { return im.data() + (size_t)j * R; };
+  const cpx* tw[RF_MAXPASS] = {nullptr, hp.tw[1].data(), hp.tw[2].data()};
+  auto passes = [&](auto sign) {
+    constexpr int SIGN = decltype(sign)::value;
+    for (int j = 0; j < T; ++j) reg_pass<M, 0, SIGN>(RE(j), IM(j), j, tw[0], xb);
+    if constexpr (S::NP > 1) {
+      for (int j = 0; j < T; ++j) reg_gather<M>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) reg_pass<M, 1, SIGN>(RE(j), IM(j), j, tw[1], xb);
+    }
+    if constexpr (S::NP > 2) {
+      for (int j = 0; j < T; ++j) reg_gather<M>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) reg_pass<M, 2, SIGN>(RE(j), IM(j), j, tw[2], xb);
+    }
+  };
+  if (fwd) {
+    for (int j = 0; j < T; ++j)
+      for (int u = 0; u < R; ++u) {
+        int e0, e1; double s0, s1;
+        reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
+        RE(j)[u] = s0 * in[e0]; IM(j)[u] = s1 * in[e1];
+      }
+    passes(std::integral_constant<int, -1>{});
+    for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
+    for (int j = 0; j < T; ++j) reg_split<M>(RE(j), IM(j), j, hp.kind, hp.wN.data(), hp.wQ.data(), xb);
+    for (int j = 0; j < T; ++j)
+      for (int u = 0; u < R; ++u) { const int k = j + T * u; out[2 * k] = scale * RE(j)[u]; out[2 * k + 1] = scale * IM(j)[u]; }
+  } else {
+    for (int j = 0; j < T; ++j)
+      for (int u = 0; u < R; ++u) { const int k = j + T * u; RE(j)[u] = in[2 * k]; IM(j)[u] = in[2 * k + 1]; }
+    for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
+    for (int j = 0; j < T; ++j) reg_merge<M>(RE(j), IM(j), j, hp.kind, hp.wN.data(), hp.wQ.data(), xb);
+    passes(std::integral_constant<int, +1>{});
+    for (int j = 0; j < T; ++j)
+      for (int u = 0; u < R; ++u) {
+        int e0, e1; double s0, s1;
+        reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
+        out[e0] = s0 * scale * RE(j)[u]; out[e1] = s1 * scale * IM(j)[u];
+      }
+  }
+}
+
+extern "C" int emul_reg_line_transform(int N, int kind, int fwd, const double* in, double* out, double scale) {
+  HostRegPlan hp = make_reg_plan(N, kind);
+  if (!hp.ok) return 1;
+  switch (hp.M) {
+    case 16: reg_line_emul<16>(hp, fwd, in, out, scale); break;
+    case 32: reg_line_emul<32>(hp, fwd, in, out, scale); break;
+    case 64: reg_line_emul<64>(hp, fwd, in, out, scale); break;
+    case 128: reg_line_emul<128>(hp, fwd, in, out, scale); break;
+    case 256: reg_line_emul<256>(hp, fwd, in, out, scale); break;
+    case 512: reg_line_emul<512>(hp, fwd, in, out, scale); break;
+    case 1024: reg_line_emul<1024>(hp, fwd, in, out, scale); break;
+    default: return 2;
+  }
+  return 0;
+}
+
+extern "C" int emul_reg_mode_index(int N, int kind, int* mode) {
+  HostRegPlan hp = make_reg_plan(N, kind);
+  if (!hp.ok) return 1;
+  std::memcpy(mode, hp.mode.data(), sizeof(int) * (size_t)N);
+  return 0;
 }

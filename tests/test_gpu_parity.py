@@ -16,7 +16,7 @@ TOL = 1e-12
 def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
     s = case.setup
     n = case.ng
-    lib.load().flutas_b200_debug_generic_fft(1 if generic_fft else 0)
+    lib.load().flutas_b200_debug_generic_fft(int(generic_fft))     # 0 = register kernels, 1 = generic tile, 2 = p2 tile
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
     assert nf == s.normfft
     if z_mode:                                        # 1 = generic scratch-field kernels, 2 = shared-memory tile kernel
@@ -33,6 +33,7 @@ def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
     else:
         api.solver(n, pl, nf, s.lambdaxy, s.a, s.b, s.c, case.cbc[2], "ccc", p)
     api.fftend(pl)
+    lib.load().flutas_b200_debug_generic_fft(0)
     halo = p.copy()
     halo[1:-1, 1:-1, 1:-1] = 7.0
     assert np.all(halo == 7.0)
@@ -80,8 +81,8 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,ng,cbc,lengths,gr", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("device,generic_fft", [(False, False), (True, False), (True, True)],
-                         ids=["hostptr", "devptr", "devptr-genericfft"])
+@pytest.mark.parametrize("device,generic_fft", [(False, 0), (True, 0), (True, 1), (True, 2)],
+                         ids=["hostptr", "devptr", "devptr-genericfft", "devptr-p2fft"])
 def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device, generic_fft):
     case = Case(ng, cbc, lengths, gr=gr, seed=4242 + len(name), name=name)
     s = case.setup

@@ -20,13 +20,15 @@ def emul():
     src = os.path.join(HERE, "emulate", "emul.cpp")
     so = os.path.join(HERE, "emulate", "libemul.so")
     deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f)
-                    for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh")]
+                    for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "reg_fft.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.emul_line_transform.argtypes = [C.c_int] * 6 + [_dp, _dp, C.c_double]
     L.emul_mode_index.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.emul_reg_line_transform.argtypes = [C.c_int] * 3 + [_dp, _dp, C.c_double]
+    L.emul_reg_mode_index.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -68,6 +70,35 @@ def test_tile_forward_matches_fftw_definition(emul, bc, n, tb, rot):
     assert emul.emul_line_transform(n, KIND[bc], tb, rot, nworkers, 0, spec.ctypes.data_as(_dp),
                                     back.ctypes.data_as(_dp), 1.0) == 0
     assert np.max(np.abs(back - refb)) <= 5e-14 * max(1.0, np.max(np.abs(refb)))
+
+
+# ---- register-resident transforms (reg_fft.cuh) --------------------------------------------------
+@pytest.mark.parametrize("bc", ["PP", "NN", "DD"])
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048])
+def test_reg_fft_matches_fftw_definition(emul, bc, n):
+    rng = np.random.default_rng(7 * n + len(bc))
+    nl = 3
+    x = rng.uniform(-1, 1, (nl, n))
+    kf, kb, norm = oracle.find_fft(bc)
+    ref = oracle.r2r(kf, np.asfortranarray(x.T.reshape(n, nl, 1).copy()), 0)[:, :, 0].T      # FFTW order
+    mode = (C.c_int * n)()
+    assert emul.emul_reg_mode_index(n, KIND[bc], mode) == 0
+    mode = np.array(mode[:])
+    assert sorted(mode) == list(range(n))
+    spec = rng.uniform(-1, 1, (nl, n))                       # arbitrary (non-consistent) spectrum
+    fftw_order = np.zeros_like(spec)
+    fftw_order[:, mode] = spec
+    refb = oracle.r2r(kb, np.asfortranarray(fftw_order.T.reshape(n, nl, 1).copy()), 0)[:, :, 0].T
+    for l in range(nl):
+        out, back, back2 = np.zeros(n), np.zeros(n), np.zeros(n)
+        xin = np.ascontiguousarray(x[l])
+        assert emul.emul_reg_line_transform(n, KIND[bc], 1, xin.ctypes.data_as(_dp), out.ctypes.data_as(_dp), 1.0) == 0
+        assert np.max(np.abs(out - ref[l, mode])) <= 5e-14 * max(1.0, np.max(np.abs(ref[l])))
+        assert emul.emul_reg_line_transform(n, KIND[bc], 0, out.ctypes.data_as(_dp), back.ctypes.data_as(_dp), 1.0) == 0
+        assert np.max(np.abs(back - xin * norm[0] * (n + norm[1]))) <= 1e-13 * n
+        sp = np.ascontiguousarray(spec[l])
+        assert emul.emul_reg_line_transform(n, KIND[bc], 0, sp.ctypes.data_as(_dp), back2.ctypes.data_as(_dp), 0.5) == 0
+        assert np.max(np.abs(back2 - 0.5 * refb[l])) <= 5e-14 * max(1.0, np.max(np.abs(refb[l])))
 
 
 def test_unsupported_lengths_are_rejected(emul):
