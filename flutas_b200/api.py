@@ -118,6 +118,18 @@ def correc(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, dzci, dt, rho0, p, u, v, w, rh
                                               _ptr(p), _ptr(u), _ptr(v), _ptr(w), None))
 
 
+def boundp(cbc, n, bc, nh_d, nh_p, dl, dzc, dzf, p):
+    """boundp(cbc,n,bc,nh_d,nh_p,halo,dl,dzc,dzf,p), src/bound.f90:146 (the MPI `halo` datatypes have no counterpart).
+    cbc: three 2-character strings; bc: (3,2) boundary values."""
+    _use_torch_stream()
+    nn = (C.c_int * 3)(*n)
+    bcv = (C.c_double * 6)(*[float(bc[d][s]) for d in range(3) for s in range(2)])
+    dlv = (C.c_double * 3)(*[float(x) for x in dl])
+    _lib.check(_lib.load().flutas_b200_boundp("".join(cbc).encode(), nn, bcv, nh_d, nh_p, dlv, _ptr(dzc), _ptr(dzf),
+                                              _ptr(p)))
+    return p
+
+
 def chkdiv(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzfi, u, v, w):
     _use_torch_stream()
     tot, mx = C.c_double(), C.c_double()

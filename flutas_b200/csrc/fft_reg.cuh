@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "geom.cuh"
 #include "reg_fft.cuh"
 
@@ -45,6 +47,8 @@ struct YTileBuf {
     r = v.x; i = v.y;
   }
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int M>
 __device__ __forceinline__ void reg_stage_tw(cpx* s1, cpx* s2, const RegPlan& P, int tid, int nthr) {
@@ -86,14 +90,35 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   const long nlines = gs.nlines;
   const long ngroups = (nlines + LG - 1) / LG;
   const long gstride = WARP ? (long)gridDim.x * 8 : (long)gridDim.x;
+  // Periodic lines whose SECOND element is 16-byte aligned (the halo'd p of the caller: interior starts at an odd
+  // element) are packed one element late, z_m = x_{2m+1} + i x_{2m+2} (indices mod N), so that all but one of
+  // the physical accesses are aligned 16-byte vectors.  A cyclic shift only multiplies mode k by a unit
+  // phase, which commutes with the (real, per-mode) z solve; the backward kernel stores with the same shift.
+  const LineGeom& gph = FWD ? gs : gd;
+  const bool shift = (kind == KIND_PP) && ((reinterpret_cast<uintptr_t>(FWD ? (const void*)src : (const void*)dst) / 8 + gph.off0 + 1) % 2 == 0) &&
+                     (gph.sj % 2 == 0) && (gph.sk % 2 == 0);
   for (long g = WARP ? (long)blockIdx.x * 8 + gi : (long)blockIdx.x; g < ngroups; g += gstride) {
     const long line = g * LG + lw;
     const bool live = line < nlines;
     const long lc = live ? line : nlines - 1;
+    {                                                  // next group's line -> L2 while this one is transformed
+      const long ln = min(line + gstride * LG, nlines - 1);
+      const double* pn = src + line_offset(gs, ln) + (N / T) * j;
+#pragma unroll
+      for (int q = 0; q < (N / T) / 16; ++q) prefetch_l2(pn + 16 * q);
+    }
     double re[R], im[R];
     if (FWD) {
       const double* ps = src + line_offset(gs, lc);
-      if (kind == KIND_PP) {
+      if (shift) {
+        const double2* pa = reinterpret_cast<const double2*>(ps + 1);
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int m = j + T * u;
+          if (u == R - 1 && j == T - 1) { re[u] = ps[N - 1]; im[u] = ps[0]; }
+          else { const double2 v = pa[m]; re[u] = v.x; im[u] = v.y; }
+        }
+      } else if (kind == KIND_PP) {
 #pragma unroll
         for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
       } else {
@@ -116,7 +141,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
     } else {
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
 #pragma unroll
-      for (int u = 0; u < R; ++u) { const double2 v = __ldcs(ps + (j + T * u)); re[u] = v.x; im[u] = v.y; }
+      for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = v.x; im[u] = v.y; }
       reg_scatter_modes<M>(re, im, j, xb);
       sync();
       reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
@@ -124,7 +149,15 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
       if (live) {
         double* pd = dst + line_offset(gd, line);
-        if (kind == KIND_PP) {
+        if (shift) {
+          double2* pa = reinterpret_cast<double2*>(pd + 1);
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const int m = j + T * u;
+            if (u == R - 1 && j == T - 1) { pd[N - 1] = scale * re[u]; pd[0] = scale * im[u]; }
+            else pa[m] = make_double2(scale * re[u], scale * im[u]);
+          }
+        } else if (kind == KIND_PP) {
 #pragma unroll
           for (int u = 0; u < R; ++u) { const int m = j + T * u; pd[2 * m] = scale * re[u]; pd[2 * m + 1] = scale * im[u]; }
         } else {
@@ -145,14 +178,16 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
 template <int N>
 struct YRegShape {
   static constexpr int T = RegSched<N / 2>::T;
-  static constexpr int TB = (256 / T > 32) ? 32 : 256 / T;
+  static constexpr int NTMAX = (T >= 32) ? 512 : 256;      // 16 lanes (128-byte rows) up to N = 1024
+  static constexpr int TB = (NTMAX / T > 32) ? 32 : NTMAX / T;
   static constexpr int NT = TB * T;
+  static constexpr int MINB = (NT > 256) ? 1 : 2;
   static constexpr size_t smem = (size_t)(RegTw<N / 2>::n1 + RegTw<N / 2>::n2) * sizeof(cpx) +
                                  (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
 };
 
 template <int N, bool FWD>
-__global__ void __launch_bounds__(YRegShape<N>::NT, 2)
+__global__ void __launch_bounds__(YRegShape<N>::NT, YRegShape<N>::MINB)
 yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
   constexpr int M = N / 2;
   using S = RegSched<M>;
@@ -178,6 +213,26 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
     const int il = i0 + (live ? lane : 0);
     double* base = W + (long)n1 * N * k + il;               // physical side
     double* sbase = spec_base(sg, il, N, k);                 // spectral side (pencil chunk of the exchange)
+    {                                                        // next tile -> L2 while this one is transformed
+      const long tn = tile + gridDim.x;
+      if (tn < ntiles) {
+        const int tin = (int)(tn % ntile_i);
+        const long kn = tn / ntile_i;
+        const int iln = min(tin * TB, n1 - 1);
+        const double* pn = FWD ? (W + (long)n1 * N * kn + iln) : spec_base(sg, iln, N, kn);
+        const long sn = FWD ? stride : sstride;
+        constexpr int ROWS_PER_LANE = (2 * R + TB - 1) / TB;   // this thread's 2R rows, shared out over the TB lanes
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_LANE; ++q) {
+          const int idx = lane * ROWS_PER_LANE + q;            // 0 .. 2R-1 -> (u, re/im)
+          if (idx < 2 * R) {
+            int row = 2 * (j + T * (idx >> 1)) + (idx & 1);
+            if (FWD && kind != KIND_PP) { int e0, e1; double s0, s1; reg_phys_slots(kind, N, j + T * (idx >> 1), e0, e1, s0, s1); row = (idx & 1) ? e1 : e0; }
+            prefetch_l2(pn + (long)row * sn);
+          }
+        }
+      }
+    }
     double re[R], im[R];
     if (FWD) {
       if (kind == KIND_PP) {
@@ -207,8 +262,8 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
 #pragma unroll
       for (int u = 0; u < R; ++u) {
         const int kk = j + T * u;
-        re[u] = __ldcs(sbase + (long)(2 * kk) * sstride);
-        im[u] = __ldcs(sbase + (long)(2 * kk + 1) * sstride);
+        re[u] = sbase[(long)(2 * kk) * sstride];
+        im[u] = sbase[(long)(2 * kk + 1) * sstride];
       }
       reg_scatter_modes<M>(re, im, j, xb);
       sync();

@@ -181,3 +181,62 @@ def gaussel(a, b, c, lambdaxy, pz, periodic):
     f = lib().oracle_gaussel_periodic if periodic else lib().oracle_gaussel
     f(nx, ny, n, _p(a), _p(b), _p(c), _p(np.asfortranarray(lambdaxy)), _p(pz))
     return pz
+
+
+# ---------------------------------------------------------------------------------------------------
+# boundp (numpy restatement; the arithmetic is one multiply-add per ghost cell, so numpy is bit-exact)
+def _set_bc(p, ctype, ibound, idir, rvalue, dr):
+    """set_bc, src/bound.f90:227-420, centred, nh_p = 1: ghost = factor + sgn * inner."""
+    n = p.shape[idir] - 2
+    ghost = [slice(None)] * 3
+    inner = [slice(None)] * 3
+    if ctype == "P":                                      # bound.f90:268-318 (both sides at once)
+        lo, hi, first, last = ([slice(None)] * 3 for _ in range(4))
+        lo[idir], hi[idir], first[idir], last[idir] = 0, n + 1, 1, n
+        p[tuple(lo)] = p[tuple(last)]
+        p[tuple(hi)] = p[tuple(first)]
+        return
+    factor, sgn = np.float64(rvalue), np.float64(0.0)
+    if ctype == "D":                                      # :247-252
+        factor, sgn = np.float64(2.0) * factor, np.float64(-1.0)
+    if ctype == "N":                                      # :253-264
+        factor = -np.float64(dr) * factor if ibound == 0 else np.float64(dr) * factor
+        sgn = np.float64(1.0)
+    ghost[idir], inner[idir] = (0, 1) if ibound == 0 else (n + 1, n)
+    p[tuple(ghost)] = factor + sgn * p[tuple(inner)]      # :334,350,...
+
+
+def boundp(cbc, n, bc, nh_d, dl, dzc, p, below=None, above=None, first_rank=True, last_rank=True):
+    """boundp, src/bound.f90:146-225, for the _DECOMP_X layout with the y direction undivided (z-slabs).
+
+    cbc: three 2-character strings, bc: (3,2) values, dzc(1-nh_d:), p(0:n1+1,0:n2+1,0:n3+1) updated in place.
+    Single rank: below = above = None.  On a slab decomposition `below` / `above` are the neighbouring
+    ranks' planes p(:,:,n3) / p(:,:,1) *after their own y-halo update* (what MPI_SENDRECV delivers,
+    bound.f90:1098-1103), or None where the neighbour is MPI_PROC_NULL."""
+    n3 = n[2]
+    py, pz = cbc[1] == "PP", cbc[2] == "PP"
+    if py:                                                # updthalo, idir = 2: the rank is its own neighbour
+        _set_bc(p, "P", 0, 1, 0.0, 0.0)
+    single = below is None and above is None and first_rank and last_rank
+    if single:
+        if pz:                                            # updthalo, idir = 3
+            _set_bc(p, "P", 0, 2, 0.0, 0.0)
+    else:
+        if below is not None:
+            p[:, :, 0] = below
+        if above is not None:
+            p[:, :, n3 + 1] = above
+    if cbc[0] == "PP":                                    # x: left = right = MPI_PROC_NULL -> set_bc (initmpi.f90:124)
+        _set_bc(p, "P", 0, 0, 0.0, 0.0)
+    else:
+        _set_bc(p, cbc[0][0], 0, 0, bc[0][0], dl[0])
+        _set_bc(p, cbc[0][1], 1, 0, bc[0][1], dl[0])
+    if not py:
+        _set_bc(p, cbc[1][0], 0, 1, bc[1][0], dl[1])
+        _set_bc(p, cbc[1][1], 1, 1, bc[1][1], dl[1])
+    if not pz:
+        if first_rank:
+            _set_bc(p, cbc[2][0], 0, 2, bc[2][0], dzc[nh_d - 1])           # dr = dzc(0)
+        if last_rank:
+            _set_bc(p, cbc[2][1], 1, 2, bc[2][1], dzc[nh_d - 1 + n3])      # dr = dzc(n3)
+    return p
