@@ -184,6 +184,7 @@ struct SolverPlan {
   double key_lam_samples[3] = {0, 0, 0};
   bool cache_valid = false;
   int thomas_mode = 0;           // 0 = auto, 1 = force generic (tests)
+  ThomasArgs z_uniform{};        // scalar coefficients when the z grid is exactly uniform (thomas_reg.cuh)
   // slab (multi-GPU) state
   DevBuf sendrecv, pencil, lam_win;
   bool p2p = false;
@@ -220,6 +221,7 @@ int launch_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst,
   LAUNCHED();
   return 0;
 }
+bool g_z_uniform_ok = true;   // test hook (thomas mode 3): ignore the uniform-grid fast path
 int g_fft_level = 0;   // test hook: 0 = register kernels where available, 1 = run-time-radix tile kernels only,
                        // 2 = tile kernels (power-of-two specialisations allowed) but no register kernels
 
@@ -330,6 +332,13 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
                                                                              maps + n1, sp->lam_int.as<double>());
   LAUNCHED();
   CK(cudaStreamSynchronize(g_stream));
+  {                                                      // exactly uniform z grid -> scalar coefficients for the z solve
+    std::vector<double> ha(nz), hb(nz), hc(nz);
+    CK(cudaMemcpy(ha.data(), a, nz * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(hb.data(), b, nz * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(hc.data(), c, nz * sizeof(double), cudaMemcpyDefault));
+    thomas_detect_uniform(nz, ha.data(), hb.data(), hc.data(), periodic, sp->z_uniform);
+  }
   sp->cached_nz = nz;
   sp->cached_periodic = periodic;
   sp->key_lam = lambdaxy;
@@ -360,7 +369,7 @@ int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const
   bool done = false;
   if (sp->thomas_mode == 0) {                               // register-resident persistent kernel
     int rc = thomas_reg_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, W, out, periodic, singular,
-                            g_nsm > 0 ? g_nsm : 148, g_stream, &done);
+                            g_nsm > 0 ? g_nsm : 148, g_z_uniform_ok ? &sp->z_uniform : nullptr, g_stream, &done);
     if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_reg launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
   }
@@ -592,7 +601,8 @@ int flutas_b200_debug_generic_fft(int level) {
 int flutas_b200_debug_thomas_mode(void* const arrplan[4], int mode) {
   SolverPlan* sp = plan_of(arrplan);
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "not a flutas_b200 plan");
-  sp->thomas_mode = mode;
+  g_z_uniform_ok = (mode != 3);                          // 3 = register kernel with coefficient tables even on a uniform grid
+  sp->thomas_mode = (mode == 3) ? 0 : mode;
   return FLUTAS_B200_OK;
 }
 
@@ -747,10 +757,11 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   const size_t chunk = (size_t)n1l * n2 * n3l, nloc = chunk * P;
   if (!was_valid || !sp->cache_valid || sp->lam_win.cap < (size_t)n1l * n2 * sizeof(double)) {
     if (int rc = sp->lam_win.reserve((size_t)n1l * n2 * sizeof(double))) return rc;
+    // this rank's x rows of the permuted eigenvalues: lam_win(i_l, ry) = lam_int(r*n1l + i_l, ry); constant until the
+    // coefficient cache is invalidated
+    CK(cudaMemcpy2DAsync(sp->lam_win.p, (size_t)n1l * sizeof(double), sp->lam_int.as<double>() + (size_t)r * n1l,
+                         (size_t)n1 * sizeof(double), (size_t)n1l * sizeof(double), n2, cudaMemcpyDeviceToDevice, g_stream));
   }
-  // this rank's x rows of the permuted eigenvalues: lam_win(i_l, ry) = lam_int(r*n1l + i_l, ry)
-  CK(cudaMemcpy2DAsync(sp->lam_win.p, (size_t)n1l * sizeof(double), sp->lam_int.as<double>() + (size_t)r * n1l,
-                       (size_t)n1 * sizeof(double), (size_t)n1l * sizeof(double), n2, cudaMemcpyDeviceToDevice, g_stream));
   if (int rc = sp->work.reserve(nloc * sizeof(double))) return rc;
   double* W1 = sp->work.as<double>();
   double *S = nullptr, *W2 = nullptr, *R = nullptr;

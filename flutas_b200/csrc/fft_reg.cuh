@@ -295,12 +295,16 @@ inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs
   constexpr int LPB = 256 / T;                         // lines per block per iteration
   const size_t smem = xfft_reg_smem<N>();
   auto kern = xfft_reg_kernel<N, FWD>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  static int per_sm = 0;                               // configured once per process (one device per process)
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = q;
+  }
   const long nblk = (gs.nlines + LPB - 1) / LPB;
   const long grid = nblk < (long)nsm * per_sm ? nblk : (long)nsm * per_sm;
   kern<<<(unsigned)grid, 256, smem, st>>>(P, src, gs, dst, gd, scale);
@@ -311,12 +315,16 @@ template <int N, bool FWD>
 inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
   using Y = YRegShape<N>;
   auto kern = yfft_reg_kernel<N, FWD>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Y::NT, Y::smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
+    if (e != cudaSuccess) return e;
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, Y::NT, Y::smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = q;
+  }
   const int nti = (n1 + Y::TB - 1) / Y::TB;
   const long ntiles = (long)nti * n3;
   const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;

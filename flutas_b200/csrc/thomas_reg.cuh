@@ -18,6 +18,8 @@
 //
 // HBM traffic: 16 B/pt (read once, write once).  Host-compilable core (tests/emulate) like tile_fft.cuh.
 #pragma once
+#include <type_traits>
+
 #include "thomas_tile.cuh"
 
 namespace fb {
@@ -26,6 +28,42 @@ template <int L>
 struct SegRegs {                 // per-thread state of the interior rows 0..L-2
   double rp[L], f[L], d[L];
 };
+
+// coefficients of this thread's rows l = 0..L-1: from the (padded, shared-memory) tables, or from a handful of
+// scalars when the z grid is uniform (no loads, and c_l z_l == a_l z_l is computed once)
+template <int L>
+struct CoefTable {
+  const double *az, *bz, *cz;
+  FB_HD CoefTable(const ThomasArgs& T, int s) : az(T.az + s * (L + 1)), bz(T.bz + s * (L + 1)), cz(T.cz + s * (L + 1)) {}
+  FB_HD double a(int l) const { return az[l]; }
+  FB_HD double b(int l) const { return bz[l]; }
+  FB_HD double c(int l) const { return cz[l]; }
+};
+template <int L>
+struct CoefUniform {
+  double a0, b0, af, bf, bl, cl;
+  bool first, last;
+  FB_HD CoefUniform(const ThomasArgs& T, int s)
+      : a0(T.a0), b0(T.b0), af(T.a_first), bf(T.b_first), bl(T.b_last), cl(T.c_last), first(s == 0), last(s == T.S - 1) {}
+  FB_HD double a(int l) const { return (l == 0 && first) ? af : a0; }
+  FB_HD double b(int l) const { return (l == 0 && first) ? bf : (l == L - 1 && last) ? bl : b0; }
+  FB_HD double c(int l) const { return (l == L - 1 && last) ? cl : a0; }
+};
+
+// true if (a,b,c) describe a uniform grid; fills the scalar fields of T.  az/cz conventions as ThomasArgs.
+inline bool thomas_detect_uniform(int nz, const double* a, const double* b, const double* c, bool periodic, ThomasArgs& T) {
+  T.uniform = 0; T.a0 = T.b0 = T.a_first = T.b_first = T.b_last = T.c_last = 0.0;
+  if (nz < 4) return false;
+  const double a0 = a[1], b0 = b[1];
+  if (c[0] != a0) return false;
+  for (int k = 1; k < nz; ++k) if (a[k] != a0) return false;
+  for (int k = 0; k < nz - 1; ++k) if (c[k] != a0) return false;
+  for (int k = 1; k < nz - 1; ++k) if (b[k] != b0) return false;
+  T.uniform = 1; T.a0 = a0; T.b0 = b0;
+  T.a_first = periodic ? a[0] : 0.0; T.b_first = b[0];
+  T.b_last = b[nz - 1]; T.c_last = periodic ? c[nz - 1] : 0.0;
+  return true;
+}
 
 template <int L, int TI>
 struct ThomasReg {
@@ -41,21 +79,22 @@ struct ThomasReg {
   //   x_l = rp_l - f_l X_{s-1} - d_l x_{l+1}   (x_{L-1} = X_s)
   //   ex[0..2] <- (R0, F0, G0): x_0     = R0 - F0 X_{s-1} - G0 X_s
   //   ex[3..5] <- (RD, FD, DD): x_{L-2} = RD - FD X_{s-1} - DD X_s
-  static FB_HD void phase1(const double* v, const ThomasArgs& T, double lam, int lane, int s, SegRegs<L>& g, double* ex) {
-    const int kc0 = s * (L + 1);                                          // padded coefficient row of level sL
+  template <class CF>
+  static FB_HD void phase1(const double* v, const ThomasArgs& T, const CF& cf, double lam, int lane, int s, SegRegs<L>& g,
+                           double* ex) {
     // Pivots without a serial division chain: the leading principal minors th_l = bb_l th_{l-1} - a_l c_{l-1} th_{l-2}
     // cost one dependent FMA per level; z_l = 1/(bb_l - a_l c_{l-1} z_{l-1}) = th_{l-1} / th_l are then L-1
     // independent reciprocals (same LU, the quotients are just formed at the end).
     double z[L];
     {
-      double thm = 1.0, th = T.bz[kc0] + lam;
+      double thm = 1.0, th = cf.b(0) + lam;
       z[0] = fb_rcp(th);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
       for (int l = 1; l < L - 1; ++l) {
-        const double gk = T.az[kc0 + l] * T.cz[kc0 + l - 1];
-        const double tn = (T.bz[kc0 + l] + lam) * th - gk * thm;
+        const double gk = cf.a(l) * cf.c(l - 1);
+        const double tn = (cf.b(l) + lam) * th - gk * thm;
         z[l] = th * fb_rcp(tn);
         thm = th; th = tn;
       }
@@ -66,10 +105,10 @@ struct ThomasReg {
 #endif
     for (int l = 0; l < L - 1; ++l) {
       const double zz = z[l];
-      const double azz = T.az[kc0 + l] * zz;
+      const double azz = cf.a(l) * zz;
       rprev = v[l] * zz - azz * rprev;
       fprev = (l == 0) ? azz : -azz * fprev;
-      dprev = T.cz[kc0 + l] * zz;
+      dprev = cf.c(l) * zz;
       g.rp[l] = rprev; g.f[l] = fprev; g.d[l] = dprev;
     }
     double R = rprev, F = fprev, G = dprev;
@@ -87,12 +126,12 @@ struct ThomasReg {
   }
 
   // ---- phase 2a: row of separator s of the reduced system, normalised to a unit diagonal: (A, C, R)
-  static FB_HD void reduced_row(double vsep, const double* ex, double* pcr, const ThomasArgs& T, double lam, int lane,
-                                int s, bool pin) {
+  template <class CF>
+  static FB_HD void reduced_row(double vsep, const double* ex, double* pcr, const ThomasArgs& T, const CF& cf, double lam,
+                                int lane, int s, bool pin) {
     const int S = T.S, st = S * TI, o = s * TI + lane;
     const int sn = (s + 1 == S) ? 0 : s + 1, on = sn * TI + lane;
-    const int kc = s * (L + 1) + L - 1;
-    const double ak = T.az[kc], ck = T.cz[kc], bk = T.bz[kc] + lam;       // ck = 0 on the last row unless periodic
+    const double ak = cf.a(L - 1), ck = cf.c(L - 1), bk = cf.b(L - 1) + lam;   // ck = 0 on the last row unless periodic
     const double r0 = ex[on], f0 = ex[st + on], g0 = ex[2 * st + on];
     const double rd = ex[3 * st + o], fd = ex[4 * st + o], dd = ex[5 * st + o];
     double A = -ak * fd;
@@ -180,7 +219,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // MAXT: upper bound of the block size TI*S (256 -> two blocks per SM, 512 -> one)
-template <int L, int TI, int MAXT>
+template <int L, int TI, int MAXT, bool UNI>
 __global__ void __launch_bounds__(MAXT, 512 / MAXT)
 thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const double* W,
                   ColGeom og) {
@@ -196,7 +235,7 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   double* X = pcrB + 3 * (size_t)st;                      // 1 array
   double* coef = X + st;                                  // az | bz | cz at padded rows
   const int lane = tid % TI, s = tid / TI;
-  {
+  if (!UNI) {
     const int tr = TR::tile_rows(nz);
     for (int k = tid; k < nz; k += nthr) {
       const int r = TR::prow(k);
@@ -204,6 +243,7 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
     }
     T.az = coef; T.bz = coef + tr; T.cz = coef + 2 * tr; T.padded = 1;
   }
+  using CF = typename std::conditional<UNI, CoefUniform<L>, CoefTable<L>>::type;
   // where this thread's levels go: chunk q of the output geometry (one GPU: the work array itself)
   const int k0 = s * L;
   const bool one_chunk = (og.n3l % L) == 0;
@@ -238,12 +278,13 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
 #pragma unroll
     for (int l = 0; l < L; ++l) v[l] = slots[l * MAXT + tid];
 
+    const CF cf(T, s);
     SegRegs<L> g;
-    TR::phase1(v, T, lm, lane, s, g, ex);
+    TR::phase1(v, T, cf, lm, lane, s, g, ex);
     const long next = tile + gridDim.x;
     if (next < ntiles) fetch(next);                       // v[] has been consumed: the slots are free again
     __syncthreads();
-    TR::reduced_row(v[L - 1], ex, pcrA, T, lm, lane, s, pin);
+    TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
     __syncthreads();
     double* src = pcrA;
     double* dst = pcrB;
@@ -273,34 +314,50 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   }
 }
 
-template <int L, int TI, int MAXT>
-inline cudaError_t thomas_reg_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
-                                     int nsm, cudaStream_t st) {
+template <int L, int TI, int MAXT, bool UNI>
+inline cudaError_t thomas_reg_launch1(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
+                                      int nsm, cudaStream_t st) {
   using TR = ThomasReg<L, TI>;
-  auto kern = thomas_reg_kernel<L, TI, MAXT>;
+  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI>;
   const size_t smem = TR::smem_doubles(T.nz, MAXT) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   const long ntiles = (ncol + TI - 1) / TI;
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TI * T.S, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  static int per_sm = 0, cfg_nz = 0;                      // configured once per (kernel, nz)
+  if (per_sm == 0 || cfg_nz != T.nz) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, TI * T.S, smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = q; cfg_nz = T.nz;
+  }
   const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
   kern<<<(unsigned)grid, TI * T.S, smem, st>>>(ncol, ntiles, T, lam, W, og);
   return cudaGetLastError();
 }
 
+template <int L, int TI, int MAXT>
+inline cudaError_t thomas_reg_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
+                                     int nsm, cudaStream_t st) {
+  return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true>(ncol, T, lam, W, og, nsm, st)
+                   : thomas_reg_launch1<L, TI, MAXT, false>(ncol, T, lam, W, og, nsm, st);
+}
+
 // *done = false if this nz is not served (caller falls back to thomas_tile / the generic kernels).
 inline int thomas_reg_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam,
                           const double* W, double* Wout, const ColGeom* out, bool periodic, int singular, int nsm,
-                          cudaStream_t st, bool* done) {
+                          const ThomasArgs* uni, cudaStream_t st, bool* done) {
   *done = false;
   int L = 0;
   if (!thomas_reg_pick(nz, periodic, &L)) return 0;
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
   T.padded = 0;
+  T.uniform = 0;
+  if (uni && uni->uniform) {
+    T.uniform = 1; T.a0 = uni->a0; T.b0 = uni->b0; T.a_first = uni->a_first; T.b_first = uni->b_first;
+    T.b_last = uni->b_last; T.c_last = uni->c_last;
+  }
   ColGeom og;
   if (out) og = *out;
   else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = Wout; og.n3l = nz; og.koff = 0; }

@@ -49,6 +49,9 @@ struct ThomasArgs {
   const double* bz;
   const double* cz;
   int padded;             // 1: coefficient arrays use the padded (shared-memory) index
+  // uniform z grid (every shipped deck): a_k = c_k = a0, b_k = b0 except in the first / last row
+  int uniform;
+  double a0, b0, a_first, b_first, b_last, c_last;
 };
 
 template <int L, int TI>
@@ -332,7 +335,7 @@ inline int thomas_tile_run(long ncol, int nz, const double* az, const double* bz
   if (!thomas_tile_pick(nz, periodic, &L)) return 0;
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
-  T.padded = 0;
+  T.padded = 0; T.uniform = 0;
   ColGeom og;
   if (out) og = *out;
   else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = W; og.n3l = nz; og.koff = 0; }

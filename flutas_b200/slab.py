@@ -53,6 +53,32 @@ class _DevPtr:
 
 
 _A2A_PROTO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+_HALO_PROTO = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                          C.c_void_p)
+
+
+def z_neighbours(rank, nranks, periodic):
+    """bottom / top ranks of a z-slab (MPI_CART_SHIFT along the decomposed direction, src/initmpi.f90:127);
+    -1 = MPI_PROC_NULL"""
+    lo = rank - 1 if rank > 0 else (nranks - 1 if periodic else -1)
+    hi = rank + 1 if rank < nranks - 1 else (0 if periodic else -1)
+    return lo, hi
+
+
+def halo_ops(dist, send_lo, send_hi, recv_lo, recv_hi, lo, hi, group=None):
+    """The MPI_SENDRECV pair of updthalo (src/bound.f90:1098-1103) as one batch of point-to-point operations.
+    Messages between the same two ranks match in posting order, so when lo == hi (two ranks, periodic) the
+    receives are posted top-halo first: the peer's first send is its bottom plane, which is this rank's top halo."""
+    ops = []
+    if lo >= 0:
+        ops.append(dist.P2POp(dist.isend, send_lo, lo, group))
+    if hi >= 0:
+        ops.append(dist.P2POp(dist.isend, send_hi, hi, group))
+    if hi >= 0:
+        ops.append(dist.P2POp(dist.irecv, recv_hi, hi, group))
+    if lo >= 0:
+        ops.append(dist.P2POp(dist.irecv, recv_lo, lo, group))
+    return ops
 
 
 class SlabComm:
@@ -112,6 +138,26 @@ class SlabComm:
         self.dist.all_gather_object(blobs, bytes(blob), group=self.group)
         allb = (C.c_char * (nb * self.nranks)).from_buffer_copy(b"".join(blobs))
         _lib.check(L.flutas_b200_p2p_attach(arrplan.h, allb))
+
+    def use_halo_exchange(self):
+        """z-halo planes of boundp through torch.distributed point-to-point (NCCL send/recv over NVLink)."""
+        import torch
+        dist, group = self.dist, self.group
+
+        def cb(ctx, send_lo, send_hi, recv_lo, recv_hi, count, lo, hi, stream):
+            try:
+                t = [torch.as_tensor(_DevPtr(ptr, count), device="cuda") for ptr in (send_lo, send_hi, recv_lo, recv_hi)]
+                ops = halo_ops(dist, t[0], t[1], t[2], t[3], lo, hi, group)
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                return 0
+            except Exception as e:
+                print("flutas_b200 halo callback failed:", e)
+                return 1
+
+        self._halo_cb = _HALO_PROTO(cb)
+        _lib.check(_lib.load().flutas_b200_set_halo_exchange(C.cast(self._halo_cb, C.c_void_p), None))
 
     def p2p_errors(self, arrplan):
         return _lib.load().flutas_b200_p2p_errors(arrplan.h)

@@ -138,9 +138,10 @@ extern "C" int emul_thomas_tile(int L, int nz, long ncol, int periodic, int sing
 // register Thomas (flutas_b200/csrc/thomas_reg.cuh): same phases as thomas_reg_kernel, serial over threads
 #include "../../flutas_b200/csrc/thomas_reg.cuh"
 
-template <int L, int TI>
+template <int L, int TI, bool UNI>
 static void thomas_reg_emul(long ncol, ThomasArgs T, const double* lam, double* W) {
   using TR = ThomasReg<L, TI>;
+  using CF = typename std::conditional<UNI, CoefUniform<L>, CoefTable<L>>::type;
   const int nz = T.nz, S = T.S, st = S * TI;
   const long ntiles = (ncol + TI - 1) / TI;
   // padded coefficient rows, as the kernel stages them
@@ -158,9 +159,9 @@ static void thomas_reg_emul(long ncol, ThomasArgs T, const double* lam, double* 
     auto vof = [&](int lane, int s) { return v.data() + ((size_t)s * TI + lane) * L; };
 #define ALLT for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
     ALLT { const long col = live(lane) ? colof(lane) : ncol - 1; for (int l = 0; l < L; ++l) vof(lane, s)[l] = W[col + (long)(s * L + l) * ncol]; }
-    ALLT TR::phase1(vof(lane, s), T, lamof(lane), lane, s, regs[s * TI + lane], ex.data());
+    ALLT TR::phase1(vof(lane, s), T, CF(T, s), lamof(lane), lane, s, regs[s * TI + lane], ex.data());
     ALLT { const bool pin = T.singular && live(lane) && lamof(lane) == 0.0;
-           TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, lamof(lane), lane, s, pin); }
+           TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, CF(T, s), lamof(lane), lane, s, pin); }
     double* src = pa.data(); double* dst = pb.data();
     const int hmax = T.periodic ? S / 2 : S;
     for (int h = 1; h < hmax; h *= 2) { ALLT TR::pcr_step(src, dst, T, lane, s, h); double* t = src; src = dst; dst = t; }
@@ -172,22 +173,27 @@ static void thomas_reg_emul(long ncol, ThomasArgs T, const double* lam, double* 
 }
 
 extern "C" int emul_thomas_reg(int L, int nz, long ncol, int periodic, int singular, const double* a, const double* b,
-                               const double* c, const double* lam, double* W) {
+                               const double* c, const double* lam, double* W, int allow_uniform) {
   if (nz % L) return 1;
   std::vector<double> az(a, a + nz), cz(c, c + nz);
   if (!periodic) { az[0] = 0.0; cz[nz - 1] = 0.0; }
   ThomasArgs T;
   T.nz = nz; T.S = nz / L; T.periodic = periodic; T.singular = singular; T.az = az.data(); T.bz = b; T.cz = cz.data();
   T.padded = 0;
+  T.uniform = 0;
   if (T.S < 2) return 2;
   if (periodic && (T.S & (T.S - 1))) return 2;
+  const bool uni = allow_uniform && thomas_detect_uniform(nz, a, b, c, periodic != 0, T);
+  if (allow_uniform == 2 && !uni) return 4;                  // the caller expected the uniform path
+#define RUN(LL) if (uni) thomas_reg_emul<LL, 8, true>(ncol, T, lam, W); else thomas_reg_emul<LL, 8, false>(ncol, T, lam, W); break;
   switch (L) {
-    case 2: thomas_reg_emul<2, 8>(ncol, T, lam, W); break;
-    case 4: thomas_reg_emul<4, 8>(ncol, T, lam, W); break;
-    case 8: thomas_reg_emul<8, 8>(ncol, T, lam, W); break;
-    case 16: thomas_reg_emul<16, 8>(ncol, T, lam, W); break;
+    case 2: RUN(2)
+    case 4: RUN(4)
+    case 8: RUN(8)
+    case 16: RUN(16)
     default: return 3;
   }
+#undef RUN
   return 0;
 }
 

@@ -70,6 +70,23 @@ def main():
                   flush=True)
         ok = ok and err <= 1e-12 and nerr == 0
         api.fftend(plan)
+        # boundp on the slabs (z halo planes through NCCL send/recv): bit-exact against the single-rank oracle
+        comm.use_halo_exchange()
+        bc = np.array([[0.0, 0.0], [0.2, -0.1], [0.3, 0.7]]) * (np.array([c != "PP" for c in cbc])[:, None])
+        rng = np.random.default_rng(5)
+        full = np.asfortranarray(rng.uniform(-1, 1, (n1 + 2, n2 + 2, n3 + 2)))
+        bref = oracle.boundp(cbc, ng, bc, s.nh_d, s.dl, s.dzc, full.copy(order="F"))
+        mine = np.asfortranarray(full[:, :, k0:k0 + n3l + 2].copy())
+        md = api.device_field(mine)
+        dzc_loc = np.ascontiguousarray(s.dzc[k0:k0 + n3l + 2 * s.nh_d])
+        api.boundp(cbc, nl, bc, s.nh_d, 1, s.dl, dzc_loc, dzc_loc, md)
+        torch.cuda.synchronize()
+        same = np.array_equal(api.host_field(md, mine.shape), bref[:, :, k0:k0 + n3l + 2])
+        flag = torch.tensor([0 if same else 1], device="cuda")
+        dist.all_reduce(flag)
+        if rank == 0:
+            print("slab boundp x%d %-5s %s: %s" % (world, name, "/".join(cbc), "bit-exact" if flag.item() == 0 else "MISMATCH"), flush=True)
+        ok = ok and flag.item() == 0
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

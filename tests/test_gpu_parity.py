@@ -19,7 +19,7 @@ def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
     lib.load().flutas_b200_debug_generic_fft(int(generic_fft))     # 0 = register kernels, 1 = generic tile, 2 = p2 tile
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
     assert nf == s.normfft
-    if z_mode:                                        # 1 = generic scratch-field kernels, 2 = shared-memory tile kernel
+    if z_mode:                   # 1 = generic scratch-field kernels, 2 = shared-memory tile kernel, 3 = no uniform-grid path
         lib.check(lib.load().flutas_b200_debug_thomas_mode(pl.h, z_mode))
     p = case.new_p()
     p[...] = 7.0                                      # halos must come back untouched
@@ -42,7 +42,7 @@ def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
 
 @pytest.mark.parametrize("path", [f for f in golden_files() if "ndp" not in f and "pdn" not in f],
                          ids=lambda p: p.split("/")[-1][:-4])
-@pytest.mark.parametrize("z_mode", [0, 2, 1], ids=["zreg", "ztile", "zgeneric"])
+@pytest.mark.parametrize("z_mode", [0, 3, 2, 1], ids=["zreg", "zreg-tables", "ztile", "zgeneric"])
 def test_solver_matches_golden(path, z_mode):
     case, rhs, pgold = load_golden(path)
     p = _solve_gpu(case, rhs, z_mode=z_mode)

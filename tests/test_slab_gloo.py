@@ -100,3 +100,55 @@ def test_pack_unpack_roundtrip_layout():
                             for r in range(P)]) for q in range(P)]
     for q in range(P):
         assert np.array_equal(slab.unpack_spec(back[q], n1, n2, n3l, P), slabs[q])
+
+
+# ---- boundp on z-slabs: the halo exchange of flutas_b200.slab (same op ordering as the NCCL callback) --------
+def _boundp_worker(rank, world, port, cbc, ng, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = Case(ng, cbc, (2.0, 1.0, 1.0), gr=(1.0 if cbc[2] != "PP" else 0.0), seed=8)
+        s = case.setup
+        n1, n2, n3 = ng
+        n3l = n3 // world
+        k0, _ = slab.local_levels(n3, rank, world)
+        rng = np.random.default_rng(12)
+        full = np.asfortranarray(rng.uniform(-1, 1, (n1 + 2, n2 + 2, n3 + 2)))
+        mine = np.asfortranarray(full[:, :, k0:k0 + n3l + 2].copy())
+        bc = np.array([[0.0, 0.0], [0.2, -0.1], [0.3, 0.7]]) * (np.array([c != "PP" for c in cbc])[:, None])
+        # what flutas_b200_boundp does on a slab: y halo, then the z planes through the exchange, then set_bc
+        if cbc[1] == "PP":
+            oracle._set_bc(mine, "P", 0, 1, 0.0, 0.0)
+        lo, hi = slab.z_neighbours(rank, world, cbc[2] == "PP")
+        send_lo = torch.from_numpy(np.ascontiguousarray(mine[:, :, 1].T))
+        send_hi = torch.from_numpy(np.ascontiguousarray(mine[:, :, n3l].T))
+        recv_lo, recv_hi = torch.empty_like(send_lo), torch.empty_like(send_hi)
+        ops = slab.halo_ops(dist, send_lo, send_hi, recv_lo, recv_hi, lo, hi)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        mine2 = np.asfortranarray(full[:, :, k0:k0 + n3l + 2].copy())
+        dzc_loc = s.dzc[k0:k0 + n3l + 2 * s.nh_d]
+        oracle.boundp(cbc, (n1, n2, n3l), bc, s.nh_d, s.dl, dzc_loc, mine2,
+                      below=recv_lo.numpy().T if lo >= 0 else None, above=recv_hi.numpy().T if hi >= 0 else None,
+                      first_rank=(rank == 0), last_rank=(rank == world - 1))
+        np.save(os.path.join(out_dir, "bp_%d.npy" % rank), mine2)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("cbc", [("PP", "PP", "PP"), ("NN", "PP", "ND"), ("PP", "DD", "NN")], ids=lambda c: "".join(c))
+def test_boundp_slabs_gloo(tmp_path, world, cbc):
+    ng = (6, 8, 12)
+    mp.spawn(_boundp_worker, args=(world, _free_port(), cbc, ng, str(tmp_path)), nprocs=world, join=True)
+    case = Case(ng, cbc, (2.0, 1.0, 1.0), gr=(1.0 if cbc[2] != "PP" else 0.0), seed=8)
+    s = case.setup
+    rng = np.random.default_rng(12)
+    full = np.asfortranarray(rng.uniform(-1, 1, (ng[0] + 2, ng[1] + 2, ng[2] + 2)))
+    bc = np.array([[0.0, 0.0], [0.2, -0.1], [0.3, 0.7]]) * (np.array([c != "PP" for c in cbc])[:, None])
+    ref = oracle.boundp(cbc, ng, bc, s.nh_d, s.dl, s.dzc, full)
+    n3l = ng[2] // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "bp_%d.npy" % r))
+        assert np.array_equal(got, ref[:, :, r * n3l:r * n3l + n3l + 2]), r

@@ -111,7 +111,7 @@ def test_unsupported_lengths_are_rejected(emul):
 @pytest.fixture(scope="module")
 def emul_t(emul):
     emul.emul_thomas_tile.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
-    emul.emul_thomas_reg.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    emul.emul_thomas_reg.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
     return emul
 
 
@@ -119,9 +119,11 @@ def emul_t(emul):
 @pytest.mark.parametrize("nz,L", [(8, 2), (16, 4), (32, 8), (64, 8), (72, 8), (40, 8), (64, 16), (128, 16), (512, 16),
                                   (256, 32), (1024, 32), (12, 2), (24, 4), (1024, 16), (48, 16), (4, 2)])
 @pytest.mark.parametrize("stretched", [False, True])
-@pytest.mark.parametrize("variant", ["tile", "reg"])
+@pytest.mark.parametrize("variant", ["tile", "reg", "reg-uniform"])
 def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched, variant):
-    if variant == "reg" and L > 16:
+    if variant == "reg-uniform" and (stretched or nz < 4):
+        pytest.skip("scalar-coefficient path: uniform grids only")
+    if variant != "tile" and L > 16:
         pytest.skip("the register kernel keeps at most 16 levels per thread")
     S = nz // L
     if periodic and (S & (S - 1)):
@@ -133,6 +135,16 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
     dzc, dzf = initsolver.initgrid(nz, 2.0 if stretched else 0.0, 1.0, 1)
     bcz = "PP" if periodic else "NN"
     a, b, c = initsolver.tridmatrix(bcz, nz, 1, 1.0 / dzc, 1.0 / dzf)
+    if variant == "reg-uniform":
+        # exactly uniform coefficients (what initgrid produces when lz/nz is a binary fraction, e.g. lz = 1, nz = 512);
+        # the oracle solves with the same arrays
+        a0 = a[1]
+        a[:] = a0
+        c[:] = a0
+        b[:] = -2.0 * a0
+        if not periodic:
+            b[0] += a0                                   # Neumann walls: b(1) += a(1), b(n) += c(n) (initsolver.f90:228-236)
+            b[-1] += a0
     nx, ny = 7, 3                                        # 21 columns: exercises the ragged last tile
     lam = -rng.uniform(0.0, 4.0 * nz * nz, (nx, ny))
     lam[0, 0] = 0.0                                      # singular column
@@ -141,10 +153,12 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
     rhs[0, 0, :] -= (rhs[0, 0, :] * dzf[1:-1]).sum() / dzf[1:-1].sum()    # compatible RHS for the singular column
     ref = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bool(periodic))
     got = rhs.copy(order="F")
-    fn = emul_t.emul_thomas_tile if variant == "tile" else emul_t.emul_thomas_reg
-    rc = fn(L, nz, nx * ny, periodic, 1, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp),
-                                 c.ctypes.data_as(_dp), np.asfortranarray(lam).ctypes.data_as(_dp),
-                                 got.ctypes.data_as(_dp))
+    args = (L, nz, nx * ny, periodic, 1, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp), c.ctypes.data_as(_dp),
+            np.asfortranarray(lam).ctypes.data_as(_dp), got.ctypes.data_as(_dp))
+    if variant == "tile":
+        rc = emul_t.emul_thomas_tile(*args)
+    else:
+        rc = emul_t.emul_thomas_reg(*args, 2 if variant == "reg-uniform" else 0)
     assert rc == 0
     for i in range(nx):
         for j in range(ny):
