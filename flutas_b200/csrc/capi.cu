@@ -794,7 +794,10 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
     for (int q = 0; q < P; ++q) sg.ptr[q] = sp->p2p ? sp->peer_pencil[q] : S + (size_t)q * chunk;
     sg.n1l = n1l; sg.koff = sp->p2p ? (long)r * (long)chunk : 0;
     StageTimer t(ST_YF);
-    if (int rc = run_y<true>(sp->py, W1, n1, n3l, sg)) return rc;
+    y_wide_request() = sp->p2p ? 1 : 0;                  // remote stores: prefer 128-byte row pieces
+    const int rc = run_y<true>(sp->py, W1, n1, n3l, sg);
+    y_wide_request() = 0;
+    if (rc) return rc;
   }
   {
     StageTimer t(ST_EXCH_F);

@@ -50,6 +50,7 @@ struct YTileBuf {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+
 template <int M>
 __device__ __forceinline__ void reg_stage_tw(cpx* s1, cpx* s2, const RegPlan& P, int tid, int nthr) {
   const double2* g1 = reinterpret_cast<const double2*>(P.tw[1]);
@@ -95,8 +96,26 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   // the physical accesses are aligned 16-byte vectors.  A cyclic shift only multiplies mode k by a unit
   // phase, which commutes with the (real, per-mode) z solve; the backward kernel stores with the same shift.
   const LineGeom& gph = FWD ? gs : gd;
-  const bool shift = (kind == KIND_PP) && ((reinterpret_cast<uintptr_t>(FWD ? (const void*)src : (const void*)dst) / 8 + gph.off0 + 1) % 2 == 0) &&
-                     (gph.sj % 2 == 0) && (gph.sk % 2 == 0);
+  const bool even_strides = (gph.sj % 2 == 0) && (gph.sk % 2 == 0);
+  const long el0 = (long)(reinterpret_cast<uintptr_t>(FWD ? (const void*)src : (const void*)dst) / 8) + gph.off0;
+  const bool al1 = even_strides && ((el0 + 1) % 2 == 0);       // element 1 of every line is 16-byte aligned
+  const bool al0 = even_strides && (el0 % 2 == 0);             // element 0 is
+  const bool shift = (kind == KIND_PP) && al1;
+  // DCT/DST lines: the Makhoul permutation makes per-thread accesses 32 bytes apart, so the physical side is
+  // read / written in natural order as aligned 16-byte pairs and permuted through the line's exchange buffer.
+  const bool viabuf = (kind != KIND_PP) && (al0 || al1);
+  // natural-order pair q of a line: elements (ea, eb); `vec` = one aligned 16-byte access at element ea
+  auto pair_elems = [&](int q, int& ea, int& eb, bool& vec) {
+    if (al0) { ea = 2 * q; eb = 2 * q + 1; vec = true; }
+    else if (q == M - 1) { ea = N - 1; eb = 0; vec = false; }
+    else { ea = 2 * q + 1; eb = 2 * q + 2; vec = true; }
+  };
+  auto slot_sign = [&](int e, double& sgn) {                   // slot (doubles) of physical element e in the buffer
+    int m, part;
+    elem_to_slot(kind, N, e, m, part, sgn);
+    return 2 * (m + (m >> 4)) + part;
+  };
+  double* lbuf = reinterpret_cast<double*>(xb.b);
   for (long g = WARP ? (long)blockIdx.x * 8 + gi : (long)blockIdx.x; g < ngroups; g += gstride) {
     const long line = g * LG + lw;
     const bool live = line < nlines;
@@ -121,6 +140,24 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       } else if (kind == KIND_PP) {
 #pragma unroll
         for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
+      } else if (viabuf) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          int ea, eb; bool vec;
+          pair_elems(j + T * u, ea, eb, vec);
+          if (vec) { const double2 v = *reinterpret_cast<const double2*>(ps + ea); re[u] = v.x; im[u] = v.y; }
+          else { re[u] = ps[ea]; im[u] = ps[eb]; }
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          int ea, eb; bool vec; double sa, sb;
+          pair_elems(j + T * u, ea, eb, vec);
+          const int pa = slot_sign(ea, sa), pb = slot_sign(eb, sb);
+          lbuf[pa] = sa * re[u]; lbuf[pb] = sb * im[u];
+        }
+        sync();
+        reg_gather<M>(re, im, j, xb);
+        sync();
       } else {
 #pragma unroll
         for (int u = 0; u < R; ++u) {
@@ -147,9 +184,28 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
       sync();
       reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
+      if (viabuf) {                                    // packed element m = slot m, then read back in natural order
+        reg_scatter_modes<M>(re, im, j, xb);
+        sync();
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          int ea, eb; bool vec; double sa, sb;
+          pair_elems(j + T * u, ea, eb, vec);
+          const int pa = slot_sign(ea, sa), pb = slot_sign(eb, sb);
+          re[u] = sa * scale * lbuf[pa]; im[u] = sb * scale * lbuf[pb];
+        }
+      }
       if (live) {
         double* pd = dst + line_offset(gd, line);
-        if (shift) {
+        if (viabuf) {
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            int ea, eb; bool vec;
+            pair_elems(j + T * u, ea, eb, vec);
+            if (vec) *reinterpret_cast<double2*>(pd + ea) = make_double2(re[u], im[u]);
+            else { pd[ea] = re[u]; pd[eb] = im[u]; }
+          }
+        } else if (shift) {
           double2* pa = reinterpret_cast<double2*>(pd + 1);
 #pragma unroll
           for (int u = 0; u < R; ++u) {
@@ -175,10 +231,12 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
 }
 
 // ---- y lines ------------------------------------------------------------------------------------
-template <int N>
+// WIDE: 512-thread blocks when a line needs >= 32 threads (N >= 1024), i.e. 16 lanes = 128-byte row pieces but one
+// block per SM; !WIDE: always 256 threads (8 lanes at N = 1024, two blocks per SM).
+template <int N, bool WIDE>
 struct YRegShape {
   static constexpr int T = RegSched<N / 2>::T;
-  static constexpr int NTMAX = (T >= 32) ? 512 : 256;      // 16 lanes (128-byte rows) up to N = 1024
+  static constexpr int NTMAX = (WIDE && T >= 32) ? 512 : 256;
   static constexpr int TB = (NTMAX / T > 32) ? 32 : NTMAX / T;
   static constexpr int NT = TB * T;
   static constexpr int MINB = (NT > 256) ? 1 : 2;
@@ -186,12 +244,12 @@ struct YRegShape {
                                  (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
 };
 
-template <int N, bool FWD>
-__global__ void __launch_bounds__(YRegShape<N>::NT, YRegShape<N>::MINB)
+template <int N, bool FWD, bool WIDE>
+__global__ void __launch_bounds__(YRegShape<N, WIDE>::NT, YRegShape<N, WIDE>::MINB)
 yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
   constexpr int M = N / 2;
   using S = RegSched<M>;
-  constexpr int T = S::T, R = S::R, TB = YRegShape<N>::TB, NT = YRegShape<N>::NT;
+  constexpr int T = S::T, R = S::R, TB = YRegShape<N, WIDE>::TB, NT = YRegShape<N, WIDE>::NT;
   extern __shared__ double2 smem2[];
   cpx* s_tw1 = reinterpret_cast<cpx*>(smem2);
   cpx* s_tw2 = s_tw1 + RegTw<M>::n1;
@@ -288,6 +346,7 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
   }
 }
 
+
 template <int N, bool FWD>
 inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                                 int nsm, cudaStream_t st) {
@@ -311,10 +370,10 @@ inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs
   return cudaGetLastError();
 }
 
-template <int N, bool FWD>
-inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
-  using Y = YRegShape<N>;
-  auto kern = yfft_reg_kernel<N, FWD>;
+template <int N, bool FWD, bool WIDE>
+inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
+  using Y = YRegShape<N, WIDE>;
+  auto kern = yfft_reg_kernel<N, FWD, WIDE>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
@@ -330,6 +389,13 @@ inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, co
   const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
   kern<<<(unsigned)grid, Y::NT, Y::smem, st>>>(P, W, n1, nti, ntiles, sg);
   return cudaGetLastError();
+}
+
+template <int N, bool FWD>
+inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, bool wide,
+                                cudaStream_t st) {
+  if (RegSched<N / 2>::T >= 32 && wide) return reg_launch_y1<N, FWD, true>(P, W, n1, n3, sg, nsm, st);
+  return reg_launch_y1<N, FWD, false>(P, W, n1, n3, sg, nsm, st);
 }
 
 }  // namespace fb

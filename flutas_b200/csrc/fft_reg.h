@@ -5,7 +5,20 @@
 #include "geom.cuh"
 #include "reg_fft.cuh"
 
+#include <cstdlib>
+
 namespace fb {
+// y tiles at N >= 1024 (a line needs >= 32 threads): "wide" = 16 lanes (128-byte row pieces) in 512-thread blocks, one
+// block per SM; otherwise 8 lanes in 256-thread blocks, two blocks per SM.  Measured on one B200 at 1024^3: narrow
+// 4.86 / 5.36 ms (fwd / bwd), wide 5.42 / 5.64 ms -> narrow is the default; the slab solver asks for wide tiles when the
+// spectral side is written straight into peer memory (NVLink stores: 128-byte pieces move ~1.5x faster than 64-byte ones).
+// FLUTAS_B200_YWIDE=0/1 overrides both.
+inline int& y_wide_request() { static int v = 0; return v; }
+inline bool y_wide_enabled() {
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("FLUTAS_B200_YWIDE"); env = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  return env >= 0 ? env == 1 : y_wide_request() == 1;
+}
 cudaError_t reg_run_x_fwd(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale, int nsm,
                           cudaStream_t st);
 cudaError_t reg_run_x_bwd(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale, int nsm,

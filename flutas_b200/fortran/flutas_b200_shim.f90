@@ -10,6 +10,7 @@
 !     use mod_fillps    -> fillps                (replaces src/fillps.f90:16)
 !     use mod_correc    -> correc                (replaces src/correc.f90:16)
 !     use mod_chkdiv    -> chkdiv                (replaces src/chkdiv.f90:18)
+!     use mod_bound_b200-> boundp                (replaces src/bound.f90:146 for nh_p = 1, i.e. p and pold)
 ! This image has no Fortran compiler, so the file is syntax-simple F2003 and is not built here; the same
 ! C entry points are exercised through ctypes by tests/ (see INTEGRATION.md).
 !
@@ -53,6 +54,11 @@ module mod_flutas_b200
                             bind(C,name='flutas_b200_chkdiv')
       import; integer(c_int), value :: nx,ny,nz,nh_d,nh_u; real(c_double), value :: dxi,dyi,dzi
       type(c_ptr), value :: dzfi,u,v,w; real(c_double), intent(out) :: divtot,divmax
+    end function
+    integer(c_int) function flutas_b200_boundp(cbc,n,bc,nh_d,nh_p,dl,dzc,dzf,p) bind(C,name='flutas_b200_boundp')
+      import; character(kind=c_char), intent(in) :: cbc(6); integer(c_int), intent(in) :: n(3)
+      real(c_double), intent(in) :: bc(6),dl(3); integer(c_int), value :: nh_d,nh_p
+      type(c_ptr), value :: dzc,dzf,p
     end function
     function flutas_b200_last_error() bind(C,name='flutas_b200_last_error') result(msg)
       import; type(c_ptr) :: msg
@@ -194,3 +200,37 @@ contains
     if(myid.eq.0) print*, 'Total divergence = ', divtot, '| Maximum divergence = ', divmax
   end subroutine chkdiv
 end module mod_chkdiv
+
+!
+! boundp for the pressure halo (nh_p = 1): same argument list as src/bound.f90:146; `halo` (MPI datatypes) is unused.
+! cbc(0:1,3) and bc(0:1,3) are passed in Fortran storage order = (x0,x1,y0,y1,z0,z1), which is what the C side expects.
+!
+module mod_bound_b200
+  use, intrinsic :: iso_c_binding
+  use mod_flutas_b200
+  implicit none
+  private
+  public :: boundp
+  contains
+  subroutine boundp(cbc,n,bc,nh_d,nh_p,halo,dl,dzc,dzf,p)
+    character(len=1), intent(in   ), dimension(0:1,3)                   :: cbc
+    integer         , intent(in   ), dimension(3)                       :: n
+    real(c_double)  , intent(in   ), dimension(0:1,3)                   :: bc
+    integer         , intent(in   )                                     :: nh_d,nh_p
+    integer         , intent(in   ), dimension(3)                       :: halo
+    real(c_double)  , intent(in   ), dimension(3)                       :: dl
+    real(c_double)  , intent(in   ), dimension(1-nh_d:), target         :: dzc,dzf
+    real(c_double)  , intent(inout), dimension(1-nh_p:,1-nh_p:,1-nh_p:), target :: p
+    character(kind=c_char) :: cc(6)
+    real(c_double) :: bv(6)
+    integer :: d,s
+    do d=1,3
+      do s=0,1
+        cc(2*(d-1)+s+1) = cbc(s,d)
+        bv(2*(d-1)+s+1) = bc(s,d)
+      enddo
+    enddo
+    call b200_check(flutas_b200_boundp(cc,int(n,c_int),bv,int(nh_d,c_int),int(nh_p,c_int),dl, &
+                                       c_loc(dzc),c_loc(dzf),c_loc(p)),'boundp')
+  end subroutine boundp
+end module mod_bound_b200

@@ -164,7 +164,12 @@ static void thomas_reg_emul(long ncol, ThomasArgs T, const double* lam, double* 
            TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, CF(T, s), lamof(lane), lane, s, pin); }
     double* src = pa.data(); double* dst = pb.data();
     const int hmax = T.periodic ? S / 2 : S;
-    for (int h = 1; h < hmax; h *= 2) { ALLT TR::pcr_step(src, dst, T, lane, s, h); double* t = src; src = dst; dst = t; }
+    for (int h = 1; h < hmax; h *= 2) {
+      bool any = false;
+      ALLT any = TR::pcr_step(src, dst, T, lane, s, h) || any;
+      double* t = src; src = dst; dst = t;
+      if (!any) break;
+    }
     ALLT TR::pcr_finish(src, X.data(), T, lane, s);
     ALLT TR::phase3(vof(lane, s), X.data(), T, lane, s, regs[s * TI + lane]);
     ALLT if (live(lane)) for (int l = 0; l < L; ++l) W[colof(lane) + (long)(s * L + l) * ncol] = vof(lane, s)[l];
