@@ -28,14 +28,16 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), tag=None):
+    """defines/tag: A/B builds of compile-time variants -> csrc/libflutas_b200_<tag>.so (select with FLUTAS_B200_LIB)"""
+    so = SO if tag is None else SO.replace(".so", "_%s.so" % tag)
+    if tag is None and not force and not is_stale():
         return SO
     nvcc = [_nvcc()]
     if os.path.exists("/usr/bin/g++"):
         nvcc += ["-ccbin", "/usr/bin/g++"]
-    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-    objdir = os.path.join(CSRC, "build")
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines]
+    objdir = os.path.join(CSRC, "build" if tag is None else "build_" + tag)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -46,9 +48,13 @@ def build(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.check_call(nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs, cwd=CSRC)
-    return SO
+    subprocess.check_call(nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs, cwd=CSRC)
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 1:                                   # python -m flutas_b200.build <tag> DEF=1 DEF2=0 ...
+        print(build(force=True, defines=sys.argv[2:], tag=sys.argv[1]))
+    else:
+        print(build(force=True, verbose=True))

@@ -20,19 +20,27 @@
 
 namespace fb {
 
-template <int M>
+// Tables staged in shared memory by every block: the pass twiddles (tw1, tw2), the split/merge twiddles wN[M] and,
+// for Makhoul (NN/DD) lines of length <= 1024, wQ[M+1].  All are indexed j + T u or k + (t-1) Ns, i.e. one run-time
+// base plus immediates (the v7 kernels fetched wN/wQ from global memory: 62 of their 94 LDG per thread and tile).
+template <int M, bool MK>
 struct RegTw {
   using S = RegSched<M>;
   static constexpr int n1 = (S::NP > 1) ? 15 * S::ns(1) : 0;
   static constexpr int n2 = (S::NP > 2) ? 15 * S::ns(2) : 0;
+  static constexpr int nN = M;
+  static constexpr bool QSM = MK && (M <= 512);
+  static constexpr int nQ = QSM ? M + 1 : 0;
+  static constexpr int total = n1 + n2 + nN + nQ + (nQ & 1);     // cpx entries (16 bytes each)
 };
 
 // exchange buffer of one x line: M slots of (re,im), one pad slot per 16 (scattered 16-slot strides -> all banks)
 struct XLineBuf {
   double2* b;
-  __device__ __forceinline__ void st(int pos, double r, double i) const { b[pos + (pos >> 4)] = make_double2(r, i); }
-  __device__ __forceinline__ void ld(int pos, double& r, double& i) const {
-    const double2 v = b[pos + (pos >> 4)];
+  __device__ __forceinline__ int base(int pos) const { return rf_pad(pos); }
+  __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[bs + coff] = make_double2(r, i); }
+  __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
+    const double2 v = b[bs + coff];
     r = v.x; i = v.y;
   }
 };
@@ -41,31 +49,59 @@ struct XLineBuf {
 template <int TB>
 struct YTileBuf {
   double2* b;   // already offset by the lane
-  __device__ __forceinline__ void st(int pos, double r, double i) const { b[(pos + (pos >> 4)) * TB] = make_double2(r, i); }
-  __device__ __forceinline__ void ld(int pos, double& r, double& i) const {
-    const double2 v = b[(pos + (pos >> 4)) * TB];
+  __device__ __forceinline__ int base(int pos) const { return rf_pad(pos) * TB; }
+  __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[bs + coff * TB] = make_double2(r, i); }
+  __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
+    const double2 v = b[bs + coff * TB];
     r = v.x; i = v.y;
   }
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Store policy of the strided sides (compile-time, for A/B builds).  tools/pattern_bench.cu (same tiles, no arithmetic)
+// puts the ceiling of plain stores above st.cs for 64-byte pieces (halves of a 128-byte line merge in L2 instead of
+// leaving it evict-first), but the transform kernels are not at that ceiling: measured on B200, 512^3 and 1024^3,
+// st.cs is 0-2 % faster than plain stores on every stage -> st.cs stays the default.
+#ifndef FB_STREAM_Y
+#define FB_STREAM_Y 1
+#endif
+#ifndef FB_STREAM_X
+#define FB_STREAM_X 1
+#endif
+__device__ __forceinline__ void st_y(double* p, double v) { if (FB_STREAM_Y) __stcs(p, v); else *p = v; }
+__device__ __forceinline__ void st_x2(double2* p, double2 v) { if (FB_STREAM_X) __stcs(p, v); else *p = v; }
 
-template <int M>
-__device__ __forceinline__ void reg_stage_tw(cpx* s1, cpx* s2, const RegPlan& P, int tid, int nthr) {
-  const double2* g1 = reinterpret_cast<const double2*>(P.tw[1]);
-  const double2* g2 = reinterpret_cast<const double2*>(P.tw[2]);
-  for (int q = tid; q < RegTw<M>::n1; q += nthr) reinterpret_cast<double2*>(s1)[q] = __ldg(g1 + q);
-  for (int q = tid; q < RegTw<M>::n2; q += nthr) reinterpret_cast<double2*>(s2)[q] = __ldg(g2 + q);
+
+// copies the tables to shared memory at `sm` in the order tw1 | tw2 | wN | wQ (offsets: RegTw).  The kernels form the
+// table pointers as plain local variables: handing them around inside a struct made nvcc 12.9 lose the shared
+// address space of one member (a generic load from the bare shared offset -> illegal address).
+template <int M, bool MK>
+__device__ __forceinline__ void reg_stage_tw(cpx* sm, const RegPlan& P, int tid, int nthr) {
+  using TW = RegTw<M, MK>;
+  auto copy = [&](cpx* d, const cpx* g, int n) {
+    const double2* g2 = reinterpret_cast<const double2*>(g);
+    for (int q = tid; q < n; q += nthr) reinterpret_cast<double2*>(d)[q] = __ldg(g2 + q);
+  };
+  copy(sm, P.tw[1], TW::n1);
+  copy(sm + TW::n1, P.tw[2], TW::n2);
+  copy(sm + TW::n1 + TW::n2, P.wN, TW::nN);
+  if (TW::QSM) copy(sm + TW::n1 + TW::n2 + TW::nN, P.wQ, TW::nQ);
 }
+#define FB_REG_TABLES(M, MK, smbase, P)                                                       \
+  const cpx* s_tw1 = reinterpret_cast<const cpx*>(smbase);                                     \
+  const cpx* s_tw2 = s_tw1 + RegTw<M, MK>::n1;                                                 \
+  const cpx* s_wN = s_tw2 + RegTw<M, MK>::n2;                                                  \
+  const cpx* s_wQ = RegTw<M, MK>::QSM ? (s_wN + RegTw<M, MK>::nN) : P.wQ;                      \
+  const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
 
-template <int N>
+template <int N, bool MK>
 constexpr size_t xfft_reg_smem() {
   constexpr int M = N / 2;
-  return (size_t)(RegTw<M>::n1 + RegTw<M>::n2) * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
+  return (size_t)RegTw<M, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
 }
 
-template <int N, bool FWD>
+template <int N, bool FWD, bool MK>
 __global__ void __launch_bounds__(256, 2)
 xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* __restrict__ dst, LineGeom gd, double scale) {
   constexpr int M = N / 2;
@@ -76,18 +112,16 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   constexpr int LG = GT / T;                          // lines per group
   constexpr int BUFL = M + M / 16;
   extern __shared__ double2 smem2[];
-  cpx* s_tw1 = reinterpret_cast<cpx*>(smem2);
-  cpx* s_tw2 = s_tw1 + RegTw<M>::n1;
-  double2* bufs = reinterpret_cast<double2*>(s_tw2 + RegTw<M>::n2);
+  double2* bufs = smem2 + RegTw<M, MK>::total;
   const int tid = threadIdx.x;
-  reg_stage_tw<M>(s_tw1, s_tw2, P, tid, 256);
+  reg_stage_tw<M, MK>(reinterpret_cast<cpx*>(smem2), P, tid, 256);
   __syncthreads();
-  const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
+  FB_REG_TABLES(M, MK, smem2, P)
   const int gi = WARP ? (tid >> 5) : 0, tg = tid % GT;
   const int lw = tg / T, j = tg % T;
   const XLineBuf xb{bufs + (size_t)(gi * LG + lw) * BUFL};
   auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
-  const int kind = P.kind;
+  const int kind = MK ? P.kind : (int)KIND_PP;
   const long nlines = gs.nlines;
   const long ngroups = (nlines + LG - 1) / LG;
   const long gstride = WARP ? (long)gridDim.x * 8 : (long)gridDim.x;
@@ -100,10 +134,10 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   const long el0 = (long)(reinterpret_cast<uintptr_t>(FWD ? (const void*)src : (const void*)dst) / 8) + gph.off0;
   const bool al1 = even_strides && ((el0 + 1) % 2 == 0);       // element 1 of every line is 16-byte aligned
   const bool al0 = even_strides && (el0 % 2 == 0);             // element 0 is
-  const bool shift = (kind == KIND_PP) && al1;
+  const bool shift = !MK && al1;
   // DCT/DST lines: the Makhoul permutation makes per-thread accesses 32 bytes apart, so the physical side is
   // read / written in natural order as aligned 16-byte pairs and permuted through the line's exchange buffer.
-  const bool viabuf = (kind != KIND_PP) && (al0 || al1);
+  const bool viabuf = MK && (al0 || al1);
   // natural-order pair q of a line: elements (ea, eb); `vec` = one aligned 16-byte access at element ea
   auto pair_elems = [&](int q, int& ea, int& eb, bool& vec) {
     if (al0) { ea = 2 * q; eb = 2 * q + 1; vec = true; }
@@ -137,7 +171,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
           if (u == R - 1 && j == T - 1) { re[u] = ps[N - 1]; im[u] = ps[0]; }
           else { const double2 v = pa[m]; re[u] = v.x; im[u] = v.y; }
         }
-      } else if (kind == KIND_PP) {
+      } else if (!MK) {
 #pragma unroll
         for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
       } else if (viabuf) {
@@ -169,11 +203,11 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
       reg_scatter_modes<M>(re, im, j, xb);
       sync();
-      reg_split<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      reg_split<M, MK>(re, im, j, s_wN, s_wQ, xb);
       if (live) {
         double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
 #pragma unroll
-        for (int u = 0; u < R; ++u) __stcs(pd + (j + T * u), make_double2(scale * re[u], scale * im[u]));
+        for (int u = 0; u < R; ++u) st_x2(pd + (j + T * u), make_double2(scale * re[u], scale * im[u]));
       }
     } else {
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
@@ -181,7 +215,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = v.x; im[u] = v.y; }
       reg_scatter_modes<M>(re, im, j, xb);
       sync();
-      reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      reg_merge<M, MK>(re, im, j, s_wN, s_wQ, xb);
       sync();
       reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
       if (viabuf) {                                    // packed element m = slot m, then read back in natural order
@@ -213,7 +247,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
             if (u == R - 1 && j == T - 1) { pd[N - 1] = scale * re[u]; pd[0] = scale * im[u]; }
             else pa[m] = make_double2(scale * re[u], scale * im[u]);
           }
-        } else if (kind == KIND_PP) {
+        } else if (!MK) {
 #pragma unroll
           for (int u = 0; u < R; ++u) { const int m = j + T * u; pd[2 * m] = scale * re[u]; pd[2 * m + 1] = scale * im[u]; }
         } else {
@@ -233,36 +267,46 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
 // ---- y lines ------------------------------------------------------------------------------------
 // WIDE: 512-thread blocks when a line needs >= 32 threads (N >= 1024), i.e. 16 lanes = 128-byte row pieces but one
 // block per SM; !WIDE: always 256 threads (8 lanes at N = 1024, two blocks per SM).
-template <int N, bool WIDE>
+template <int N, bool WIDE, bool MK>
 struct YRegShape {
   static constexpr int T = RegSched<N / 2>::T;
   static constexpr int NTMAX = (WIDE && T >= 32) ? 512 : 256;
   static constexpr int TB = (NTMAX / T > 32) ? 32 : NTMAX / T;
   static constexpr int NT = TB * T;
   static constexpr int MINB = (NT > 256) ? 1 : 2;
-  static constexpr size_t smem = (size_t)(RegTw<N / 2>::n1 + RegTw<N / 2>::n2) * sizeof(cpx) +
-                                 (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
+  static constexpr size_t smem = (size_t)RegTw<N / 2, MK>::total * sizeof(cpx) + (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
 };
 
-template <int N, bool FWD, bool WIDE>
-__global__ void __launch_bounds__(YRegShape<N, WIDE>::NT, YRegShape<N, WIDE>::MINB)
+// element `c * stride` past p with a compile-time c: one IMAD.WIDE (32-bit stride times immediate plus 64-bit base)
+// (stride in BYTES as an unsigned 32-bit value: a signed or element stride costs a high-word fix-up per address)
+__device__ __forceinline__ const double* yrow(const double* p, unsigned sbytes, int c) {
+  const char* q = reinterpret_cast<const char*>(p);
+  return reinterpret_cast<const double*>(c >= 0 ? q + (size_t)sbytes * (unsigned)c : q - (size_t)sbytes * (unsigned)(-c));
+}
+__device__ __forceinline__ double* yrow(double* p, unsigned sbytes, int c) {
+  char* q = reinterpret_cast<char*>(p);
+  return reinterpret_cast<double*>(c >= 0 ? q + (size_t)sbytes * (unsigned)c : q - (size_t)sbytes * (unsigned)(-c));
+}
+
+template <int N, bool FWD, bool WIDE, bool MK>
+__global__ void __launch_bounds__(YRegShape<N, WIDE, MK>::NT, YRegShape<N, WIDE, MK>::MINB)
 yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
   constexpr int M = N / 2;
   using S = RegSched<M>;
-  constexpr int T = S::T, R = S::R, TB = YRegShape<N, WIDE>::TB, NT = YRegShape<N, WIDE>::NT;
+  using Y = YRegShape<N, WIDE, MK>;
+  using MR = MkRows<N>;
+  constexpr int T = S::T, R = S::R, TB = Y::TB, NT = Y::NT;
   extern __shared__ double2 smem2[];
-  cpx* s_tw1 = reinterpret_cast<cpx*>(smem2);
-  cpx* s_tw2 = s_tw1 + RegTw<M>::n1;
-  double2* buf = reinterpret_cast<double2*>(s_tw2 + RegTw<M>::n2);
+  double2* buf = smem2 + RegTw<M, MK>::total;
   const int tid = threadIdx.x;
-  reg_stage_tw<M>(s_tw1, s_tw2, P, tid, NT);
+  reg_stage_tw<M, MK>(reinterpret_cast<cpx*>(smem2), P, tid, NT);
   __syncthreads();
-  const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
+  FB_REG_TABLES(M, MK, smem2, P)
   const int lane = tid % TB, j = tid / TB;
   const YTileBuf<TB> xb{buf + lane};
   auto sync = [] { __syncthreads(); };
-  const int kind = P.kind;
-  const long stride = n1, sstride = sg.n1l;
+  const double sdd = (MK && P.kind == KIND_DD) ? -1.0 : 1.0;   // DST-II/III through the DCT: odd physical elements change sign
+  const unsigned sstride = (unsigned)sg.n1l * 8u, pstride = (unsigned)n1 * 8u;      // row strides in bytes (< 4 GB)
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int ti = (int)(tile % ntile_i);
     const long k = tile / ntile_i;
@@ -278,66 +322,66 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
         const long kn = tn / ntile_i;
         const int iln = min(tin * TB, n1 - 1);
         const double* pn = FWD ? (W + (long)n1 * N * kn + iln) : spec_base(sg, iln, N, kn);
-        const long sn = FWD ? stride : sstride;
-        constexpr int ROWS_PER_LANE = (2 * R + TB - 1) / TB;   // this thread's 2R rows, shared out over the TB lanes
+        const unsigned sn = FWD ? pstride : sstride;
+        constexpr int LP = (TB * 8 > 128) ? TB * 8 / 128 : 1;          // 128-byte lines per row piece
+        constexpr int OPS = N * LP / NT;                               // prefetches per thread (N * LP >= NT)
 #pragma unroll
-        for (int q = 0; q < ROWS_PER_LANE; ++q) {
-          const int idx = lane * ROWS_PER_LANE + q;            // 0 .. 2R-1 -> (u, re/im)
-          if (idx < 2 * R) {
-            int row = 2 * (j + T * (idx >> 1)) + (idx & 1);
-            if (FWD && kind != KIND_PP) { int e0, e1; double s0, s1; reg_phys_slots(kind, N, j + T * (idx >> 1), e0, e1, s0, s1); row = (idx & 1) ? e1 : e0; }
-            prefetch_l2(pn + (long)row * sn);
-          }
+        for (int q = 0; q < OPS; ++q) {
+          const int op = tid + NT * q;
+          prefetch_l2(yrow(pn, sn, op / LP) + 16 * (op % LP));
         }
       }
     }
     double re[R], im[R];
     if (FWD) {
-      if (kind == KIND_PP) {
+      if (!MK) {
+        const double* p0 = yrow(base, pstride, 2 * j);
 #pragma unroll
-        for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = base[(long)(2 * m) * stride]; im[u] = base[(long)(2 * m + 1) * stride]; }
+        for (int u = 0; u < R; ++u) { re[u] = *yrow(p0, pstride, 2 * T * u); im[u] = *yrow(p0, pstride, 2 * T * u + 1); }
       } else {
+        const double* plo = yrow(base, pstride, MR::base_lo(j));
+        const double* phi = yrow(base, pstride, MR::base_hi(j));
 #pragma unroll
         for (int u = 0; u < R; ++u) {
-          int e0, e1; double s0, s1;
-          reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
-          re[u] = s0 * base[(long)e0 * stride]; im[u] = s1 * base[(long)e1 * stride];
+          if (!MR::upper(u)) { re[u] = *yrow(plo, pstride, MR::off0(u)); im[u] = *yrow(plo, pstride, MR::off1(u)); }
+          else { re[u] = sdd * *yrow(phi, pstride, MR::off0(u)); im[u] = sdd * *yrow(phi, pstride, MR::off1(u)); }
         }
       }
       reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
       reg_scatter_modes<M>(re, im, j, xb);
       sync();
-      reg_split<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      reg_split<M, MK>(re, im, j, s_wN, s_wQ, xb);
       if (live) {
+        double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
         for (int u = 0; u < R; ++u) {
-          const int kk = j + T * u;
-          __stcs(sbase + (long)(2 * kk) * sstride, re[u]);
-          __stcs(sbase + (long)(2 * kk + 1) * sstride, im[u]);
+          st_y(yrow(ps, sstride, 2 * T * u), re[u]);
+          st_y(yrow(ps, sstride, 2 * T * u + 1), im[u]);
         }
       }
     } else {
+      {
+        const double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
-      for (int u = 0; u < R; ++u) {
-        const int kk = j + T * u;
-        re[u] = sbase[(long)(2 * kk) * sstride];
-        im[u] = sbase[(long)(2 * kk + 1) * sstride];
+        for (int u = 0; u < R; ++u) { re[u] = *yrow(ps, sstride, 2 * T * u); im[u] = *yrow(ps, sstride, 2 * T * u + 1); }
       }
       reg_scatter_modes<M>(re, im, j, xb);
       sync();
-      reg_merge<M>(re, im, j, kind, P.wN, P.wQ, xb);
+      reg_merge<M, MK>(re, im, j, s_wN, s_wQ, xb);
       sync();
       reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
       if (live) {
-        if (kind == KIND_PP) {
+        if (!MK) {
+          double* p0 = yrow(base, pstride, 2 * j);
 #pragma unroll
-          for (int u = 0; u < R; ++u) { const int m = j + T * u; base[(long)(2 * m) * stride] = re[u]; base[(long)(2 * m + 1) * stride] = im[u]; }
+          for (int u = 0; u < R; ++u) { *yrow(p0, pstride, 2 * T * u) = re[u]; *yrow(p0, pstride, 2 * T * u + 1) = im[u]; }
         } else {
+          double* plo = yrow(base, pstride, MR::base_lo(j));
+          double* phi = yrow(base, pstride, MR::base_hi(j));
 #pragma unroll
           for (int u = 0; u < R; ++u) {
-            int e0, e1; double s0, s1;
-            reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
-            base[(long)e0 * stride] = s0 * re[u]; base[(long)e1 * stride] = s1 * im[u];
+            if (!MR::upper(u)) { *yrow(plo, pstride, MR::off0(u)) = re[u]; *yrow(plo, pstride, MR::off1(u)) = im[u]; }
+            else { *yrow(phi, pstride, MR::off0(u)) = sdd * re[u]; *yrow(phi, pstride, MR::off1(u)) = sdd * im[u]; }
           }
         }
       }
@@ -347,13 +391,13 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
 }
 
 
-template <int N, bool FWD>
-inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
-                                int nsm, cudaStream_t st) {
+template <int N, bool FWD, bool MK>
+inline cudaError_t reg_launch_x1(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
+                                 int nsm, cudaStream_t st) {
   constexpr int M = N / 2, T = RegSched<M>::T;
   constexpr int LPB = 256 / T;                         // lines per block per iteration
-  const size_t smem = xfft_reg_smem<N>();
-  auto kern = xfft_reg_kernel<N, FWD>;
+  const size_t smem = xfft_reg_smem<N, MK>();
+  auto kern = xfft_reg_kernel<N, FWD, MK>;
   static int per_sm = 0;                               // configured once per process (one device per process)
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,10 +414,17 @@ inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs
   return cudaGetLastError();
 }
 
-template <int N, bool FWD, bool WIDE>
+template <int N, bool FWD>
+inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
+                                int nsm, cudaStream_t st) {
+  return (P.kind == KIND_PP) ? reg_launch_x1<N, FWD, false>(P, src, gs, dst, gd, scale, nsm, st)
+                             : reg_launch_x1<N, FWD, true>(P, src, gs, dst, gd, scale, nsm, st);
+}
+
+template <int N, bool FWD, bool WIDE, bool MK>
 inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
-  using Y = YRegShape<N, WIDE>;
-  auto kern = yfft_reg_kernel<N, FWD, WIDE>;
+  using Y = YRegShape<N, WIDE, MK>;
+  auto kern = yfft_reg_kernel<N, FWD, WIDE, MK>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
@@ -394,8 +445,10 @@ inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, c
 template <int N, bool FWD>
 inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, bool wide,
                                 cudaStream_t st) {
-  if (RegSched<N / 2>::T >= 32 && wide) return reg_launch_y1<N, FWD, true>(P, W, n1, n3, sg, nsm, st);
-  return reg_launch_y1<N, FWD, false>(P, W, n1, n3, sg, nsm, st);
+  const bool mk = (P.kind != KIND_PP);
+  if (RegSched<N / 2>::T >= 32 && wide)
+    return mk ? reg_launch_y1<N, FWD, true, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, true, false>(P, W, n1, n3, sg, nsm, st);
+  return mk ? reg_launch_y1<N, FWD, false, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, false, false>(P, W, n1, n3, sg, nsm, st);
 }
 
 }  // namespace fb

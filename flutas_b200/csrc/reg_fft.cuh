@@ -112,6 +112,19 @@ template <int R, int SIGN> FB_HD void rbfly(double* re, double* im) {
   else bfly<R, SIGN>(re, im);
 }
 
+// ---- exchange-buffer addressing ------------------------------------------------------------------
+// Slot `pos` of a line's exchange buffer lives at padded index pos + (pos >> 4) (one pad slot per 16: the
+// scattered 16-slot strides of the Stockham passes then hit all banks).  Every access of the passes has the form
+// pos = (run-time base) + (compile-time offset c) where adding c never carries across a multiple of 16 beyond
+// c's own multiples of 16 (shown case by case below), so pad(pos) = pad(base) + pad(c): the kernels compute one
+// padded base per butterfly and the offsets fold into the immediate field of the LDS/STS instructions (the v7
+// profile had 18 integer instructions per point, mostly this index arithmetic).  An exchange buffer XB provides
+//   int  base(pos)               : scaled padded index of a run-time position
+//   void st(base, coff, re, im)  : store at base + coff, coff = rf_padoff(c) (already padded, unscaled)
+//   void ld(base, coff, re, im)
+FB_CX int rf_pad(int pos) { return pos + (pos >> 4); }
+FB_CX int rf_padoff(int c) { return c >= 0 ? c + (c >> 4) : -((-c) + ((-c) >> 4)); }
+
 // One Stockham pass of the T threads owning a line.  Thread j holds element j + T*u in (re[u], im[u]).
 // Not the last pass: results go to the exchange buffer (scattered), the caller synchronises and gathers.
 // Last pass: results stay in registers, again as element (= mode) j + T*u.
@@ -120,6 +133,10 @@ FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) 
   using S = RegSched<M>;
   constexpr int r = S::radix(Q), Ns = S::ns(Q), NB = S::R / r, T = S::T;
   constexpr bool last = (Q == S::NP - 1);
+  // pass 0 (Ns = 1): pos = jb r + t = j r + (T r) b + t with t < r | 16: no carry from t; T r is a multiple of 16 for
+  // M >= 64, then the b term is a compile-time offset too.  Later passes (r = 16, one butterfly per thread):
+  // pos = (j - k) 16 + k + t Ns, k < Ns: for Ns < 16 the low four bits are k + (t Ns mod 16) < 16, for Ns >= 16 they are k's.
+  constexpr bool BCONST = (Ns == 1) && ((T * r) % 16 == 0);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -149,58 +166,83 @@ FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) 
 #endif
       for (int t = 0; t < r; ++t) { re[b + t * NB] = vr[t]; im[b + t * NB] = vi[t]; }
     } else {
-      const int base = (jb - k) * r + k;               // (jb / Ns) * Ns * r + k
+      const int base = BCONST ? xb.base(j * r) : xb.base((jb - k) * r + k);     // (jb / Ns) * Ns * r + k
+      const int boff = BCONST ? rf_padoff(T * r * b) : 0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 0; t < r; ++t) xb.st(base + t * Ns, vr[t], vi[t]);
+      for (int t = 0; t < r; ++t) xb.st(base, boff + rf_padoff(t * Ns), vr[t], vi[t]);
     }
   }
 }
 
+// positions j + T u: for T >= 16 the offset is a multiple of 16, for T < 16 the low bits are j + (T u mod 16) < 16
 template <int M, class XB>
 FB_HD void reg_gather(double* re, double* im, int j, const XB& xb) {
   using S = RegSched<M>;
+  const int base = xb.base(j);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int u = 0; u < S::R; ++u) xb.ld(j + S::T * u, re[u], im[u]);
+  for (int u = 0; u < S::R; ++u) xb.ld(base, rf_padoff(S::T * u), re[u], im[u]);
 }
 
 template <int M, class XB>
 FB_HD void reg_scatter_modes(const double* re, const double* im, int j, const XB& xb) {
   using S = RegSched<M>;
+  const int base = xb.base(j);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int u = 0; u < S::R; ++u) xb.st(j + S::T * u, re[u], im[u]);
+  for (int u = 0; u < S::R; ++u) xb.st(base, rf_padoff(S::T * u), re[u], im[u]);
 }
+
+// partner mode of k = j + T u in the exchange buffer: M - k (k > 0), 0 (k = 0).  T >= 16: M - j - T u is a base
+// (M - j; for j = 0 it is never dereferenced itself) minus a multiple of 16.
+template <int M, class XB>
+struct RegPartner {
+  using S = RegSched<M>;
+  static constexpr bool CONSTOFF = (S::T % 16 == 0);
+  int bm, b0;
+  FB_HD RegPartner(int j, const XB& xb) : bm(CONSTOFF ? xb.base(M - j) : 0), b0(CONSTOFF ? (j == 0 ? xb.base(0) : xb.base(M - j)) : 0) {}
+  FB_HD void ld(const XB& xb, int j, int u, double& r, double& i) const {
+    if (CONSTOFF) {
+      if (u == 0) xb.ld(b0, 0, r, i);
+      else xb.ld(bm, rf_padoff(-S::T * u), r, i);
+    } else {
+      const int k = j + S::T * u;
+      xb.ld(xb.base((M - k) & (M - 1)), 0, r, i);
+    }
+  }
+};
 
 // forward split for this thread's modes k = j + T*u: (re,im)[u] <- the two spectral rows of mode k.
 // The exchange buffer holds Z (all modes of the line).  Same arithmetic as split_core (tile_fft.cuh).
-template <int M, class XB>
-FB_HD void reg_split(double* re, double* im, int j, int kind, const cpx* wN, const cpx* wQ, const XB& xb) {
+// MK: Makhoul post-twiddle (NN/DD lines); wN / wQ may point to shared memory (indexed j + T u: immediates).
+template <int M, bool MK, class XB>
+FB_HD void reg_split(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
   using S = RegSched<M>;
-  const bool mk = (kind != KIND_PP);
+  const RegPartner<M, XB> pt(j, xb);
+  const cpx* wNj = wN + j;
+  const cpx* wQj = wQ + j;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int u = 0; u < S::R; ++u) {
-    const int k = j + S::T * u;
-    const int kj = (M - k) & (M - 1);                  // partner mode (0 -> 0)
     const double zkr = re[u], zki = im[u];
     double zjr, zji;
-    xb.ld(kj, zjr, zji);
+    pt.ld(xb, j, u, zjr, zji);
     const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
     const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
-    const cpx w = wN[k];
+    const cpx w = wNj[S::T * u];
     const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
     double xr = er + wor, xi = ei + woi;
-    if (k == 0) xi = zkr - zki;                        // row 1 holds X_M = Re Z_0 - Im Z_0
-    if (mk) {
-      if (k == 0) { xr = 2.0 * xr; xi = 2.0 * wQ[M].x * xi; }
+    const bool k0 = (u == 0) && (j == 0);
+    if (k0) xi = zkr - zki;                            // row 1 holds X_M = Re Z_0 - Im Z_0
+    if (MK) {
+      if (k0) { xr = 2.0 * xr; xi = 2.0 * wQ[M].x * xi; }
       else {
-        const cpx q = wQ[k];
+        const cpx q = wQj[S::T * u];
         const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
         xr = 2.0 * tr; xi = -2.0 * ti;
       }
@@ -211,36 +253,52 @@ FB_HD void reg_split(double* re, double* im, int j, int kind, const cpx* wN, con
 
 // backward merge: (re,im)[u] holds this thread's spectral rows of mode k = j + T*u, the exchange buffer
 // holds all modes of the line; result: Z'_k (input of the inverse complex FFT).  Same arithmetic as merge_core.
-template <int M, class XB>
-FB_HD void reg_merge(double* re, double* im, int j, int kind, const cpx* wN, const cpx* wQ, const XB& xb) {
+template <int M, bool MK, class XB>
+FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
   using S = RegSched<M>;
-  const bool mk = (kind != KIND_PP);
+  const RegPartner<M, XB> pt(j, xb);
+  const cpx* wNj = wN + j;
+  const cpx* wQj = wQ + j;
+  const cpx* wQm = wQ + (M - j);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int u = 0; u < S::R; ++u) {
-    const int k = j + S::T * u;
-    const int kj = (M - k) & (M - 1);
     double xkr = re[u], xki = im[u], xjr, xji;
-    xb.ld(kj, xjr, xji);
-    if (k == 0) {
+    pt.ld(xb, j, u, xjr, xji);
+    if ((u == 0) && (j == 0)) {
       double xm = xki;
-      if (mk) xm = 2.0 * wQ[M].x * xm;
+      if (MK) xm = 2.0 * wQ[M].x * xm;
       re[u] = xkr + xm; im[u] = xkr - xm;
       continue;
     }
-    if (mk) {
-      const cpx qk = wQ[k], qj = wQ[M - k];
+    if (MK) {
+      const cpx qk = wQj[S::T * u], qj = wQm[-S::T * u];
       const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
       const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
       xkr = vkr; xki = vki; xjr = vjr; xji = vji;
     }
     const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
-    const cpx w = wN[k];
+    const cpx w = wNj[S::T * u];
     const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
     re[u] = sr - ci; im[u] = si + cr;                                     // S + i conj(w) D
   }
 }
+
+// Physical rows of packed element m = j + T u of a Makhoul (NN/DD) line, T = N/32 threads per line, R = 16:
+//   u <  8 (m <  N/4): e0 = 4 m,            e1 = e0 + 2      (even elements; DD sign +)
+//   u >= 8 (m >= N/4): e0 = 2 N - 1 - 4 m,  e1 = e0 - 2      (odd elements;  DD sign -)
+// (slot_to_elem, tile_fft.cuh, for v = 2m and 2m+1.)  So a thread needs two row bases, 4 j and 2N-1-4j, and
+// compile-time multiples of the row stride.
+template <int N>
+struct MkRows {
+  static constexpr int T = N / 32;
+  static FB_CX bool upper(int u) { return u >= 8; }
+  static FB_CX int off0(int u) { return u < 8 ? 4 * T * u : -4 * T * u; }
+  static FB_CX int off1(int u) { return u < 8 ? 4 * T * u + 2 : -4 * T * u - 2; }
+  FB_HD static int base_lo(int j) { return 4 * j; }
+  FB_HD static int base_hi(int j) { return 2 * N - 1 - 4 * j; }
+};
 
 // physical element indices (and DST sign) of packed complex element m: z_m = s0 x[e0] + i s1 x[e1]
 FB_HD void reg_phys_slots(int kind, int N, int m, int& e0, int& e1, double& s0, double& s1) {

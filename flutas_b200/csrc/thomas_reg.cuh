@@ -18,6 +18,7 @@
 //
 // HBM traffic: 16 B/pt (read once, write once).  Host-compilable core (tests/emulate) like tile_fft.cuh.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "thomas_tile.cuh"
@@ -69,10 +70,10 @@ template <int L, int TI>
 struct ThomasReg {
   static FB_HD int prow(int k) { return k + k / L; }
   static FB_HD int tile_rows(int nz) { return nz + nz / L; }
-  // shared memory (doubles): fetch slots L*maxt | ex 6*S*TI | pcr 2*3*S*TI | X S*TI | coefficients 3*tile_rows
-  static FB_HD size_t smem_doubles(int nz, int maxt) {
+  // shared memory (doubles): nbuf fetch slots of L*maxt | ex 6*S*TI | pcr 2*3*S*TI | X S*TI | coefficients 3*tile_rows
+  static FB_HD size_t smem_doubles(int nz, int maxt, int nbuf = 1) {
     const size_t S = (size_t)(nz / L), st = S * TI;
-    return (size_t)L * maxt + 13 * st + 3 * (size_t)tile_rows(nz);
+    return (size_t)nbuf * L * maxt + 13 * st + 3 * (size_t)tile_rows(nz);
   }
 
   // ---- phase 1: LU sweep down the interior rows + 3-term back substitution.
@@ -218,15 +219,25 @@ inline bool thomas_reg_pick(int nz, bool periodic, int* Lout) {
 #if defined(__CUDACC__)
 namespace fb {
 
+// store policy: see fft_reg.cuh (FB_STREAM_Y); the z tiles are 64-byte pieces 8*ncol bytes apart
+#ifndef FB_STREAM_Z
+#define FB_STREAM_Z 1
+#endif
+__device__ __forceinline__ void st_z(double* p, double v) { if (FB_STREAM_Z) __stcs(p, v); else *p = v; }
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int NLEFT> __device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
 
 // MAXT: upper bound of the block size TI*S (256 -> two blocks per SM, 512 -> one)
-template <int L, int TI, int MAXT, bool UNI, int MINB>
+// NBUF: fetch depth.  1: the next tile is fetched after phase 1 of the current one (nothing of this block is in flight
+// during phase 1); 2: two private slot sets, the tile after next is requested as soon as the current one sits in
+// registers, so one whole tile per block is always in flight (ncu, v7: 16 warps/SM, 34 % issue utilisation, the
+// stalls spread over load waits and dependent FP64 chains -> the kernel was latency-, not bandwidth-bound).
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF>
 __global__ void __launch_bounds__(MAXT, MINB)
 thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const double* W,
                   ColGeom og) {
@@ -235,8 +246,8 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   const int nz = T.nz, S = T.S;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int st = S * TI;
-  double* slots = smem;                                   // [L][MAXT], private per thread
-  double* ex = slots + (size_t)L * MAXT;                  // 6 arrays
+  double* slots = smem;                                   // [NBUF][L][MAXT], private per thread
+  double* ex = slots + (size_t)NBUF * L * MAXT;           // 6 arrays
   double* pcrA = ex + 6 * (size_t)st;                     // 3 arrays
   double* pcrB = pcrA + 3 * (size_t)st;                   // 3 arrays
   double* X = pcrB + 3 * (size_t)st;                      // 1 array
@@ -257,11 +268,14 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   double* obase = nullptr;
   if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
 
-  auto fetch = [&](long tile) {
-    const long col = min(tile * TI + lane, ncol - 1);
-    const double* src = W + col + (long)k0 * ncol;
+  auto fetch = [&](long tile, int buf) {                   // always commits a group (possibly empty): uniform counting
+    if (tile < ntiles) {
+      const long col = min(tile * TI + lane, ncol - 1);
+      const double* src = W + col + (long)k0 * ncol;
+      double* sl = slots + (size_t)buf * L * MAXT + tid;
 #pragma unroll
-    for (int l = 0; l < L; ++l) cp_async8(slots + l * MAXT + tid, src + (long)l * ncol);
+      for (int l = 0; l < L; ++l) cp_async8(sl + l * MAXT, src + (long)l * ncol);
+    }
     cp_async_commit();
   };
 
@@ -271,25 +285,30 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   };
   long tile = blockIdx.x;
   double lm_next = 0.0;
-  if (tile < ntiles) { fetch(tile); lm_next = lam_of(tile); }
+  if (tile < ntiles) { fetch(tile, 0); lm_next = lam_of(tile); }
+  if (NBUF == 2) fetch(tile + gridDim.x, 1);
   __syncthreads();                                        // coefficients staged
 
-  for (; tile < ntiles; tile += gridDim.x) {
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const long col = tile * TI + lane;
     const bool live = col < ncol;
     const double lm = lm_next;                            // loaded one tile ahead
     if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
     const bool pin = T.singular && live && (lm == 0.0);
     double v[L];
-    cp_async_wait_all();
+    const int buf = (NBUF == 2) ? (it & 1) : 0;
+    if (NBUF == 2) cp_async_wait_but<1>(); else cp_async_wait_all();
+    {
+      const double* sl = slots + (size_t)buf * L * MAXT + tid;
 #pragma unroll
-    for (int l = 0; l < L; ++l) v[l] = slots[l * MAXT + tid];
+      for (int l = 0; l < L; ++l) v[l] = sl[l * MAXT];
+    }
+    if (NBUF == 2) fetch(tile + 2 * (long)gridDim.x, buf);   // this slot set is free again (slots are private per thread)
 
     const CF cf(T, s);
     SegRegs<L> g;
     TR::phase1(v, T, cf, lm, lane, s, g, ex);
-    const long next = tile + gridDim.x;
-    if (next < ntiles) fetch(next);                       // v[] has been consumed: the slots are free again
+    if (NBUF == 1) fetch(tile + gridDim.x, 0);            // v[] has been consumed: the slots are free again
     __syncthreads();
     TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
     __syncthreads();
@@ -309,12 +328,12 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
       if (one_chunk) {
         double* dstp = obase + col;
 #pragma unroll
-        for (int l = 0; l < L; ++l) __stcs(dstp + (long)l * ncol, v[l]);
+        for (int l = 0; l < L; ++l) st_z(dstp + (long)l * ncol, v[l]);
       } else {
 #pragma unroll
         for (int l = 0; l < L; ++l) {
           const int k = k0 + l, q = k / og.n3l;
-          __stcs(og.ptr[q] + og.koff + col + ncol * (long)(k - q * og.n3l), v[l]);
+          st_z(og.ptr[q] + og.koff + col + ncol * (long)(k - q * og.n3l), v[l]);
         }
       }
     }
@@ -322,12 +341,12 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   }
 }
 
-template <int L, int TI, int MAXT, bool UNI, int MINB>
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF>
 inline cudaError_t thomas_reg_launch1(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
                                       int nsm, cudaStream_t st) {
   using TR = ThomasReg<L, TI>;
-  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB>;
-  const size_t smem = TR::smem_doubles(T.nz, MAXT) * sizeof(double);
+  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB, NBUF>;
+  const size_t smem = TR::smem_doubles(T.nz, MAXT, NBUF) * sizeof(double);
   const long ntiles = (ncol + TI - 1) / TI;
   static int per_sm = 0, cfg_nz = 0;                      // configured once per (kernel, nz)
   if (per_sm == 0 || cfg_nz != T.nz) {
@@ -350,8 +369,13 @@ inline cudaError_t thomas_reg_launch(long ncol, const ThomasArgs& T, const doubl
   // two 256-thread blocks or one 512-thread block per SM (128 registers).  Forcing three blocks (80 registers, 32
   // doubles of the segment state spilled) was measured 1.5x slower at 512^3.
   constexpr int MINB = 512 / MAXT;
-  return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB>(ncol, T, lam, W, og, nsm, st)
-                   : thomas_reg_launch1<L, TI, MAXT, false, MINB>(ncol, T, lam, W, og, nsm, st);
+  static const int nbuf = [] { const char* e = getenv("FLUTAS_B200_THOMAS_NBUF"); return (e && atoi(e) == 2) ? 2 : 1; }();
+  // two slot sets need 2 * L * MAXT doubles: fits for every L <= 16 (208 KB per SM at MAXT = 256 x 2 blocks or 512 x 1)
+  if (nbuf == 2 && ThomasReg<L, TI>::smem_doubles(T.nz, MAXT, 2) * sizeof(double) * MINB <= 220 * 1024)
+    return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB, 2>(ncol, T, lam, W, og, nsm, st)
+                     : thomas_reg_launch1<L, TI, MAXT, false, MINB, 2>(ncol, T, lam, W, og, nsm, st);
+  return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB, 1>(ncol, T, lam, W, og, nsm, st)
+                   : thomas_reg_launch1<L, TI, MAXT, false, MINB, 1>(ncol, T, lam, W, og, nsm, st);
 }
 
 // *done = false if this nz is not served (caller falls back to thomas_tile / the generic kernels).

@@ -3,6 +3,7 @@
 // (lane, worker) with the phase boundaries where the CUDA kernels have __syncthreads().  It lets
 // the index logic (Makhoul permutation, rotation swizzle, digit reversal, split/merge, mode map) be
 // checked against the oracle without a GPU.  Nothing in the product links this file.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -210,17 +211,19 @@ extern "C" int emul_thomas_reg_pick(int nz, int periodic) {
 // ---------------------------------------------------------------------------------------------
 // register-resident transforms (flutas_b200/csrc/reg_fft.cuh): the per-thread functions the kernels call, run
 // serially over the T threads of one line with the phase boundaries where the kernels synchronise.
-struct EmulXB {                          // exchange buffer of one line (the kernels add padding / lanes)
+struct EmulXB {                          // exchange buffer of one line, padded like the kernels' (they add lanes)
   double* re; double* im;
-  void st(int pos, double r, double i) const { re[pos] = r; im[pos] = i; }
-  void ld(int pos, double& r, double& i) const { r = re[pos]; i = im[pos]; }
+  int base(int pos) const { return rf_pad(pos); }
+  void st(int b, int coff, double r, double i) const { re[b + coff] = r; im[b + coff] = i; }
+  void ld(int b, int coff, double& r, double& i) const { r = re[b + coff]; i = im[b + coff]; }
 };
 
 template <int M>
 static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
   using S = RegSched<M>;
   constexpr int T = S::T, R = S::R, N = 2 * M;
-  std::vector<double> bre(M), bim(M);
+  // poisoned padded buffer: a wrong padded address reads NaN (or clobbers a slot that is read later)
+  std::vector<double> bre(M + M / 16 + 2, std::nan("")), bim(M + M / 16 + 2, std::nan(""));
   EmulXB xb{bre.data(), bim.data()};
   std::vector<double> re((size_t)T * R), im((size_t)T * R);
   auto RE = [&](int j) { return re.data() + (size_t)j * R; };
@@ -243,18 +246,31 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
       for (int u = 0; u < R; ++u) {
         int e0, e1; double s0, s1;
         reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
+        if (hp.kind != KIND_PP && M >= 16) {               // the kernels' closed form of the same rows
+          using MR = MkRows<N>;
+          const int b = MR::upper(u) ? MR::base_hi(j) : MR::base_lo(j);
+          if (b + MR::off0(u) != e0 || b + MR::off1(u) != e1) std::abort();
+          const double sg = (hp.kind == KIND_DD && MR::upper(u)) ? -1.0 : 1.0;
+          if (sg != s0 || sg != s1) std::abort();
+        }
         RE(j)[u] = s0 * in[e0]; IM(j)[u] = s1 * in[e1];
       }
     passes(std::integral_constant<int, -1>{});
     for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
-    for (int j = 0; j < T; ++j) reg_split<M>(RE(j), IM(j), j, hp.kind, hp.wN.data(), hp.wQ.data(), xb);
+    for (int j = 0; j < T; ++j) {
+      if (hp.kind == KIND_PP) reg_split<M, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      else reg_split<M, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+    }
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) { const int k = j + T * u; out[2 * k] = scale * RE(j)[u]; out[2 * k + 1] = scale * IM(j)[u]; }
   } else {
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) { const int k = j + T * u; RE(j)[u] = in[2 * k]; IM(j)[u] = in[2 * k + 1]; }
     for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
-    for (int j = 0; j < T; ++j) reg_merge<M>(RE(j), IM(j), j, hp.kind, hp.wN.data(), hp.wQ.data(), xb);
+    for (int j = 0; j < T; ++j) {
+      if (hp.kind == KIND_PP) reg_merge<M, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      else reg_merge<M, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+    }
     passes(std::integral_constant<int, +1>{});
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) {

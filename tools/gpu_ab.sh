@@ -1,0 +1,21 @@
+#!/bin/bash
+# A/B runs of kernel variants (environment variables / FLUTAS_B200_LIB builds); prints one summary line per run
+mkdir -p gpurun_out
+: > gpurun_out/ab.log
+run() { W=$1; tag=$2; shift 2; echo "== $W $tag" >> gpurun_out/ab.log; env "$@" timeout 300 python bench.py --solver-only --steps 10 --warmup 3 --workload $W 2>&1 | tail -1 >> gpurun_out/ab.log; }
+CS=$PWD/flutas_b200/csrc
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for W in ${WORKLOADS:-C2 C3 NS C5w1}; do
+  run $W new X=1
+  run $W v7 FLUTAS_B200_LIB=$CS/libflutas_b200_cs.so
+done
+python - <<'PY'
+import json
+tag=None
+for l in open('gpurun_out/ab.log'):
+    if l.startswith('=='): tag=l.strip(); continue
+    try:
+        d=json.loads(l); st=d['roofline']['stages']
+        print("%-16s %7.3f Gpts/s "%(tag[3:], d['value']), " ".join("%s %.3f"%(k[:6]+k[-3:],v['ms']) for k,v in st.items()))
+    except Exception as e: print(tag, 'ERR', l[:300])
+PY
