@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "line_plan.h"
 #include "thomas_reg.cuh"
+#include "thomas_uni.cuh"
 #include "thomas_tile.cuh"
 
 using namespace fb;
@@ -367,7 +368,16 @@ __global__ void scatter_cols_kernel(long ncol, int nz, const double* __restrict_
 int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
   const double* abc = sp->abc.as<double>();
   bool done = false;
-  if (sp->thomas_mode == 0) {                               // register-resident persistent kernel
+  static const bool uni_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_UNI"); return !(e && e[0] == '0'); }();
+  // exactly uniform z grid AND a column too long for a 16-column tile of the general kernel (nz > 512): shared LU factors.
+  // Shorter columns: the general kernel with 16-column tiles is faster (B200: 1024x512x512 0.97 vs 1.05 ms).
+  static const bool uni_all = [] { const char* e = getenv("FLUTAS_B200_THOMAS_UNI"); return e && e[0] == '2'; }();
+  if (sp->thomas_mode == 0 && g_z_uniform_ok && uni_env && sp->z_uniform.uniform && (nz > 512 || uni_all)) {
+    int rc = thomas_uni_run(ncol, nz, lam, W, W, out, periodic, singular, g_nsm > 0 ? g_nsm : 148, &sp->z_uniform, g_stream, &done);
+    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_uni launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (!done && sp->thomas_mode == 0) {                      // register-resident persistent kernel
     int rc = thomas_reg_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, W, out, periodic, singular,
                             g_nsm > 0 ? g_nsm : 148, g_z_uniform_ok ? &sp->z_uniform : nullptr, g_stream, &done);
     if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_reg launch failed: %s", cudaGetErrorString((cudaError_t)rc));

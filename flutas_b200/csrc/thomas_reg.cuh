@@ -232,27 +232,55 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 template <int NLEFT> __device__ __forceinline__ void cp_async_wait_but() { asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory"); }
 
-// MAXT: upper bound of the block size TI*S (256 -> two blocks per SM, 512 -> one)
-// NBUF: fetch depth.  1: the next tile is fetched after phase 1 of the current one (nothing of this block is in flight
-// during phase 1); 2: two private slot sets, the tile after next is requested as soon as the current one sits in
-// registers, so one whole tile per block is always in flight (ncu, v7: 16 warps/SM, 34 % issue utilisation, the
-// stalls spread over load waits and dependent FP64 chains -> the kernel was latency-, not bandwidth-bound).
-template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF>
+// ---- thread-block clusters: CL CTAs (one or two per SM) share one tile ------------------------------------------
+// A 16-column tile (128-byte row pieces: the access-pattern ceiling at 1024^3 is 2.6 TB/s for 8-column tiles and
+// 5.1 TB/s for 16, tools/pattern_bench.cu) of nz = 1024 levels does not fit the registers of one SM.  With CL = 2 the
+// CTAs of a cluster split the LEVELS: CTA r keeps segments [r S/CL, (r+1) S/CL) in registers, sends its seven reduced-
+// system inputs per segment (R0,F0,G0,RD,FD,DD and the separator's right-hand side) to the peer's shared memory
+// (st.shared::cluster), and after ONE cluster barrier per tile both CTAs solve the whole reduced system redundantly
+// (2 rows per thread) -- no second exchange, nothing else crosses the SM boundary.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_store(double* local, unsigned peer, double v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(peer));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
+// shared memory (doubles) of the kernel below
+template <int L, int TI>
+inline size_t thomas_reg_smem_doubles(int nz, int maxt, int nbuf, int cl, bool uni) {
+  const size_t st = (size_t)(nz / L) * TI;
+  const size_t exch = (cl > 1) ? 2 * 7 * st + 3 * st : 13 * st;     // CL > 1: ex[2 parities][7] | pcrA (pcrB, X alias the dead parity)
+  return (size_t)nbuf * L * maxt + exch + (uni ? 0 : 3 * (size_t)ThomasReg<L, TI>::tile_rows(nz));
+}
+
+// MAXT: upper bound of the block size TI*S/CL (256 -> two blocks per SM, 512 -> one)
+// NBUF: fetch depth.  1: the next tile is fetched after phase 1 of the current one; 2: two private slot sets, the tile
+// after next is requested as soon as the current one sits in registers.  Measured (B200, v7): NBUF = 2 is SLOWER
+// (512^3: 0.59 -> 0.76 ms, 1024^3: 6.36 -> 6.69 ms) -- more requests in flight do not help a kernel that sits at its
+// access-pattern ceiling; kept as a compile-time option, default 1.
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL>
 __global__ void __launch_bounds__(MAXT, MINB)
 thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const double* W,
                   ColGeom og) {
   using TR = ThomasReg<L, TI>;
   extern __shared__ double smem[];
-  const int nz = T.nz, S = T.S;
+  const int nz = T.nz, S = T.S;                           // S = segments of a whole column (all CTAs of the cluster)
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int st = S * TI;
+  const int S_loc = S / CL;
+  const unsigned rank = (CL > 1) ? cluster_ctarank() : 0u;
   double* slots = smem;                                   // [NBUF][L][MAXT], private per thread
-  double* ex = slots + (size_t)NBUF * L * MAXT;           // 6 arrays
-  double* pcrA = ex + 6 * (size_t)st;                     // 3 arrays
-  double* pcrB = pcrA + 3 * (size_t)st;                   // 3 arrays
-  double* X = pcrB + 3 * (size_t)st;                      // 1 array
-  double* coef = X + st;                                  // az | bz | cz at padded rows
-  const int lane = tid % TI, s = tid / TI;
+  double* exbase = slots + (size_t)NBUF * L * MAXT;       // CL = 1: ex[6] ; CL > 1: ex[2][7]
+  double* pcrA = exbase + (CL > 1 ? 14 : 6) * (size_t)st; // 3 arrays
+  double* pcrB1 = pcrA + 3 * (size_t)st;                  // CL = 1 only: 3 arrays + X
+  double* coef = pcrA + (CL > 1 ? 3 : 7) * (size_t)st;    // az | bz | cz at padded rows
+  const int lane = tid % TI, s_loc = tid / TI;
+  const int s = (int)rank * S_loc + s_loc;                // this thread's segment of the column
   if (!UNI) {
     const int tr = TR::tile_rows(nz);
     for (int k = tid; k < nz; k += nthr) {
@@ -267,6 +295,7 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   const bool one_chunk = (og.n3l % L) == 0;
   double* obase = nullptr;
   if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
+  const long tstride = gridDim.x / CL;                    // clusters in the grid
 
   auto fetch = [&](long tile, int buf) {                   // always commits a group (possibly empty): uniform counting
     if (tile < ntiles) {
@@ -283,17 +312,17 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
     const long col = tile * TI + lane;
     return (col < ncol) ? __ldg(lam + col) : -1.0;
   };
-  long tile = blockIdx.x;
+  long tile = blockIdx.x / CL;
   double lm_next = 0.0;
   if (tile < ntiles) { fetch(tile, 0); lm_next = lam_of(tile); }
-  if (NBUF == 2) fetch(tile + gridDim.x, 1);
-  __syncthreads();                                        // coefficients staged
+  if (NBUF == 2) fetch(tile + tstride, 1);
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // coefficients staged; the peer CTA is resident (DSMEM stores below)
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+  for (int it = 0; tile < ntiles; tile += tstride, ++it) {
     const long col = tile * TI + lane;
     const bool live = col < ncol;
     const double lm = lm_next;                            // loaded one tile ahead
-    if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
+    if (tile + tstride < ntiles) lm_next = lam_of(tile + tstride);
     const bool pin = T.singular && live && (lm == 0.0);
     double v[L];
     const int buf = (NBUF == 2) ? (it & 1) : 0;
@@ -303,25 +332,51 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
 #pragma unroll
       for (int l = 0; l < L; ++l) v[l] = sl[l * MAXT];
     }
-    if (NBUF == 2) fetch(tile + 2 * (long)gridDim.x, buf);   // this slot set is free again (slots are private per thread)
+    if (NBUF == 2) fetch(tile + 2 * tstride, buf);        // this slot set is free again (slots are private per thread)
 
+    double* ex = exbase + ((CL > 1) ? (size_t)(it & 1) * 7 * st : 0);
+    double* pcrB = (CL > 1) ? ex : pcrB1;                  // CL > 1: the current parity's ex is dead once the rows are built
+    double* X = pcrB + 3 * (size_t)st;
     const CF cf(T, s);
     SegRegs<L> g;
     TR::phase1(v, T, cf, lm, lane, s, g, ex);
-    if (NBUF == 1) fetch(tile + gridDim.x, 0);            // v[] has been consumed: the slots are free again
-    __syncthreads();
-    TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
+    // NBUF = 1: the slots have been free since v[] was read, but issuing the copies BEFORE phase 1 keeps 16 address pairs
+    // alive across it: the coefficient-table variant then spills (56 bytes) and runs 20 % slower (B200, 512^3, measured)
+    if (NBUF == 1) fetch(tile + tstride, 0);
+    if (CL > 1) {
+      const int o = s * TI + lane;
+      ex[6 * st + o] = v[L - 1];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int pr = 1; pr < CL; ++pr) dsmem_store(ex + q * st + o, (rank + pr) % CL, ex[q * st + o]);
+      }
+      cluster_sync_all();
+#pragma unroll
+      for (int rr = 0; rr < CL; ++rr) {
+        const int s2 = s_loc + rr * S_loc;
+        const CF cf2(T, s2);
+        TR::reduced_row(ex[6 * st + s2 * TI + lane], ex, pcrA, T, cf2, lm, lane, s2, pin);
+      }
+    } else {
+      __syncthreads();
+      TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
+    }
     __syncthreads();
     double* src = pcrA;
     double* dst = pcrB;
     const int hmax = T.periodic ? S / 2 : S;
     for (int h = 1; h < hmax; h *= 2) {
-      const bool coupled = TR::pcr_step(src, dst, T, lane, s, h);
+      bool coupled = false;
+#pragma unroll
+      for (int rr = 0; rr < CL; ++rr) coupled = TR::pcr_step(src, dst, T, lane, s_loc + rr * S_loc, h) || coupled;
       const int any = __syncthreads_or(coupled ? 1 : 0);
       double* t = src; src = dst; dst = t;
       if (!any) break;                                    // every column of the tile is decoupled already
     }
-    TR::pcr_finish(src, X, T, lane, s);
+    // X must not overlay the rows pcr_finish still reads: with CL > 1 it sits in ex[3], pcrB = ex[0..2], pcrA separate
+#pragma unroll
+    for (int rr = 0; rr < CL; ++rr) TR::pcr_finish(src, X, T, lane, s_loc + rr * S_loc);
     __syncthreads();
     TR::phase3(v, X, T, lane, s, g);
     if (live) {
@@ -337,45 +392,76 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
         }
       }
     }
-    // X / ex / pcr buffers are rewritten only after the next iteration's barriers
+    // CL = 1: X / ex / pcr buffers are rewritten only after the next iteration's barriers.  CL > 1: the next tile uses
+    // the other ex parity; the peer writes THIS parity again only after the next cluster barrier, which this CTA
+    // reaches after it is done with the tile.
   }
+  if (CL > 1) cluster_sync_all();                         // no CTA exits while its peer may still address its shared memory
 }
 
-template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF>
+struct ThomasCfgKey { int nz, uni, periodic; };
+
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL>
 inline cudaError_t thomas_reg_launch1(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
                                       int nsm, cudaStream_t st) {
-  using TR = ThomasReg<L, TI>;
-  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB, NBUF>;
-  const size_t smem = TR::smem_doubles(T.nz, MAXT, NBUF) * sizeof(double);
+  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB, NBUF, CL>;
+  const size_t smem = thomas_reg_smem_doubles<L, TI>(T.nz, MAXT, NBUF, CL, UNI) * sizeof(double);
   const long ntiles = (ncol + TI - 1) / TI;
-  static int per_sm = 0, cfg_nz = 0;                      // configured once per (kernel, nz)
-  if (per_sm == 0 || cfg_nz != T.nz) {
+  const int threads = TI * T.S / CL;
+  static int nclusters = 0, cfg_nz = 0;                   // configured once per (kernel, nz)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+  if (nclusters == 0 || cfg_nz != T.nz) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int q = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, TI * T.S, smem);
-    if (e != cudaSuccess) return e;
+    if (CL > 1) {
+      cfg.gridDim = dim3(CL * nsm);
+      e = cudaOccupancyMaxActiveClusters(&q, kern, &cfg);
+      if (e != cudaSuccess) return e;
+    } else {
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem);
+      if (e != cudaSuccess) return e;
+      q *= nsm;
+    }
     if (q < 1) return cudaErrorLaunchOutOfResources;
-    per_sm = q; cfg_nz = T.nz;
+    nclusters = q; cfg_nz = T.nz;
   }
-  const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
-  kern<<<(unsigned)grid, TI * T.S, smem, st>>>(ncol, ntiles, T, lam, W, og);
-  return cudaGetLastError();
+  const long ncl = ntiles < (long)nclusters ? ntiles : (long)nclusters;
+  cfg.gridDim = dim3((unsigned)(ncl * CL));
+  return cudaLaunchKernelEx(&cfg, kern, ncol, ntiles, T, lam, W, og);
 }
 
-template <int L, int TI, int MAXT>
-inline cudaError_t thomas_reg_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
-                                     int nsm, cudaStream_t st) {
-  // two 256-thread blocks or one 512-thread block per SM (128 registers).  Forcing three blocks (80 registers, 32
-  // doubles of the segment state spilled) was measured 1.5x slower at 512^3.
-  constexpr int MINB = 512 / MAXT;
-  static const int nbuf = [] { const char* e = getenv("FLUTAS_B200_THOMAS_NBUF"); return (e && atoi(e) == 2) ? 2 : 1; }();
-  // two slot sets need 2 * L * MAXT doubles: fits for every L <= 16 (208 KB per SM at MAXT = 256 x 2 blocks or 512 x 1)
-  if (nbuf == 2 && ThomasReg<L, TI>::smem_doubles(T.nz, MAXT, 2) * sizeof(double) * MINB <= 220 * 1024)
-    return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB, 2>(ncol, T, lam, W, og, nsm, st)
-                     : thomas_reg_launch1<L, TI, MAXT, false, MINB, 2>(ncol, T, lam, W, og, nsm, st);
-  return T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB, 1>(ncol, T, lam, W, og, nsm, st)
-                   : thomas_reg_launch1<L, TI, MAXT, false, MINB, 1>(ncol, T, lam, W, og, nsm, st);
+// Tile shapes.  cfg 0: 8 columns, one CTA per tile (v4-v7).  cfg 1: 16 columns, one 512-thread CTA (nz <= 512 at L = 16).
+// cfg 2: 16 columns, a cluster of two CTAs splits the levels (nz = 1024: 2 x 512 threads on two SMs; nz = 512: 2 x 256).
+template <int L>
+inline cudaError_t thomas_reg_dispatch(int cfgsel, long ncol, const ThomasArgs& T, const double* lam, const double* W,
+                                       const ColGeom& og, int nsm, cudaStream_t st, bool* served) {
+  const int S = T.S;
+  *served = true;
+#define FB_TL(TI, MAXT, MINB, CL)                                                                                     \
+  (T.uniform ? thomas_reg_launch1<L, TI, MAXT, true, MINB, 1, CL>(ncol, T, lam, W, og, nsm, st)                         \
+             : thomas_reg_launch1<L, TI, MAXT, false, MINB, 1, CL>(ncol, T, lam, W, og, nsm, st))
+  static const bool nbuf2 = [] { const char* e = getenv("FLUTAS_B200_THOMAS_NBUF"); return e && atoi(e) == 2; }();
+  if (nbuf2 && cfgsel == 1 && 16 * S <= 512 && (ncol % 16) == 0 &&
+      thomas_reg_smem_doubles<L, 16>(T.nz, 512, 2, 1, T.uniform) * 8 <= 227 * 1024)
+    return T.uniform ? thomas_reg_launch1<L, 16, 512, true, 1, 2, 1>(ncol, T, lam, W, og, nsm, st)
+                     : thomas_reg_launch1<L, 16, 512, false, 1, 2, 1>(ncol, T, lam, W, og, nsm, st);
+  const size_t lim = 227 * 1024;
+  if (cfgsel == 2 && S % 2 == 0 && (ncol % 16) == 0) {
+    const int thr = 16 * S / 2;
+    if (thr <= 256 && 2 * (thomas_reg_smem_doubles<L, 16>(T.nz, 256, 1, 2, T.uniform) * 8 + 1024) <= lim + 1024) return FB_TL(16, 256, 2, 2);
+    if (thr <= 512 && thomas_reg_smem_doubles<L, 16>(T.nz, 512, 1, 2, T.uniform) * 8 <= lim) return FB_TL(16, 512, 1, 2);
+  }
+  if (cfgsel == 1 && 16 * S <= 512 && (ncol % 16) == 0) return FB_TL(16, 512, 1, 1);
+  if (8 * S <= 256) return FB_TL(8, 256, 2, 1);
+  if (8 * S <= 512) return FB_TL(8, 512, 1, 1);
+#undef FB_TL
+  *served = false;
+  return cudaSuccess;
 }
 
 // *done = false if this nz is not served (caller falls back to thomas_tile / the generic kernels).
@@ -396,16 +482,23 @@ inline int thomas_reg_run(long ncol, int nz, const double* az, const double* bz,
   ColGeom og;
   if (out) og = *out;
   else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = Wout; og.n3l = nz; og.koff = 0; }
-  const bool big = (8 * T.S > 256);
+  // FLUTAS_B200_THOMAS_CFG = 0 / 1 / 2 forces a tile shape (see thomas_reg_dispatch); default: two-CTA clusters with
+  // 16-column tiles when a column needs more than 512 threads at 8 columns... (set from measurements)
+  static const int cfg_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_CFG"); return e ? atoi(e) : -1; }();
+  // default: 16-column tiles in one 512-thread CTA whenever a column fits (S <= 32 segments); measured on B200 against
+  // 8-column tiles: 512^3 0.585 -> 0.494 ms, 1024x512x512 1.30 -> 0.97 ms, 1024x1024x512 2.99 -> 1.80 ms.  The cluster
+  // variant (cfg 2) is correct but slower (1024^3: 8.1 vs 6.4 ms) and stays an option only.
+  int cfgsel = cfg_env >= 0 ? cfg_env : ((16 * T.S <= 512) ? 1 : 0);
+  bool served = false;
   cudaError_t e = cudaSuccess;
   switch (L) {
-    case 2: e = big ? thomas_reg_launch<2, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<2, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
-    case 4: e = big ? thomas_reg_launch<4, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<4, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
-    case 8: e = big ? thomas_reg_launch<8, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<8, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
-    default: e = big ? thomas_reg_launch<16, 8, 512>(ncol, T, lam, W, og, nsm, st) : thomas_reg_launch<16, 8, 256>(ncol, T, lam, W, og, nsm, st); break;
+    case 2: e = thomas_reg_dispatch<2>(cfgsel, ncol, T, lam, W, og, nsm, st, &served); break;
+    case 4: e = thomas_reg_dispatch<4>(cfgsel, ncol, T, lam, W, og, nsm, st, &served); break;
+    case 8: e = thomas_reg_dispatch<8>(cfgsel, ncol, T, lam, W, og, nsm, st, &served); break;
+    default: e = thomas_reg_dispatch<16>(cfgsel, ncol, T, lam, W, og, nsm, st, &served); break;
   }
   if (e != cudaSuccess) return (int)e;
-  *done = true;
+  *done = served;
   return 0;
 }
 

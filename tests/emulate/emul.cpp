@@ -203,6 +203,62 @@ extern "C" int emul_thomas_reg(int L, int nz, long ncol, int periodic, int singu
   return 0;
 }
 
+// shared-LU kernel for exactly uniform grids (flutas_b200/csrc/thomas_uni.cuh): same phases as thomas_uni_kernel
+#include "../../flutas_b200/csrc/thomas_uni.cuh"
+
+template <int L, int TI>
+static void thomas_uni_emul(long ncol, ThomasArgs T, const double* lam, double* W) {
+  using TU = ThomasUni<L, TI>;
+  using TR = ThomasReg<L, TI>;
+  const int S = T.S, st = S * TI;
+  const long ntiles = (ncol + TI - 1) / TI;
+  std::vector<double> tab(TU::tab_doubles()), ex(6 * (size_t)st), pa(3 * (size_t)st), pb(3 * (size_t)st), X(st);
+  std::vector<double> v((size_t)st * L);
+  for (long tile = 0; tile < ntiles; ++tile) {
+    auto colof = [&](int lane) { return tile * TI + lane; };
+    auto live = [&](int lane) { return colof(lane) < ncol; };
+    auto lamof = [&](int lane) { return live(lane) ? lam[colof(lane)] : -1.0; };
+    auto vof = [&](int lane, int s) { return v.data() + ((size_t)s * TI + lane) * L; };
+#define ALLT for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
+    std::fill(tab.begin(), tab.end(), std::nan(""));
+    for (int var = 0; var < 2; ++var) for (int lane = 0; lane < TI; ++lane) TU::build(tab.data(), T, lamof(lane), lane, var);
+    ALLT { const long col = live(lane) ? colof(lane) : ncol - 1; for (int l = 0; l < L; ++l) vof(lane, s)[l] = W[col + (long)(s * L + l) * ncol]; }
+    ALLT TU::phase1(vof(lane, s), tab.data(), T, lane, s, ex.data());
+    ALLT { const bool pin = T.singular && live(lane) && lamof(lane) == 0.0;
+           TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, CoefUniform<L>(T, s), lamof(lane), lane, s, pin); }
+    double* src = pa.data(); double* dst = pb.data();
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) {
+      bool any = false;
+      ALLT any = TR::pcr_step(src, dst, T, lane, s, h) || any;
+      double* t = src; src = dst; dst = t;
+      if (!any) break;
+    }
+    ALLT TR::pcr_finish(src, X.data(), T, lane, s);
+    ALLT TU::phase3(vof(lane, s), X.data(), tab.data(), T, lane, s);
+    ALLT if (live(lane)) for (int l = 0; l < L; ++l) W[colof(lane) + (long)(s * L + l) * ncol] = vof(lane, s)[l];
+#undef ALLT
+  }
+}
+
+// returns the segment length used (> 0), 0 if the grid is not exactly uniform / nz not served
+extern "C" int emul_thomas_uni(int nz, long ncol, int periodic, int singular, const double* a, const double* b,
+                               const double* c, const double* lam, double* W) {
+  ThomasArgs T;
+  T.nz = nz; T.periodic = periodic; T.singular = singular; T.az = T.bz = T.cz = nullptr; T.padded = 0;
+  if (!thomas_detect_uniform(nz, a, b, c, periodic != 0, T)) return 0;
+  int L = 0;
+  if (!thomas_uni_pick(nz, periodic != 0, &L)) return 0;
+  T.S = nz / L;
+  switch (L) {
+    case 4: thomas_uni_emul<4, 16>(ncol, T, lam, W); break;
+    case 8: thomas_uni_emul<8, 16>(ncol, T, lam, W); break;
+    case 16: thomas_uni_emul<16, 16>(ncol, T, lam, W); break;
+    default: thomas_uni_emul<32, 16>(ncol, T, lam, W); break;
+  }
+  return L;
+}
+
 extern "C" int emul_thomas_reg_pick(int nz, int periodic) {
   int L = 0;
   return thomas_reg_pick(nz, periodic != 0, &L) ? L : 0;

@@ -77,6 +77,10 @@ CASES = [
     ("p2d", (2048, 64, 4), ("NN", "PP", "NN"), (2.0, 1.0, 1.0), 0.0),
     ("p2e", (72, 2048, 4), ("PP", "NN", "NN"), (2.0, 1.0, 1.0), 0.0),
     ("p2f", (1000, 128, 6), ("DD", "PP", "PP"), (2.0, 1.0, 1.0), 0.0),
+    # exactly uniform z grids (lz/nz a binary fraction): the shared-LU z kernel (thomas_uni.cuh), L = 32 / 16 / 32 periodic
+    ("uni1024", (16, 24, 1024), ("PP", "PP", "NN"), (1.0, 1.0, 1.0), 0.0),
+    ("uni512", (40, 16, 512), ("NN", "PP", "DD"), (1.0, 1.0, 2.0), 0.0),
+    ("uni1024p", (16, 16, 1024), ("PP", "PP", "PP"), (1.0, 1.0, 4.0), 0.0),
 ]
 
 

@@ -112,6 +112,7 @@ def test_unsupported_lengths_are_rejected(emul):
 def emul_t(emul):
     emul.emul_thomas_tile.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     emul.emul_thomas_reg.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
+    emul.emul_thomas_uni.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     return emul
 
 
@@ -119,12 +120,17 @@ def emul_t(emul):
 @pytest.mark.parametrize("nz,L", [(8, 2), (16, 4), (32, 8), (64, 8), (72, 8), (40, 8), (64, 16), (128, 16), (512, 16),
                                   (256, 32), (1024, 32), (12, 2), (24, 4), (1024, 16), (48, 16), (4, 2)])
 @pytest.mark.parametrize("stretched", [False, True])
-@pytest.mark.parametrize("variant", ["tile", "reg", "reg-uniform"])
+@pytest.mark.parametrize("variant", ["tile", "reg", "reg-uniform", "uni"])
 def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched, variant):
-    if variant == "reg-uniform" and (stretched or nz < 4):
+    if variant in ("reg-uniform", "uni") and (stretched or nz < 4):
         pytest.skip("scalar-coefficient path: uniform grids only")
-    if variant != "tile" and L > 16:
+    if variant in ("reg", "reg-uniform") and L > 16:
         pytest.skip("the register kernel keeps at most 16 levels per thread")
+    if variant == "uni":                                 # the shared-LU kernel picks its own segment length
+        L = next((q for q in (4, 8, 16, 32) if nz % q == 0 and 2 <= nz // q <= 32
+                  and not (periodic and (nz // q) & (nz // q - 1))), None)
+        if L is None:
+            pytest.skip("nz not served by the shared-LU kernel (falls back to the register kernel)")
     S = nz // L
     if periodic and (S & (S - 1)):
         pytest.skip("cyclic PCR needs a power-of-two number of separators (falls back to the generic kernel)")
@@ -135,7 +141,7 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
     dzc, dzf = initsolver.initgrid(nz, 2.0 if stretched else 0.0, 1.0, 1)
     bcz = "PP" if periodic else "NN"
     a, b, c = initsolver.tridmatrix(bcz, nz, 1, 1.0 / dzc, 1.0 / dzf)
-    if variant == "reg-uniform":
+    if variant in ("reg-uniform", "uni"):
         # exactly uniform coefficients (what initgrid produces when lz/nz is a binary fraction, e.g. lz = 1, nz = 512);
         # the oracle solves with the same arrays
         a0 = a[1]
@@ -157,6 +163,8 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
             np.asfortranarray(lam).ctypes.data_as(_dp), got.ctypes.data_as(_dp))
     if variant == "tile":
         rc = emul_t.emul_thomas_tile(*args)
+    elif variant == "uni":
+        rc = 0 if emul_t.emul_thomas_uni(*args[1:]) == L else 5
     else:
         rc = emul_t.emul_thomas_reg(*args, 2 if variant == "reg-uniform" else 0)
     assert rc == 0
