@@ -369,15 +369,20 @@ int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const
   const double* abc = sp->abc.as<double>();
   bool done = false;
   static const bool uni_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_UNI"); return !(e && e[0] == '0'); }();
-  // exactly uniform z grid AND a column too long for a 16-column tile of the general kernel (nz > 512): shared LU factors.
-  // Shorter columns: the general kernel with 16-column tiles is faster (B200: 1024x512x512 0.97 vs 1.05 ms).
-  static const bool uni_all = [] { const char* e = getenv("FLUTAS_B200_THOMAS_UNI"); return e && e[0] == '2'; }();
-  if (sp->thomas_mode == 0 && g_z_uniform_ok && uni_env && sp->z_uniform.uniform && (nz > 512 || uni_all)) {
+  // exactly uniform z grid: shared LU factors + TMA tile loads (thomas_uni.cuh).  B200, z stage: 1024^3 6.38 -> 4.56 ms,
+  // 1024x512x512 0.97 -> 0.86 ms, 1024x1024x512 1.80 -> 1.74 ms against the general kernel's best tile shape.
+  if (sp->thomas_mode == 0 && g_z_uniform_ok && uni_env && sp->z_uniform.uniform) {
     int rc = thomas_uni_run(ncol, nz, lam, W, W, out, periodic, singular, g_nsm > 0 ? g_nsm : 148, &sp->z_uniform, g_stream, &done);
     if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_uni launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  if (!done && sp->thomas_mode == 0) {                      // register-resident persistent kernel
+  if (!done && sp->thomas_mode == 0) {                      // register-resident kernel, tiles through TMA (L = 16 shapes)
+    int rc = thomas_reg_tma_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, W, out, periodic, singular,
+                                g_nsm > 0 ? g_nsm : 148, g_z_uniform_ok ? &sp->z_uniform : nullptr, g_stream, &done);
+    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_reg_tma launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  if (!done && sp->thomas_mode == 0) {                      // register-resident persistent kernel (cp.async slots)
     int rc = thomas_reg_run(ncol, nz, abc + 3 * nz, abc + 4 * nz, abc + 5 * nz, lam, W, W, out, periodic, singular,
                             g_nsm > 0 ? g_nsm : 148, g_z_uniform_ok ? &sp->z_uniform : nullptr, g_stream, &done);
     if (rc) return fail(FLUTAS_B200_ERR_CUDA, "thomas_reg launch failed: %s", cudaGetErrorString((cudaError_t)rc));

@@ -19,6 +19,8 @@
 // the last bit and the general kernel (coefficient tables) is used -- never an averaged coefficient.
 // Host-compilable core (tests/emulate), like thomas_reg.cuh.
 #pragma once
+#include <cstdint>
+
 #include "thomas_reg.cuh"
 
 namespace fb {
@@ -132,7 +134,350 @@ inline bool thomas_uni_pick(int nz, bool periodic, int* Lout) {
 }  // namespace fb
 
 #if defined(__CUDACC__)
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 namespace fb {
+
+// ---- TMA (cp.async.bulk.tensor) plumbing ---------------------------------------------------------------------
+// The 16-column tile is a 2-D box {16 columns, up to 256 levels} of the (ncol x nz) work array: nz/256 bulk tensor copies
+// issued by ONE thread bring a whole tile into shared memory and signal an mbarrier, instead of L cp.async per thread
+// (ncu, v9 kernel at 1024^3: 17 % issue utilisation, top stalls lg_throttle 5.1 and mio_throttle 4.1 per issue -- the
+// LSU queue, not HBM; one LDGSTS costs ~8 issue cycles, 32 per thread x 16 warps ~ 4000 cycles of a 15000-cycle tile).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+template <int L, int TI, int MINB>
+__global__ void __launch_bounds__(512 / MINB, MINB)
+thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const __grid_constant__ CUtensorMap tmap,
+                      int box_rows, ColGeom og) {
+  using TU = ThomasUni<L, TI>;
+  using TR = ThomasReg<L, TI>;
+  extern __shared__ __align__(128) double smem[];
+  const int S = T.S, nz = T.nz;
+  const int tid = threadIdx.x;
+  const int st = S * TI;
+  double* tile_s = smem;                                  // [nz][TI] dense, filled by the TMA unit
+  double* tab = tile_s + (size_t)nz * TI;
+  double* ex = tab + TU::tab_doubles();                   // 6 arrays
+  double* pcrA = ex + 6 * (size_t)st;
+  double* pcrB = pcrA + 3 * (size_t)st;
+  double* X = pcrB + 3 * (size_t)st;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(X + st);
+  const int lane = tid % TI, s = tid / TI;
+  const int k0 = s * L;
+  const bool one_chunk = (og.n3l % L) == 0;
+  double* obase = nullptr;
+  if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
+  const unsigned tile_bytes = (unsigned)nz * TI * sizeof(double);
+
+  auto fetch = [&](long tile) {                            // one thread: whole tile, completion counted in bytes on `bar`
+    if (tid == 0 && tile < ntiles) {
+      mbar_expect_tx(bar, tile_bytes);                     // (out-of-range columns of a ragged last tile are zero-filled and counted)
+      for (int r = 0; r < nz; r += box_rows) tma_load_2d(tile_s + (size_t)r * TI, &tmap, (int)(tile * TI), r, bar);
+    }
+  };
+  auto lam_of = [&](long tile) {                           // dead lanes of a ragged last tile: any regular column
+    const long col = tile * TI + lane;
+    return (col < ncol) ? __ldg(lam + col) : -1.0;
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long tile = blockIdx.x;
+  double lm_next = 0.0;
+  if (tile < ntiles) { fetch(tile); lm_next = lam_of(tile); }
+
+  for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const long col = tile * TI + lane;
+    const bool live = col < ncol;
+    const double lm = lm_next;
+    if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
+    const bool pin = T.singular && live && (lm == 0.0);
+    if (tid < 2 * TI) TU::build(tab, T, lm, lane, tid / TI);           // overlaps the wait for the tile
+    double v[L];
+    mbar_wait(bar, it & 1u);
+    {
+      const double* ts = tile_s + (size_t)k0 * TI + lane;
+#pragma unroll
+      for (int l = 0; l < L; ++l) v[l] = ts[l * TI];
+    }
+    __syncthreads();                                        // tables ready; every thread has its levels: the tile buffer is free
+    fetch(tile + gridDim.x);                                // next tile streams in during the rest of this iteration
+    TU::phase1(v, tab, T, lane, s, ex);
+    __syncthreads();
+    const CoefUniform<L> cf(T, s);
+    TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
+    __syncthreads();
+    double* src = pcrA;
+    double* dst = pcrB;
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) {
+      const bool coupled = TR::pcr_step(src, dst, T, lane, s, h);
+      const int any = __syncthreads_or(coupled ? 1 : 0);
+      double* t = src; src = dst; dst = t;
+      if (!any) break;
+    }
+    TR::pcr_finish(src, X, T, lane, s);
+    __syncthreads();
+    TU::phase3(v, X, tab, T, lane, s);
+    if (live) {
+      if (one_chunk) {
+        double* dstp = obase + col;
+#pragma unroll
+        for (int l = 0; l < L; ++l) st_z(dstp + (long)l * ncol, v[l]);
+      } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const int k = k0 + l, q = k / og.n3l;
+          st_z(og.ptr[q] + og.koff + col + ncol * (long)(k - q * og.n3l), v[l]);
+        }
+      }
+    }
+    __syncthreads();                                        // the tables are rebuilt by the next iteration
+  }
+}
+
+// General (coefficient-table or scalar-coefficient) register kernel of thomas_reg.cuh with the tile brought in by TMA:
+// same phases as thomas_reg_kernel<.., CL = 1>, the per-thread cp.async slots replaced by one dense [nz][TI] tile.
+template <int L, int TI, bool UNI>
+__global__ void __launch_bounds__(512, 1)
+thomas_reg_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const __grid_constant__ CUtensorMap tmap,
+                      int box_rows, ColGeom og) {
+  using TR = ThomasReg<L, TI>;
+  extern __shared__ __align__(128) double smem[];
+  const int nz = T.nz, S = T.S;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int st = S * TI;
+  double* tile_s = smem;                                  // [nz][TI] dense, filled by the TMA unit
+  double* ex = tile_s + (size_t)nz * TI;                  // 6 arrays
+  double* pcrA = ex + 6 * (size_t)st;
+  double* pcrB = pcrA + 3 * (size_t)st;
+  double* X = pcrB + 3 * (size_t)st;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(X + st);
+  double* coef = X + st + 2;                              // az | bz | cz at padded rows
+  const int lane = tid % TI, s = tid / TI;
+  if (!UNI) {
+    const int tr = TR::tile_rows(nz);
+    for (int k = tid; k < nz; k += nthr) {
+      const int r = TR::prow(k);
+      coef[r] = __ldg(T.az + k); coef[tr + r] = __ldg(T.bz + k); coef[2 * tr + r] = __ldg(T.cz + k);
+    }
+    T.az = coef; T.bz = coef + tr; T.cz = coef + 2 * tr; T.padded = 1;
+  }
+  using CF = typename std::conditional<UNI, CoefUniform<L>, CoefTable<L>>::type;
+  const int k0 = s * L;
+  const bool one_chunk = (og.n3l % L) == 0;
+  double* obase = nullptr;
+  if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
+  const unsigned tile_bytes = (unsigned)nz * TI * sizeof(double);
+  auto fetch = [&](long tile) {
+    if (tid == 0 && tile < ntiles) {
+      mbar_expect_tx(bar, tile_bytes);
+      for (int r = 0; r < nz; r += box_rows) tma_load_2d(tile_s + (size_t)r * TI, &tmap, (int)(tile * TI), r, bar);
+    }
+  };
+  auto lam_of = [&](long tile) {
+    const long col = tile * TI + lane;
+    return (col < ncol) ? __ldg(lam + col) : -1.0;
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();                                        // barrier initialised, coefficients staged
+  long tile = blockIdx.x;
+  double lm_next = 0.0;
+  if (tile < ntiles) { fetch(tile); lm_next = lam_of(tile); }
+
+  for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const long col = tile * TI + lane;
+    const bool live = col < ncol;
+    const double lm = lm_next;
+    if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
+    const bool pin = T.singular && live && (lm == 0.0);
+    double v[L];
+    mbar_wait(bar, it & 1u);
+    {
+      const double* ts = tile_s + (size_t)k0 * TI + lane;
+#pragma unroll
+      for (int l = 0; l < L; ++l) v[l] = ts[l * TI];
+    }
+    const CF cf(T, s);
+    SegRegs<L> g;
+    TR::phase1(v, T, cf, lm, lane, s, g, ex);
+    __syncthreads();                                        // every thread holds its levels: the tile buffer is free
+    fetch(tile + gridDim.x);
+    TR::reduced_row(v[L - 1], ex, pcrA, T, cf, lm, lane, s, pin);
+    __syncthreads();
+    double* src = pcrA;
+    double* dst = pcrB;
+    const int hmax = T.periodic ? S / 2 : S;
+    for (int h = 1; h < hmax; h *= 2) {
+      const bool coupled = TR::pcr_step(src, dst, T, lane, s, h);
+      const int any = __syncthreads_or(coupled ? 1 : 0);
+      double* t = src; src = dst; dst = t;
+      if (!any) break;
+    }
+    TR::pcr_finish(src, X, T, lane, s);
+    __syncthreads();
+    TR::phase3(v, X, T, lane, s, g);
+    if (live) {
+      if (one_chunk) {
+        double* dstp = obase + col;
+#pragma unroll
+        for (int l = 0; l < L; ++l) st_z(dstp + (long)l * ncol, v[l]);
+      } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const int k = k0 + l, q = k / og.n3l;
+          st_z(og.ptr[q] + og.koff + col + ncol * (long)(k - q * og.n3l), v[l]);
+        }
+      }
+    }
+    // X / ex / pcr buffers are rewritten only after the next iteration's barriers
+  }
+}
+
+// tensor map of the (ncol x nz) FP64 work array with a {TI, box_rows} box; cached for the last (pointer, shape)
+inline cudaError_t thomas_uni_tensor_map(const double* W, long ncol, int nz, int ti, int box_rows, CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  static const double* cW = nullptr; static long cncol = 0; static int cnz = 0, cti = 0, cbr = 0; static CUtensorMap cmap;
+  if (cW != W || cncol != ncol || cnz != nz || cti != ti || cbr != box_rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)ncol, (cuuint64_t)nz};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ncol * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)ti, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    static const int promo = [] { const char* e = getenv("FLUTAS_B200_TMA_L2"); return e ? atoi(e) : 128; }();
+    const CUtensorMapL2promotion l2 = promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                    : promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    const CUresult r = encode(&cmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(W), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cW = nullptr; return cudaErrorInvalidValue; }
+    cW = W; cncol = ncol; cnz = nz; cti = ti; cbr = box_rows;
+  }
+  *out = cmap;
+  return cudaSuccess;
+}
+
+template <int L, int TI, int MINB>
+inline cudaError_t thomas_uni_tma_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
+                                         int nsm, cudaStream_t st) {
+  using TU = ThomasUni<L, TI>;
+  auto kern = thomas_uni_tma_kernel<L, TI, MINB>;
+  const int threads = TI * T.S;
+  const int box_rows = T.nz < 256 ? T.nz : 256;
+  if (T.nz % box_rows) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)T.nz * TI + TU::tab_doubles() + 13 * (size_t)T.S * TI + 2) * sizeof(double);
+  const long ntiles = (ncol + TI - 1) / TI;
+  CUtensorMap map;
+  cudaError_t e = thomas_uni_tensor_map(W, ncol, T.nz, TI, box_rows, &map);
+  if (e != cudaSuccess) return e;
+  static int per_sm = 0, cfg_nz = 0;
+  if (per_sm == 0 || cfg_nz != T.nz) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = q; cfg_nz = T.nz;
+  }
+  const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
+  kern<<<(unsigned)grid, threads, smem, st>>>(ncol, ntiles, T, lam, map, box_rows, og);
+  return cudaGetLastError();
+}
+
+template <int L, int TI, bool UNI>
+inline cudaError_t thomas_reg_tma_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
+                                         int nsm, cudaStream_t st) {
+  using TR = ThomasReg<L, TI>;
+  auto kern = thomas_reg_tma_kernel<L, TI, UNI>;
+  const int threads = TI * T.S;
+  const int box_rows = T.nz < 256 ? T.nz : 256;
+  if (T.nz % box_rows || threads > 512) return cudaErrorInvalidValue;
+  const size_t smem = ((size_t)T.nz * TI + 13 * (size_t)T.S * TI + 2 + (UNI ? 0 : 3 * (size_t)TR::tile_rows(T.nz))) * sizeof(double);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  const long ntiles = (ncol + TI - 1) / TI;
+  CUtensorMap map;
+  cudaError_t e = thomas_uni_tensor_map(W, ncol, T.nz, TI, box_rows, &map);
+  if (e != cudaSuccess) return e;
+  static int per_sm = 0, cfg_nz = 0;
+  if (per_sm == 0 || cfg_nz != T.nz) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int q = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (q < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = q; cfg_nz = T.nz;
+  }
+  const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
+  kern<<<(unsigned)grid, threads, smem, st>>>(ncol, ntiles, T, lam, map, box_rows, og);
+  return cudaGetLastError();
+}
+
+// General kernel with TMA tile loads: 16-column tiles when a column has <= 32 segments, else 8-column tiles (<= 64).
+// *done = false when the shape / alignment is not served (caller: thomas_reg_run with cp.async slots).
+inline int thomas_reg_tma_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam,
+                              const double* W, double* Wout, const ColGeom* out, bool periodic, int singular, int nsm,
+                              const ThomasArgs* uni, cudaStream_t st, bool* done) {
+  *done = false;
+  // Measured on B200: no gain over the cp.async slots for this kernel (512^3 0.492 vs 0.493 ms; 8-column tiles at 1024^3
+  // 7.2 vs 6.4 ms) -- its 16 copies per thread do not saturate the LSU queue the way the 32 of the shared-LU kernel do.
+  // Kept as an option: FLUTAS_B200_THOMAS_TMA_GEN=1.
+  static const bool tma_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_TMA_GEN"); return e && e[0] == '1'; }();
+  int L = 0;
+  if (!tma_env || (ncol % 2) || (reinterpret_cast<uintptr_t>(W) % 16) || !thomas_reg_pick(nz, periodic, &L) || L != 16) return 0;
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / L; T.periodic = periodic ? 1 : 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz;
+  T.padded = 0; T.uniform = 0;
+  if (uni && uni->uniform) {
+    T.uniform = 1; T.a0 = uni->a0; T.b0 = uni->b0; T.a_first = uni->a_first; T.b_first = uni->b_first;
+    T.b_last = uni->b_last; T.c_last = uni->c_last;
+  }
+  ColGeom og;
+  if (out) og = *out;
+  else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = Wout; og.n3l = nz; og.koff = 0; }
+  cudaError_t e;
+  if (T.S <= 32) e = T.uniform ? thomas_reg_tma_launch<16, 16, true>(ncol, T, lam, W, og, nsm, st) : thomas_reg_tma_launch<16, 16, false>(ncol, T, lam, W, og, nsm, st);
+  else if (T.S <= 64) e = T.uniform ? thomas_reg_tma_launch<16, 8, true>(ncol, T, lam, W, og, nsm, st) : thomas_reg_tma_launch<16, 8, false>(ncol, T, lam, W, og, nsm, st);
+  else return 0;
+  if (e == cudaErrorInvalidValue) { (void)cudaGetLastError(); return 0; }     // shape not served (shared memory): fall back
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
+  return 0;
+}
 
 template <int L, int TI, int MINB>
 __global__ void __launch_bounds__(512 / MINB, MINB)
@@ -258,6 +603,19 @@ inline int thomas_uni_run(long ncol, int nz, const double* lam, const double* W,
   if (out) og = *out;
   else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = Wout; og.n3l = nz; og.koff = 0; }
   cudaError_t e = cudaSuccess;
+  // TMA tile loads need a 16-byte aligned base and row pitch (ncol even); FLUTAS_B200_THOMAS_TMA=0 keeps the cp.async kernel
+  static const bool tma_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_TMA"); return !(e && e[0] == '0'); }();
+  if (tma_env && (ncol % 2) == 0 && (reinterpret_cast<uintptr_t>(W) % 16) == 0) {
+    switch (L) {
+      case 4: e = thomas_uni_tma_launch<4, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
+      case 8: e = thomas_uni_tma_launch<8, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
+      case 16: e = thomas_uni_tma_launch<16, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
+      default: e = thomas_uni_tma_launch<32, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
+    }
+    if (e != cudaSuccess) return (int)e;
+    *done = true;
+    return 0;
+  }
   switch (L) {
     case 4: e = thomas_uni_launch<4, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
     case 8: e = thomas_uni_launch<8, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
