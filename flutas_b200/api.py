@@ -118,6 +118,27 @@ def correc(nx, ny, nz, nh_d, nh_u, dxi, dyi, dzi, dzci, dt, rho0, p, u, v, w, rh
                                               _ptr(p), _ptr(u), _ptr(v), _ptr(w), None))
 
 
+def pres_sp_src(nx, ny, nz, f_t12, dxi, dyi, dzi, nh_d, nh_u, dzci, rho0i, pold, u, v, w):
+    """pres_sp_src(nx,ny,nz,f_t12,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,pold,u,v,w), src/source.f90:311"""
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_pres_sp_src(nx, ny, nz, f_t12, dxi, dyi, dzi, nh_d, nh_u, _ptr(dzci), rho0i,
+                                                   _ptr(pold), _ptr(u), _ptr(v), _ptr(w)))
+
+
+def pres_tw_src(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzci, rho0i, f_t12, f_t12_o, p, pold, rho, u, v, w):
+    """pres_tw_src(nx,ny,nz,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,f_t12,f_t12_o,p,pold,rho,u,v,w), src/source.f90:247
+    (constant-coefficient Poisson branch)"""
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_pres_tw_src(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, _ptr(dzci), rho0i, f_t12,
+                                                   f_t12_o, _ptr(p), _ptr(pold), _ptr(rho), _ptr(u), _ptr(v), _ptr(w)))
+
+
+def pold_update(nx, ny, nz, mode, p, pold):
+    """mode 0: pold = p (main__single_phase.f90:693-699); mode 1: p = pold + p (:734-740); interior only"""
+    _use_torch_stream()
+    _lib.check(_lib.load().flutas_b200_pold_update(nx, ny, nz, mode, _ptr(p), _ptr(pold)))
+
+
 def boundp(cbc, n, bc, nh_d, nh_p, dl, dzc, dzf, p):
     """boundp(cbc,n,bc,nh_d,nh_p,halo,dl,dzc,dzf,p), src/bound.f90:146 (the MPI `halo` datatypes have no counterpart).
     cbc: three 2-character strings; bc: (3,2) boundary values."""

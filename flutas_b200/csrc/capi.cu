@@ -450,7 +450,7 @@ StencilGeom stencil_geom(int nx, int ny, int nz, int nh_u) {
 }
 
 // staging of host fields for the stencil entry points
-DevBuf g_stage[4], g_coef, g_red;
+DevBuf g_stage[6], g_coef, g_red;
 
 struct FieldRef {            // a field that is either already on the device or staged into g_stage[slot]
   double* dev = nullptr;
@@ -942,6 +942,83 @@ int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   if (int rc = stage_out(fv)) return rc;
   if (int rc = stage_out(fw)) return rc;
   if (fu.staged || fv.staged || fw.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_pres_sp_src(int nx, int ny, int nz, double f_t12, double dxi, double dyi, double dzi, int nh_d, int nh_u,
+                            const double* dzci, double rho0i, const double* pold, double* u, double* v, double* w) {
+  (void)dzi;
+  if (int rc = ensure_device()) return rc;
+  if (!dzci || !u || !v || !w || !pold) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (nh_u < 1 || nh_d < 1) return fail(FLUTAS_B200_ERR_ARG, "halo widths must be >= 1");
+  StencilGeom g = stencil_geom(nx, ny, nz, nh_u);
+  const size_t ucount = (size_t)g.su1 * g.su2 * (nz + 2 * nh_u), pcount = (size_t)g.sp1 * g.sp2 * (nz + 2);
+  FieldRef fu, fv, fw, fp;
+  if (int rc = stage_in(fu, 0, u, ucount, true)) return rc;
+  if (int rc = stage_in(fv, 1, v, ucount, true)) return rc;
+  if (int rc = stage_in(fw, 2, w, ucount, true)) return rc;
+  if (int rc = stage_in(fp, 3, pold, pcount, true)) return rc;
+  const size_t nd = (size_t)nz + 2 * nh_d;
+  if (int rc = g_coef.reserve(nd * sizeof(double))) return rc;
+  CK(cudaMemcpyAsync(g_coef.p, dzci, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+  dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  pres_sp_src_kernel<<<grd, blk, 0, g_stream>>>(g, f_t12, dxi, dyi, g_coef.as<double>() + (nh_d - 1), rho0i, fp.dev, fu.dev,
+                                                fv.dev, fw.dev);
+  LAUNCHED();
+  if (int rc = stage_out(fu)) return rc;
+  if (int rc = stage_out(fv)) return rc;
+  if (int rc = stage_out(fw)) return rc;
+  if (fu.staged || fv.staged || fw.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_pres_tw_src(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u, const double* dzci,
+                            double rho0i, double f_t12, double f_t12_o, const double* p, const double* pold,
+                            const double* rho, double* u, double* v, double* w) {
+  (void)dzi;
+  if (int rc = ensure_device()) return rc;
+  if (!dzci || !u || !v || !w || !p || !pold || !rho) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (nh_u < 1 || nh_d < 1) return fail(FLUTAS_B200_ERR_ARG, "halo widths must be >= 1");
+  if (f_t12_o == 0.0) return fail(FLUTAS_B200_ERR_ARG, "pres_tw_src: f_t12_o must not be zero");
+  StencilGeom g = stencil_geom(nx, ny, nz, nh_u);
+  const size_t ucount = (size_t)g.su1 * g.su2 * (nz + 2 * nh_u), pcount = (size_t)g.sp1 * g.sp2 * (nz + 2);
+  FieldRef fu, fv, fw, fp, fo, fr;
+  if (int rc = stage_in(fu, 0, u, ucount, true)) return rc;
+  if (int rc = stage_in(fv, 1, v, ucount, true)) return rc;
+  if (int rc = stage_in(fw, 2, w, ucount, true)) return rc;
+  if (int rc = stage_in(fp, 3, p, pcount, true)) return rc;
+  if (int rc = stage_in(fo, 4, pold, pcount, true)) return rc;
+  if (int rc = stage_in(fr, 5, rho, pcount, true)) return rc;
+  const size_t nd = (size_t)nz + 2 * nh_d;
+  if (int rc = g_coef.reserve(nd * sizeof(double))) return rc;
+  CK(cudaMemcpyAsync(g_coef.p, dzci, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+  const double f1 = 1.0 + (f_t12 / f_t12_o), f2 = (f_t12 / f_t12_o);      // source.f90:266-269
+  dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  pres_tw_src_kernel<<<grd, blk, 0, g_stream>>>(g, dxi, dyi, g_coef.as<double>() + (nh_d - 1), rho0i, f_t12, f1, f2, fp.dev,
+                                                fo.dev, fr.dev, fu.dev, fv.dev, fw.dev);
+  LAUNCHED();
+  if (int rc = stage_out(fu)) return rc;
+  if (int rc = stage_out(fv)) return rc;
+  if (int rc = stage_out(fw)) return rc;
+  if (fu.staged || fv.staged || fw.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_pold_update(int nx, int ny, int nz, int mode, double* p, double* pold) {
+  if (int rc = ensure_device()) return rc;
+  if (!p || !pold) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (mode != 0 && mode != 1) return fail(FLUTAS_B200_ERR_ARG, "pold_update: mode must be 0 (pold = p) or 1 (p = pold + p)");
+  StencilGeom g = stencil_geom(nx, ny, nz, 1);
+  const size_t pcount = (size_t)g.sp1 * g.sp2 * (nz + 2);
+  FieldRef fp, fo;
+  if (int rc = stage_in(fp, 0, p, pcount, true)) return rc;
+  if (int rc = stage_in(fo, 1, pold, pcount, true)) return rc;
+  dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  pold_update_kernel<<<grd, blk, 0, g_stream>>>(g, mode, fp.dev, fo.dev);
+  LAUNCHED();
+  if (mode == 0) { if (int rc = stage_out(fo)) return rc; }
+  else { if (int rc = stage_out(fp)) return rc; }
+  if (fp.staged || fo.staged) CK(cudaStreamSynchronize(g_stream));
   return FLUTAS_B200_OK;
 }
 

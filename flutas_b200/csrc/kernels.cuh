@@ -327,6 +327,59 @@ __global__ void __launch_bounds__(256) correc_kernel(StencilGeom g, double facto
   w[c] = __dsub_rn(w[c], __dmul_rn(__dmul_rn(__dmul_rn(dt, dzci[k]), __dsub_rn(p[q + g.sp1 * g.sp2], pc)), rho0i));
 }
 
+// source.f90:311-346 (pres_sp_src): u += f_t12*( -(pold(ip)-pold(i))*dxi )*rho0i, left to right, no FMA contraction
+__global__ void __launch_bounds__(256) pres_sp_src_kernel(StencilGeom g, double f_t12, double dxi, double dyi,
+                                                          const double* __restrict__ dzci, double rho0i,
+                                                          const double* __restrict__ pold, double* __restrict__ u,
+                                                          double* __restrict__ v, double* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k), q = pidx(g, i, j, k);
+  const double pc = pold[q];
+  u[c] = __dadd_rn(u[c], __dmul_rn(__dmul_rn(f_t12, -__dmul_rn(__dsub_rn(pold[q + 1], pc), dxi)), rho0i));
+  v[c] = __dadd_rn(v[c], __dmul_rn(__dmul_rn(f_t12, -__dmul_rn(__dsub_rn(pold[q + g.sp1], pc), dyi)), rho0i));
+  w[c] = __dadd_rn(w[c], __dmul_rn(__dmul_rn(f_t12, -__dmul_rn(__dsub_rn(pold[q + g.sp1 * g.sp2], pc), dzci[k])), rho0i));
+}
+
+// source.f90:247-309 (pres_tw_src), _CONSTANT_COEFFS_POISSON branch :288-293
+__global__ void __launch_bounds__(256) pres_tw_src_kernel(StencilGeom g, double dxi, double dyi, const double* __restrict__ dzci,
+                                                          double rho0i, double f_t12, double f1, double f2,
+                                                          const double* __restrict__ p, const double* __restrict__ pold,
+                                                          const double* __restrict__ rho, double* __restrict__ u,
+                                                          double* __restrict__ v, double* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k), q = pidx(g, i, j, k);
+  const long qs[3] = {q + 1, q + g.sp1, q + (long)g.sp1 * g.sp2};
+  const double dl[3] = {dxi, dyi, dzci[k]};
+  double* vel[3] = {u, v, w};
+  const double pc = p[q], rc = rho[q];
+  const double e = __dsub_rn(__dmul_rn(f1, pc), __dmul_rn(f2, pold[q]));
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double rhoi = __ddiv_rn(1.0, __dmul_rn(0.5, __dadd_rn(rho[qs[d]], rc)));
+    const double A = __dmul_rn(-__dmul_rn(__dsub_rn(p[qs[d]], pc), dl[d]), rho0i);
+    const double en = __dsub_rn(__dmul_rn(f1, p[qs[d]]), __dmul_rn(f2, pold[qs[d]]));
+    const double B = __dmul_rn(__dmul_rn(__dsub_rn(rhoi, rho0i), __dsub_rn(en, e)), dl[d]);
+    vel[d][c] = __dadd_rn(vel[d][c], __dmul_rn(f_t12, __dsub_rn(A, B)));
+  }
+}
+
+// main__single_phase.f90:693-699 (mode 0: pold = p) and :734-740 (mode 1: p = pold + p), interior only
+__global__ void __launch_bounds__(256) pold_update_kernel(StencilGeom g, int mode, double* __restrict__ p, double* __restrict__ pold) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long q = pidx(g, i, j, k);
+  if (mode == 0) pold[q] = p[q];
+  else p[q] = __dadd_rn(pold[q], p[q]);
+}
+
 // chkdiv.f90:46-58: per-block partial (sum, max|div|), finished by chkdiv_final_kernel (deterministic)
 __global__ void __launch_bounds__(256) chkdiv_kernel(StencilGeom g, double dxi, double dyi,
                                                      const double* __restrict__ dzfi, const double* __restrict__ u,

@@ -55,6 +55,19 @@ module mod_flutas_b200
       import; integer(c_int), value :: nx,ny,nz,nh_d,nh_u; real(c_double), value :: dxi,dyi,dzi
       type(c_ptr), value :: dzfi,u,v,w; real(c_double), intent(out) :: divtot,divmax
     end function
+    integer(c_int) function flutas_b200_pres_sp_src(nx,ny,nz,f_t12,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,pold,u,v,w) &
+                            bind(C,name='flutas_b200_pres_sp_src')
+      import; integer(c_int), value :: nx,ny,nz,nh_d,nh_u; real(c_double), value :: f_t12,dxi,dyi,dzi,rho0i
+      type(c_ptr), value :: dzci,pold,u,v,w
+    end function
+    integer(c_int) function flutas_b200_pres_tw_src(nx,ny,nz,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,f_t12,f_t12_o,p,pold,rho,u,v,w) &
+                            bind(C,name='flutas_b200_pres_tw_src')
+      import; integer(c_int), value :: nx,ny,nz,nh_d,nh_u; real(c_double), value :: dxi,dyi,dzi,rho0i,f_t12,f_t12_o
+      type(c_ptr), value :: dzci,p,pold,rho,u,v,w
+    end function
+    integer(c_int) function flutas_b200_pold_update(nx,ny,nz,mode,p,pold) bind(C,name='flutas_b200_pold_update')
+      import; integer(c_int), value :: nx,ny,nz,mode; type(c_ptr), value :: p,pold
+    end function
     integer(c_int) function flutas_b200_boundp(cbc,n,bc,nh_d,nh_p,dl,dzc,dzf,p) bind(C,name='flutas_b200_boundp')
       import; character(kind=c_char), intent(in) :: cbc(6); integer(c_int), intent(in) :: n(3)
       real(c_double), intent(in) :: bc(6),dl(3); integer(c_int), value :: nh_d,nh_p
@@ -234,3 +247,41 @@ module mod_bound_b200
                                        c_loc(dzc),c_loc(dzf),c_loc(p)),'boundp')
   end subroutine boundp
 end module mod_bound_b200
+
+!
+! pressure-gradient source terms of the predictor, same signatures as src/source.f90:247,311 (constant-coefficient
+! Poisson build), and the two pressure bookkeeping loops of main__single_phase.f90:693-699 / :734-740 as
+!   call pold_update(n,0,p,pold)   ! pold = p        call pold_update(n,1,p,pold)   ! p = pold + p
+!
+module mod_source_b200
+  use, intrinsic :: iso_c_binding
+  use mod_flutas_b200
+  implicit none
+  private
+  public :: pres_sp_src,pres_tw_src,pold_update
+  contains
+  subroutine pres_sp_src(nx,ny,nz,f_t12,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,pold,u,v,w)
+    integer       , intent(in   )                                     :: nx,ny,nz,nh_d,nh_u
+    real(c_double), intent(in   )                                     :: f_t12,dxi,dyi,dzi,rho0i
+    real(c_double), intent(in   ), dimension(1-nh_d:), target         :: dzci
+    real(c_double), intent(in   ), dimension(0:,0:,0:), target        :: pold
+    real(c_double), intent(inout), dimension(1-nh_u:,1-nh_u:,1-nh_u:), target :: u,v,w
+    call b200_check(flutas_b200_pres_sp_src(nx,ny,nz,f_t12,dxi,dyi,dzi,nh_d,nh_u,c_loc(dzci),rho0i, &
+                                            c_loc(pold),c_loc(u),c_loc(v),c_loc(w)),'pres_sp_src')
+  end subroutine pres_sp_src
+  subroutine pres_tw_src(nx,ny,nz,dxi,dyi,dzi,nh_d,nh_u,dzci,rho0i,f_t12,f_t12_o,p,pold,rho,u,v,w)
+    integer       , intent(in   )                                     :: nx,ny,nz,nh_d,nh_u
+    real(c_double), intent(in   )                                     :: dxi,dyi,dzi,rho0i,f_t12,f_t12_o
+    real(c_double), intent(in   ), dimension(1-nh_d:), target         :: dzci
+    real(c_double), intent(in   ), dimension(0:,0:,0:), target        :: p,pold,rho
+    real(c_double), intent(inout), dimension(1-nh_u:,1-nh_u:,1-nh_u:), target :: u,v,w
+    call b200_check(flutas_b200_pres_tw_src(nx,ny,nz,dxi,dyi,dzi,nh_d,nh_u,c_loc(dzci),rho0i,f_t12,f_t12_o, &
+                                            c_loc(p),c_loc(pold),c_loc(rho),c_loc(u),c_loc(v),c_loc(w)),'pres_tw_src')
+  end subroutine pres_tw_src
+  subroutine pold_update(n,mode,p,pold)
+    integer       , intent(in   ), dimension(3)                 :: n
+    integer       , intent(in   )                               :: mode
+    real(c_double), intent(inout), dimension(0:,0:,0:), target  :: p,pold
+    call b200_check(flutas_b200_pold_update(n(1),n(2),n(3),mode,c_loc(p),c_loc(pold)),'pold_update')
+  end subroutine pold_update
+end module mod_source_b200

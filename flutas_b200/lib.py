@@ -43,6 +43,9 @@ def load():
     L.flutas_b200_correc.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp, vp]
     L.flutas_b200_chkdiv.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] * 4 + [_dp, _dp]
     L.flutas_b200_boundp.argtypes = [cc, ip, _dp, ci, ci, _dp, vp, vp, vp]
+    L.flutas_b200_pres_sp_src.argtypes = [ci] * 3 + [cd] * 4 + [ci] * 2 + [vp, cd, vp, vp, vp, vp]
+    L.flutas_b200_pres_tw_src.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] + [cd] * 3 + [vp] * 6
+    L.flutas_b200_pold_update.argtypes = [ci] * 4 + [vp, vp]
     L.flutas_b200_set_halo_exchange.argtypes = [vp, vp]
     L.flutas_b200_set_alltoall.argtypes = [vp, vp]
     L.flutas_b200_p2p_handle_bytes.restype = C.c_size_t
@@ -72,4 +75,5 @@ EXPORTS = [
     "flutas_b200_profile_stage_name", "flutas_b200_profile_read", "flutas_b200_set_alltoall",
     "flutas_b200_p2p_handle_bytes", "flutas_b200_p2p_export", "flutas_b200_p2p_attach", "flutas_b200_p2p_errors",
     "flutas_b200_solver_slab", "flutas_b200_boundp", "flutas_b200_set_halo_exchange",
+    "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src", "flutas_b200_pold_update",
 ]

@@ -118,6 +118,22 @@ int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
                        const double *dzci, double dt, double rho0, const double *p, double *u, double *v,
                        double *w, const double *rho);
 
+/* pres_sp_src, src/source.f90:311-346 (single phase): predictor pressure-gradient term from the OLD pressure,
+ * u += f_t12*( -(pold(i+1)-pold(i))*dxi )*rho0i (and v, w); called at main__single_phase.f90 before the solve. */
+int flutas_b200_pres_sp_src(int nx, int ny, int nz, double f_t12, double dxi, double dyi, double dzi, int nh_d,
+                            int nh_u, const double *dzci, double rho0i, const double *pold, double *u, double *v,
+                            double *w);
+
+/* pres_tw_src, src/source.f90:247-309 (two phase), _CONSTANT_COEFFS_POISSON branch (:288-293): split pressure
+ * gradient with the extrapolated pressure (1 + f_t12/f_t12_o) p - (f_t12/f_t12_o) pold.  rho(0:,0:,0:) as p. */
+int flutas_b200_pres_tw_src(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u,
+                            const double *dzci, double rho0i, double f_t12, double f_t12_o, const double *p,
+                            const double *pold, const double *rho, double *u, double *v, double *w);
+
+/* Pressure bookkeeping loops of the RK sub-step (interior of the halo-1 arrays, halos untouched):
+ * mode 0: pold = p (src/apps/single_phase/main__single_phase.f90:693-699); mode 1: p = pold + p (:734-740). */
+int flutas_b200_pold_update(int nx, int ny, int nz, int mode, double *p, double *pold);
+
 /* chkdiv, src/chkdiv.f90:18-69.  Returns this rank's divtot / divmax (the caller all-reduces across
  * ranks exactly where the reference calls MPI_ALLREDUCE, :64-65).  Synchronous. */
 int flutas_b200_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u,

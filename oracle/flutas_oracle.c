@@ -15,6 +15,8 @@
  *   oracle_solver_cpu    src/solver_cpu.f90:20-115 (one rank: the 2DECOMP transposes are identities)
  *   gaussel / gaussel_periodic / dgtsv_homebrewed  src/solver_cpu.f90:117-223 (exact operation order)
  *   oracle_correc        src/correc.f90:16-81      (_CONSTANT_COEFFS_POISSON branch)
+ *   oracle_pres_sp_src   src/source.f90:311-346    oracle_pres_tw_src  src/source.f90:247-309 (constant-coefficient branch)
+ *   oracle_pold_update   src/apps/single_phase/main__single_phase.f90:693-699, 734-740
  *   oracle_chkdiv        src/chkdiv.f90:18-69
  *   oracle_initgrid      src/initgrid.f90:17-118   (two-end tanh clustering)
  *
@@ -521,6 +523,65 @@ void oracle_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dzi, i
         tot += div;
       }
   *divtot = tot; *divmax = mx;
+}
+
+/* src/source.f90:311-346 (single phase): the predictor's pressure-gradient term from the OLD pressure.
+ *   u = u + f_t12*( - ( pold(ip)-pold(i) )*dxi )*rho0i      evaluated left to right as written */
+void oracle_pres_sp_src(int nx, int ny, int nz, double f_t12, double dxi, double dyi, double dzi, int nh_d, int nh_u,
+                        const double *dzci_, double rho0i, const double *pold, double *u, double *v, double *w) {
+  (void)dzi;
+  const long su1 = nx + 2 * nh_u, su2 = ny + 2 * nh_u, sp1 = nx + 2, sp2 = ny + 2;
+  const double *dzci = dzci_ + (nh_d - 1);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= nz; ++k)
+    for (int j = 1; j <= ny; ++j)
+      for (int i = 1; i <= nx; ++i) {
+        const double pc = pold[PIDX(i, j, k)];
+        u[UIDX(i, j, k)] = u[UIDX(i, j, k)] + f_t12 * (-((pold[PIDX(i + 1, j, k)] - pc) * dxi)) * rho0i;
+        v[UIDX(i, j, k)] = v[UIDX(i, j, k)] + f_t12 * (-((pold[PIDX(i, j + 1, k)] - pc) * dyi)) * rho0i;
+        w[UIDX(i, j, k)] = w[UIDX(i, j, k)] + f_t12 * (-((pold[PIDX(i, j, k + 1)] - pc) * dzci[k])) * rho0i;
+      }
+}
+
+/* src/source.f90:247-309 (two phase), _CONSTANT_COEFFS_POISSON branch (:288-293): split pressure gradient with the
+ * extrapolated pressure f1*p - f2*pold, f1 = 1 + f_t12/f_t12_o, f2 = f_t12/f_t12_o (:266-269).
+ * rho(0:,0:,0:) has the same halo-1 layout as p. */
+void oracle_pres_tw_src(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u,
+                        const double *dzci_, double rho0i, double f_t12, double f_t12_o, const double *p,
+                        const double *pold, const double *rho, double *u, double *v, double *w) {
+  (void)dzi;
+  const long su1 = nx + 2 * nh_u, su2 = ny + 2 * nh_u, sp1 = nx + 2, sp2 = ny + 2;
+  const double *dzci = dzci_ + (nh_d - 1);
+  const double f1 = 1.0 + (f_t12 / f_t12_o), f2 = (f_t12 / f_t12_o);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= nz; ++k)
+    for (int j = 1; j <= ny; ++j)
+      for (int i = 1; i <= nx; ++i) {
+        const long c = PIDX(i, j, k), cx = PIDX(i + 1, j, k), cy = PIDX(i, j + 1, k), cz = PIDX(i, j, k + 1);
+        const double rhoxi = 1.0 / (0.5 * (rho[cx] + rho[c]));
+        const double rhoyi = 1.0 / (0.5 * (rho[cy] + rho[c]));
+        const double rhozi = 1.0 / (0.5 * (rho[cz] + rho[c]));
+        const double e = f1 * p[c] - f2 * pold[c];
+        u[UIDX(i, j, k)] = u[UIDX(i, j, k)] + f_t12 * ((-((p[cx] - p[c]) * dxi)) * rho0i -
+                                                      (rhoxi - rho0i) * ((f1 * p[cx] - f2 * pold[cx]) - e) * dxi);
+        v[UIDX(i, j, k)] = v[UIDX(i, j, k)] + f_t12 * ((-((p[cy] - p[c]) * dyi)) * rho0i -
+                                                      (rhoyi - rho0i) * ((f1 * p[cy] - f2 * pold[cy]) - e) * dyi);
+        w[UIDX(i, j, k)] = w[UIDX(i, j, k)] + f_t12 * ((-((p[cz] - p[c]) * dzci[k])) * rho0i -
+                                                      (rhozi - rho0i) * ((f1 * p[cz] - f2 * pold[cz]) - e) * dzci[k]);
+      }
+}
+
+/* pressure bookkeeping around the solve, interior only (halos untouched):
+ * mode 0: pold = p          (src/apps/single_phase/main__single_phase.f90:693-699)
+ * mode 1: p = pold + p      (:734-740) */
+void oracle_pold_update(int nx, int ny, int nz, int mode, double *p, double *pold) {
+  const long sp1 = nx + 2, sp2 = ny + 2;
+  for (int k = 1; k <= nz; ++k)
+    for (int j = 1; j <= ny; ++j)
+      for (int i = 1; i <= nx; ++i) {
+        if (mode == 0) pold[PIDX(i, j, k)] = p[PIDX(i, j, k)];
+        else p[PIDX(i, j, k)] = pold[PIDX(i, j, k)] + p[PIDX(i, j, k)];
+      }
 }
 
 int oracle_num_threads(void) {

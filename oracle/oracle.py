@@ -169,6 +169,26 @@ def correc(n, nh_d, nh_u, dli, dzci, dt, rho0, p, u, v, w):
                         _p(p), _p(u), _p(v), _p(w))
 
 
+def pres_sp_src(n, f_t12, dli, nh_d, nh_u, dzci, rho0i, pold, u, v, w):
+    L = lib()
+    L.oracle_pres_sp_src.argtypes = [C.c_int] * 3 + [C.c_double] * 4 + [C.c_int] * 2 + [_dp, C.c_double, _dp, _dp, _dp, _dp]
+    L.oracle_pres_sp_src(n[0], n[1], n[2], f_t12, dli[0], dli[1], dli[2], nh_d, nh_u, _p(dzci), rho0i, _p(pold), _p(u), _p(v), _p(w))
+
+
+def pres_tw_src(n, dli, nh_d, nh_u, dzci, rho0i, f_t12, f_t12_o, p, pold, rho, u, v, w):
+    L = lib()
+    L.oracle_pres_tw_src.argtypes = ([C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2 + [_dp] + [C.c_double] * 3 +
+                                     [_dp] * 6)
+    L.oracle_pres_tw_src(n[0], n[1], n[2], dli[0], dli[1], dli[2], nh_d, nh_u, _p(dzci), rho0i, f_t12, f_t12_o,
+                         _p(p), _p(pold), _p(rho), _p(u), _p(v), _p(w))
+
+
+def pold_update(n, mode, p, pold):
+    L = lib()
+    L.oracle_pold_update.argtypes = [C.c_int] * 4 + [_dp, _dp]
+    L.oracle_pold_update(n[0], n[1], n[2], mode, _p(p), _p(pold))
+
+
 def chkdiv(n, dli, nh_d, nh_u, dzfi, u, v, w):
     tot, mx = C.c_double(), C.c_double()
     lib().oracle_chkdiv(n[0], n[1], n[2], dli[0], dli[1], dli[2], nh_d, nh_u, _p(dzfi), _p(u), _p(v), _p(w),

@@ -3,12 +3,9 @@
 mkdir -p gpurun_out
 : > gpurun_out/ab.log
 run() { W=$1; tag=$2; shift 2; echo "== $W $tag" >> gpurun_out/ab.log; env "$@" timeout 300 python bench.py --solver-only --steps 10 --warmup 3 --workload $W 2>&1 | tail -1 >> gpurun_out/ab.log; }
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "$(tail -1 gpurun_out/pytest_gpu.log)"
-FLUTAS_B200_THOMAS_UNI=0 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_nouni.log 2>&1; echo "no-uni: $(tail -1 gpurun_out/pytest_gpu_nouni.log)"
-for W in ${WORKLOADS:-C2 NS C3}; do
+for W in ${WORKLOADS:-NS C5w1}; do
   run $W default X=1
-  run $W gen-tma FLUTAS_B200_THOMAS_UNI=0
-  run $W gen-cpasync FLUTAS_B200_THOMAS_UNI=0 FLUTAS_B200_THOMAS_TMA=0
+  run $W ywide FLUTAS_B200_YWIDE=1
 done
 python - <<'PY'
 import json
