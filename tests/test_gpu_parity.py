@@ -188,3 +188,76 @@ def test_multi_gpu_slab_solver(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0 and "SLAB_OK" in out.stdout
+
+
+FULL_SIZE = [
+    ("C2", (512, 512, 512), ("PP", "PP", "PP"), (2 * np.pi,) * 3),
+    ("C3", (1024, 512, 512), ("PP", "PP", "NN"), (6.0, 3.0, 1.0)),
+    ("C5w1-half", (1024, 512, 512), ("NN", "NN", "NN"), (2.0, 1.0, 1.0)),
+]
+
+
+@pytest.mark.parametrize("name,ng,cbc,lengths", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_residual_and_linearity(name, ng, cbc, lengths):
+    """BASELINE-sized grids, where the CPU oracle would take minutes: size-independent properties evaluated on the
+    device -- (i) the solution satisfies the discrete 7-point operator the solver inverts (second differences with the
+    reference's ghost-cell closures in x,y; the tridiagonal a,b,c of initsolver.f90:188-246 in z), (ii) linearity."""
+    import torch
+    case = Case(ng, cbc, lengths, gr=0.0, seed=77)
+    s = case.setup
+    n1, n2, n3 = ng
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    dev = torch.device("cuda")
+
+    def rhs():
+        r = torch.rand((n3, n2, n1), dtype=torch.float64, device=dev, generator=g) - 0.5      # [k][j][i] = Fortran (i,j,k)
+        return r - r.mean()                                  # compatible with the singular (all-Neumann/periodic) operator
+
+    def solve(r):
+        p = torch.zeros((n3 + 2, n2 + 2, n1 + 2), dtype=torch.float64, device=dev)
+        p[1:-1, 1:-1, 1:-1] = r
+        api.solver(ng, pl, nf, s.lambdaxy, s.a, s.b, s.c, cbc[2], "ccc", p)
+        torch.cuda.synchronize()
+        return p[1:-1, 1:-1, 1:-1].clone()
+
+    def second_diff(x, dim, bc, dli2):
+        # cell-centred ghost closures (bound.f90:247-268): P wrap, N ghost = interior, D ghost = -interior
+        lo = torch.roll(x, 1, dim)
+        hi = torch.roll(x, -1, dim)
+        first = [slice(None)] * 3
+        last = [slice(None)] * 3
+        first[dim], last[dim] = slice(0, 1), slice(-1, None)
+        if bc != "PP":
+            sgn = 1.0 if bc == "NN" else -1.0
+            lo[tuple(first)] = sgn * x[tuple(first)]
+            hi[tuple(last)] = sgn * x[tuple(last)]
+        return (lo - 2.0 * x + hi) * dli2
+
+    def apply_operator(x):
+        out = second_diff(x, 2, cbc[0], s.dli[0] ** 2)
+        out += second_diff(x, 1, cbc[1], s.dli[1] ** 2)
+        a = torch.from_numpy(np.ascontiguousarray(s.a)).to(dev)[:, None, None]
+        b = torch.from_numpy(np.ascontiguousarray(s.b)).to(dev)[:, None, None]
+        c = torch.from_numpy(np.ascontiguousarray(s.c)).to(dev)[:, None, None]
+        lo = torch.roll(x, 1, 0)
+        hi = torch.roll(x, -1, 0)
+        if cbc[2] != "PP":                                   # the wall closures are folded into b (initsolver.f90:228-236)
+            lo[0] = 0.0
+            hi[-1] = 0.0
+        out += a * lo + b * x + c * hi
+        return out
+
+    pl, nf = api.fftini(ng, ng, (cbc[0], cbc[1]))
+    r1, r2 = rhs(), rhs()
+    x1 = solve(r1)
+    res = float((apply_operator(x1) - r1).abs().max() / r1.abs().max())
+    assert res <= 1e-9, res
+    x2 = solve(r2)
+    x3 = solve(2.0 * r1 - 3.0 * r2)
+    comb = 2.0 * x1 - 3.0 * x2
+    d = (x3 - x3.mean()) - (comb - comb.mean())
+    lin = float(d.abs().max() / comb.abs().max())
+    assert lin <= 1e-11, lin
+    print("%s %s: residual %.2e, linearity %.2e" % (name, ng, res, lin))
+    api.fftend(pl)
