@@ -139,6 +139,16 @@ def pold_update(nx, ny, nz, mode, p, pold):
     _lib.check(_lib.load().flutas_b200_pold_update(nx, ny, nz, mode, _ptr(p), _ptr(pold)))
 
 
+def load(io, filename, n, fld, ng=None, start=(0, 0, 0), nh=0):
+    """load(io,filename,n,fld), src/load.f90:21: read ('r') / write ('w') this rank's block of a raw FP64 restart file in
+    global column-major order.  ng defaults to n (single rank); start = 0-based global offset of the block; nh = halo
+    width of fld (numpy F-ordered array or CUDA tensor)."""
+    ng = tuple(n) if ng is None else tuple(ng)
+    _lib.check(_lib.load().flutas_b200_load(io.encode(), str(filename).encode(), (C.c_int * 3)(*ng), (C.c_int * 3)(*n),
+                                            (C.c_int * 3)(*start), nh, _ptr(fld)))
+    return fld
+
+
 def boundp(cbc, n, bc, nh_d, nh_p, dl, dzc, dzf, p):
     """boundp(cbc,n,bc,nh_d,nh_p,halo,dl,dzc,dzf,p), src/bound.f90:146 (the MPI `halo` datatypes have no counterpart).
     cbc: three 2-character strings; bc: (3,2) boundary values."""

@@ -2,6 +2,9 @@
 // launches for the FluTAS pressure-Poisson path on one B200 (the multi-GPU slab exchange lives in
 // exchange.cuh).  Build: see flutas_b200/build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <cstdarg>
@@ -1019,6 +1022,78 @@ int flutas_b200_pold_update(int nx, int ny, int nz, int mode, double* p, double*
   if (mode == 0) { if (int rc = stage_out(fo)) return rc; }
   else { if (int rc = stage_out(fp)) return rc; }
   if (fp.staged || fo.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+// load(io,filename,n,fld), src/load.f90:21-89: restart fields are headerless raw FP64 in GLOBAL column-major (ng1,ng2,ng3)
+// order, independent of the decomposition (each rank reads/writes its block through a subarray file view,
+// src/2decomp/io_write_var.f90:28-60).  Here: pread/pwrite of the block's x-rows (one contiguous run for a z-slab),
+// staged through host memory; `fld` may be a host or a device pointer with `nh` halo cells on every side.
+int flutas_b200_load(char io, const char* filename, const int ng[3], const int n[3], const int start[3], int nh, double* fld) {
+  if (!filename || !ng || !n || !start || !fld) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (io != 'r' && io != 'w') return fail(FLUTAS_B200_ERR_ARG, "load: io must be 'r' or 'w'");
+  if (nh < 0) return fail(FLUTAS_B200_ERR_ARG, "load: nh must be >= 0");
+  for (int d = 0; d < 3; ++d)
+    if (n[d] < 1 || start[d] < 0 || start[d] + n[d] > ng[d]) return fail(FLUTAS_B200_ERR_ARG, "load: block outside the global grid");
+  const long long good = 8LL * ng[0] * ng[1] * ng[2];
+  const size_t count = (size_t)n[0] * n[1] * n[2];
+  const bool dev = on_device(fld);
+  if (dev) { if (int rc = ensure_device()) return rc; }
+  std::vector<double> dense;
+  double* blk = fld;                                        // dense (n1,n2,n3) image of the block in host memory
+  if (dev || nh > 0) { dense.resize(count); blk = dense.data(); }
+  const size_t s1 = (size_t)n[0] + 2 * nh, s2 = (size_t)n[1] + 2 * nh;
+  auto halo_copy = [&](bool to_fld) -> int {                // dense block <-> interior of the (possibly halo'd, possibly device) fld
+    if (!dev && nh == 0) return 0;
+    cudaMemcpy3DParms pm = {};
+    cudaPitchedPtr pd = make_cudaPitchedPtr(blk, (size_t)n[0] * 8, (size_t)n[0], (size_t)n[1]);
+    cudaPitchedPtr pf = make_cudaPitchedPtr(fld, s1 * 8, s1, s2);
+    pm.extent = make_cudaExtent((size_t)n[0] * 8, (size_t)n[1], (size_t)n[2]);
+    pm.kind = cudaMemcpyDefault;
+    if (to_fld) { pm.srcPtr = pd; pm.dstPtr = pf; pm.dstPos = make_cudaPos((size_t)nh * 8, (size_t)nh, (size_t)nh); }
+    else { pm.srcPtr = pf; pm.srcPos = make_cudaPos((size_t)nh * 8, (size_t)nh, (size_t)nh); pm.dstPtr = pd; }
+    if (dev) { CK(cudaMemcpy3D(&pm)); return 0; }
+    for (int k = 0; k < n[2]; ++k)                          // host array with halos: no CUDA call needed
+      for (int j = 0; j < n[1]; ++j) {
+        double* f = fld + (size_t)nh + s1 * ((size_t)(j + nh) + s2 * (size_t)(k + nh));
+        double* b = blk + (size_t)n[0] * ((size_t)j + (size_t)n[1] * k);
+        if (to_fld) memcpy(f, b, (size_t)n[0] * 8); else memcpy(b, f, (size_t)n[0] * 8);
+      }
+    return 0;
+  };
+  int fd = -1;
+  if (io == 'r') {
+    fd = open(filename, O_RDONLY);
+    if (fd < 0) return fail(FLUTAS_B200_ERR_ARG, "load: the restarting field %s does not exist", filename);   // load.f90:40-46
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (long long)sb.st_size != good) {                                                 // load.f90:52-66
+      const long long have = (long long)sb.st_size;
+      close(fd);
+      return fail(FLUTAS_B200_ERR_ARG, "load: checkpoint file %s has incorrect size (expected %lld, actual %lld)", filename, good, have);
+    }
+  } else {
+    if (dev) CK(cudaStreamSynchronize(g_stream));
+    if (int rc = halo_copy(false)) return rc;
+    fd = open(filename, O_CREAT | O_WRONLY, 0644);
+    if (fd < 0) return fail(FLUTAS_B200_ERR_ARG, "load: cannot create %s", filename);
+    if (ftruncate(fd, (off_t)good) != 0) { close(fd); return fail(FLUTAS_B200_ERR_ARG, "load: cannot size %s", filename); }
+  }
+  const bool rows_contiguous = (n[0] == ng[0]) && (n[1] == ng[1]);
+  const size_t run = rows_contiguous ? count : (size_t)n[0];           // doubles per contiguous file run
+  const size_t nruns = count / run;
+  for (size_t r = 0; r < nruns; ++r) {
+    const size_t j = rows_contiguous ? 0 : r % n[1], k = rows_contiguous ? 0 : r / n[1];
+    const off_t off = 8 * ((off_t)start[0] + (off_t)ng[0] * ((off_t)(start[1] + j) + (off_t)ng[1] * (off_t)(start[2] + k)));
+    char* q = reinterpret_cast<char*>(blk + r * run);
+    size_t left = run * 8, done_b = 0;
+    while (left) {
+      const ssize_t got = (io == 'r') ? pread(fd, q + done_b, left, off + (off_t)done_b) : pwrite(fd, q + done_b, left, off + (off_t)done_b);
+      if (got <= 0) { close(fd); return fail(FLUTAS_B200_ERR_ARG, "load: short %s on %s", io == 'r' ? "read" : "write", filename); }
+      left -= (size_t)got; done_b += (size_t)got;
+    }
+  }
+  close(fd);
+  if (io == 'r') { if (int rc = halo_copy(true)) return rc; }
   return FLUTAS_B200_OK;
 }
 

@@ -65,6 +65,10 @@ module mod_flutas_b200
       import; integer(c_int), value :: nx,ny,nz,nh_d,nh_u; real(c_double), value :: dxi,dyi,dzi,rho0i,f_t12,f_t12_o
       type(c_ptr), value :: dzci,p,pold,rho,u,v,w
     end function
+    integer(c_int) function flutas_b200_load(io,filename,ng,n,start,nh,fld) bind(C,name='flutas_b200_load')
+      import; character(kind=c_char), value :: io; character(kind=c_char), intent(in) :: filename(*)
+      integer(c_int), intent(in) :: ng(3),n(3),start(3); integer(c_int), value :: nh; type(c_ptr), value :: fld
+    end function
     integer(c_int) function flutas_b200_pold_update(nx,ny,nz,mode,p,pold) bind(C,name='flutas_b200_pold_update')
       import; integer(c_int), value :: nx,ny,nz,mode; type(c_ptr), value :: p,pold
     end function
@@ -285,3 +289,25 @@ module mod_source_b200
     call b200_check(flutas_b200_pold_update(n(1),n(2),n(3),mode,c_loc(p),c_loc(pold)),'pold_update')
   end subroutine pold_update
 end module mod_source_b200
+
+!
+! restart files: same signature as src/load.f90:21 (decomposition from 2DECOMP's xstart, global size from mod_param)
+!
+module mod_load_b200
+  use, intrinsic :: iso_c_binding
+  use mod_flutas_b200
+  use mod_param , only: ng
+  use decomp_2d , only: xstart
+  implicit none
+  private
+  public :: load
+  contains
+  subroutine load(io,filename,n,fld)
+    character(len=1), intent(in   )                                    :: io
+    character(len=*), intent(in   )                                    :: filename
+    integer         , intent(in   ), dimension(3)                      :: n
+    real(c_double)  , intent(inout), dimension(n(1),n(2),n(3)), target :: fld
+    call b200_check(flutas_b200_load(io,trim(filename)//c_null_char,int(ng,c_int),int(n,c_int),int(xstart-1,c_int), &
+                                     0_c_int,c_loc(fld)),'load')
+  end subroutine load
+end module mod_load_b200

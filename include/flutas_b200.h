@@ -140,6 +140,14 @@ int flutas_b200_chkdiv(int nx, int ny, int nz, double dxi, double dyi, double dz
                        const double *dzfi, const double *u, const double *v, const double *w,
                        double *divtot, double *divmax);
 
+/* load(io,filename,n,fld), src/load.f90:21-89: restart files (fldp.bin, fldu.bin, ...) are headerless raw FP64 in GLOBAL
+ * column-major (ng1,ng2,ng3) order whatever the decomposition.  io = 'r' | 'w'; n[3] = this rank's block, start[3] its
+ * 0-based global offset (2DECOMP xstart-1); `fld` = host or device pointer to an array with `nh` halo cells per side
+ * (nh = 0: the reference's dense fld(n1,n2,n3)).  'r' fails if the file is missing or its size is not 8*ng1*ng2*ng3
+ * (the reference aborts, :40-66); 'w' sizes the file and writes the block (any rank order, no truncation race). */
+int flutas_b200_load(char io, const char *filename, const int ng[3], const int n[3], const int start[3], int nh,
+                     double *fld);
+
 /* boundp, src/bound.f90:146-225 (with set_bc :227-420 and updthalo :946-1110), halo width nh_p = 1:
  * ghost cells of a cell-centred scalar (p, pold) for the reference's _DECOMP_X layout.  Same step order as
  * the reference (y halo, z halo, x faces, y faces, z faces), so edges and corners are bit-identical.
