@@ -23,6 +23,10 @@ CONFIGS = {
                desc="Rayleigh-Benard 2048x2048x1024, DCT x,y + walls z"),
     "C5w1": dict(ng=(1024, 1024, 512), cbc=("NN", "NN", "NN"), l=(2.0, 2.0, 1.0), rho0=1.0, idx=5,
                  desc="Rayleigh-Benard weak-scaling unit 1024x1024x512 per GPU"),
+    # one eighth (a z-slab of 128 levels) of C5: the x / y transform kernels at N = 2048 on ONE GPU (kernel timing only;
+    # its z stage sees nz = 128 and says nothing about C5's)
+    "C5xy": dict(ng=(2048, 2048, 128), cbc=("NN", "NN", "NN"), l=(2.0, 2.0, 0.125), rho0=1.0, idx=5,
+                 desc="x/y stages of Rayleigh-Benard 2048x2048x1024 on one z-slab of 128 levels"),
     "NS": dict(ng=(1024, 1024, 1024), cbc=("PP", "PP", "NN"), l=(2 * np.pi, 2 * np.pi, 1.0), rho0=1.0, idx=6,
                desc="north-star 1024^3 channel"),
 }

@@ -19,6 +19,7 @@ inline bool y_wide_enabled() {
   if (env == -2) { const char* e = getenv("FLUTAS_B200_YWIDE"); env = e ? (e[0] == '0' ? 0 : 1) : -1; }
   return env >= 0 ? env == 1 : y_wide_request() == 1;
 }
+inline bool y_wide_forced_off() { const char* e = getenv("FLUTAS_B200_YWIDE"); return e && e[0] == '0'; }
 cudaError_t reg_run_x_fwd(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale, int nsm,
                           cudaStream_t st);
 cudaError_t reg_run_x_bwd(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale, int nsm,
