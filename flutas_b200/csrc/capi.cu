@@ -129,7 +129,7 @@ struct DevLinePlan {
   const std::vector<int>& mode() const { return use_reg ? hr.mode : h.mode; }
   int upload_reg() {
     size_t n = hr.wN.size() + hr.wQ.size();
-    for (int q = 0; q < RF_MAXPASS; ++q) n += hr.tw[q].size();
+    for (int q = 0; q < RF_MAXPASS; ++q) n += hr.tw[q].size() + hr.tw8[q].size();
     if (int rc = rtables.reserve((n + 1) * sizeof(cpx))) return rc;
     cpx* at = rtables.as<cpx>();
     r.N = hr.N; r.M = hr.M; r.kind = hr.kind;
@@ -137,6 +137,11 @@ struct DevLinePlan {
       r.tw[q] = at; r.tw_count[q] = (int)hr.tw[q].size();
       if (!hr.tw[q].empty()) CK(cudaMemcpy(at, hr.tw[q].data(), hr.tw[q].size() * sizeof(cpx), cudaMemcpyHostToDevice));
       at += hr.tw[q].size();
+    }
+    for (int q = 0; q < RF_MAXPASS; ++q) {
+      r.tw8[q] = hr.tw8[q].empty() ? nullptr : at;
+      if (!hr.tw8[q].empty()) CK(cudaMemcpy(at, hr.tw8[q].data(), hr.tw8[q].size() * sizeof(cpx), cudaMemcpyHostToDevice));
+      at += hr.tw8[q].size();
     }
     r.wN = at;
     CK(cudaMemcpy(at, hr.wN.data(), hr.wN.size() * sizeof(cpx), cudaMemcpyHostToDevice));

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "geom.cuh"
 #include "reg_fft.cuh"
@@ -23,15 +24,15 @@ namespace fb {
 // Tables staged in shared memory by every block: the pass twiddles (tw1, tw2), the split/merge twiddles wN[M] and,
 // for Makhoul (NN/DD) lines of length <= 1024, wQ[M+1].  All are indexed j + T u or k + (t-1) Ns, i.e. one run-time
 // base plus immediates (the v7 kernels fetched wN/wQ from global memory: 62 of their 94 LDG per thread and tile).
-template <int M, bool MK>
+template <class S, bool MK>
 struct RegTw {
-  using S = RegSched<M>;
-  static constexpr int n1 = (S::NP > 1) ? 15 * S::ns(1) : 0;
-  static constexpr int n2 = (S::NP > 2) ? 15 * S::ns(2) : 0;
+  static constexpr int M = S::M;
+  static constexpr int n1 = (S::NP > 1) ? (S::radix(1) - 1) * S::ns(1) : 0;
+  static constexpr int n2 = (S::NP > 2) ? (S::radix(2) - 1) * S::ns(2) : 0;
   static constexpr int nN = M;
   static constexpr bool QSM = MK && (M <= 512);
   static constexpr int nQ = QSM ? M + 1 : 0;
-  static constexpr int total = n1 + n2 + nN + nQ + (nQ & 1);     // cpx entries (16 bytes each)
+  static constexpr int total = n1 + n2 + nN + nQ + ((n1 + n2 + nQ) & 1);     // cpx entries (16 bytes each)
 };
 
 // exchange buffer of one x line: M slots of (re,im), one pad slot per 16 (scattered 16-slot strides -> all banks)
@@ -63,6 +64,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // puts the ceiling of plain stores above st.cs for 64-byte pieces (halves of a 128-byte line merge in L2 instead of
 // leaving it evict-first), but the transform kernels are not at that ceiling: measured on B200, 512^3 and 1024^3,
 // st.cs is 0-2 % faster than plain stores on every stage -> st.cs stays the default.
+// y lines of N = 1024 with 8 values per thread (YRegShape, RR = 8): 64 registers, 28 resident warps per SM instead of 16.
+// Measured on B200 (1024^3): y fwd 4.57 -> 4.35 ms, y inv 4.55 -> 4.52 ms; 1024x1024x512 NN: 2.36 -> 2.25, 2.51 -> 2.42 ms.
+// The ncu capture of this shape (profiles/r01_ncu_full_v10_y8_keys.txt) still shows mio_throttle (5.6 per issue) and
+// barrier (4.0) on top: the block-synchronous exchange phases arrive at the shared-memory pipe in bursts.
+#ifndef FB_Y8_DEFAULT
+#define FB_Y8_DEFAULT 1
+#endif
 #ifndef FB_STREAM_Y
 #define FB_STREAM_Y 1
 #endif
@@ -76,29 +84,29 @@ __device__ __forceinline__ void st_x2(double2* p, double2 v) { if (FB_STREAM_X) 
 // copies the tables to shared memory at `sm` in the order tw1 | tw2 | wN | wQ (offsets: RegTw).  The kernels form the
 // table pointers as plain local variables: handing them around inside a struct made nvcc 12.9 lose the shared
 // address space of one member (a generic load from the bare shared offset -> illegal address).
-template <int M, bool MK>
+template <class S, bool MK>
 __device__ __forceinline__ void reg_stage_tw(cpx* sm, const RegPlan& P, int tid, int nthr) {
-  using TW = RegTw<M, MK>;
+  using TW = RegTw<S, MK>;
   auto copy = [&](cpx* d, const cpx* g, int n) {
     const double2* g2 = reinterpret_cast<const double2*>(g);
     for (int q = tid; q < n; q += nthr) reinterpret_cast<double2*>(d)[q] = __ldg(g2 + q);
   };
-  copy(sm, P.tw[1], TW::n1);
-  copy(sm + TW::n1, P.tw[2], TW::n2);
+  copy(sm, S::R == 16 ? P.tw[1] : P.tw8[1], TW::n1);
+  copy(sm + TW::n1, S::R == 16 ? P.tw[2] : P.tw8[2], TW::n2);
   copy(sm + TW::n1 + TW::n2, P.wN, TW::nN);
   if (TW::QSM) copy(sm + TW::n1 + TW::n2 + TW::nN, P.wQ, TW::nQ);
 }
-#define FB_REG_TABLES(M, MK, smbase, P)                                                       \
+#define FB_REG_TABLES(S, MK, smbase, P)                                                       \
   const cpx* s_tw1 = reinterpret_cast<const cpx*>(smbase);                                     \
-  const cpx* s_tw2 = s_tw1 + RegTw<M, MK>::n1;                                                 \
-  const cpx* s_wN = s_tw2 + RegTw<M, MK>::n2;                                                  \
-  const cpx* s_wQ = RegTw<M, MK>::QSM ? (s_wN + RegTw<M, MK>::nN) : P.wQ;                      \
+  const cpx* s_tw2 = s_tw1 + RegTw<S, MK>::n1;                                                 \
+  const cpx* s_wN = s_tw2 + RegTw<S, MK>::n2;                                                  \
+  const cpx* s_wQ = RegTw<S, MK>::QSM ? (s_wN + RegTw<S, MK>::nN) : P.wQ;                      \
   const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
 
 template <int N, bool MK>
 constexpr size_t xfft_reg_smem() {
   constexpr int M = N / 2;
-  return (size_t)RegTw<M, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
+  return (size_t)RegTw<RegSched<M>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
 }
 
 template <int N, bool FWD, bool MK>
@@ -112,11 +120,11 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   constexpr int LG = GT / T;                          // lines per group
   constexpr int BUFL = M + M / 16;
   extern __shared__ double2 smem2[];
-  double2* bufs = smem2 + RegTw<M, MK>::total;
+  double2* bufs = smem2 + RegTw<S, MK>::total;
   const int tid = threadIdx.x;
-  reg_stage_tw<M, MK>(reinterpret_cast<cpx*>(smem2), P, tid, 256);
+  reg_stage_tw<S, MK>(reinterpret_cast<cpx*>(smem2), P, tid, 256);
   __syncthreads();
-  FB_REG_TABLES(M, MK, smem2, P)
+  FB_REG_TABLES(S, MK, smem2, P)
   const int gi = WARP ? (tid >> 5) : 0, tg = tid % GT;
   const int lw = tg / T, j = tg % T;
   const XLineBuf xb{bufs + (size_t)(gi * LG + lw) * BUFL};
@@ -195,7 +203,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
           lbuf[pa] = sa * re[u]; lbuf[pb] = sb * im[u];
         }
         sync();
-        reg_gather<M>(re, im, j, xb);
+        reg_gather<S>(re, im, j, xb);
         sync();
       } else {
 #pragma unroll
@@ -205,10 +213,10 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
           re[u] = s0 * ps[e0]; im[u] = s1 * ps[e1];
         }
       }
-      reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
-      reg_scatter_modes<M>(re, im, j, xb);
+      reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
+      reg_scatter_modes<S>(re, im, j, xb);
       sync();
-      reg_split<M, MK>(re, im, j, s_wN, s_wQ, xb);
+      reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
       if (live) {
         double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
 #pragma unroll
@@ -218,13 +226,13 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
 #pragma unroll
       for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = v.x; im[u] = v.y; }
-      reg_scatter_modes<M>(re, im, j, xb);
+      reg_scatter_modes<S>(re, im, j, xb);
       sync();
-      reg_merge<M, MK>(re, im, j, s_wN, s_wQ, xb);
+      reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
       sync();
-      reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
+      reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
       if (viabuf) {                                    // packed element m = slot m, then read back in natural order
-        reg_scatter_modes<M>(re, im, j, xb);
+        reg_scatter_modes<S>(re, im, j, xb);
         sync();
 #pragma unroll
         for (int u = 0; u < R; ++u) {
@@ -272,14 +280,17 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
 // ---- y lines ------------------------------------------------------------------------------------
 // WIDE: 512-thread blocks when a line needs >= 32 threads (N >= 1024), i.e. 16 lanes = 128-byte row pieces but one
 // block per SM; !WIDE: always 256 threads (8 lanes at N = 1024, two blocks per SM).
-template <int N, bool WIDE, bool MK>
+// RR = 8 (N = 1024 only): 64 threads per line at 8 values each -> 8 lanes in a 512-thread block at <= 64 registers, two
+// blocks = 32 warps per SM (twice the warps of the RR = 16 shape with the same shared-memory footprint and pass count).
+template <int N, bool WIDE, bool MK, int RR = 16>
 struct YRegShape {
-  static constexpr int T = RegSched<N / 2>::T;
-  static constexpr int NTMAX = (WIDE && T >= 32) ? 512 : 256;
+  using S = RegSched<N / 2, RR>;
+  static constexpr int T = S::T;
+  static constexpr int NTMAX = (RR == 8) ? 512 : (WIDE && T >= 32) ? 512 : 256;
   static constexpr int TB = (NTMAX / T > 32) ? 32 : NTMAX / T;
   static constexpr int NT = TB * T;
-  static constexpr int MINB = (NT > 256) ? 1 : 2;
-  static constexpr size_t smem = (size_t)RegTw<N / 2, MK>::total * sizeof(cpx) + (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
+  static constexpr int MINB = (RR == 8) ? 2 : (NT > 256) ? 1 : 2;
+  static constexpr size_t smem = (size_t)RegTw<S, MK>::total * sizeof(cpx) + (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
 };
 
 // element `c * stride` past p with a compile-time c: one IMAD.WIDE (32-bit stride times immediate plus 64-bit base)
@@ -293,20 +304,20 @@ __device__ __forceinline__ double* yrow(double* p, unsigned sbytes, int c) {
   return reinterpret_cast<double*>(c >= 0 ? q + (size_t)sbytes * (unsigned)c : q - (size_t)sbytes * (unsigned)(-c));
 }
 
-template <int N, bool FWD, bool WIDE, bool MK>
-__global__ void __launch_bounds__(YRegShape<N, WIDE, MK>::NT, YRegShape<N, WIDE, MK>::MINB)
+template <int N, bool FWD, bool WIDE, bool MK, int RR>
+__global__ void __launch_bounds__(YRegShape<N, WIDE, MK, RR>::NT, YRegShape<N, WIDE, MK, RR>::MINB)
 yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
   constexpr int M = N / 2;
-  using S = RegSched<M>;
-  using Y = YRegShape<N, WIDE, MK>;
-  using MR = MkRows<N>;
+  using S = RegSched<M, RR>;
+  using Y = YRegShape<N, WIDE, MK, RR>;
+  using MR = MkRows<N, RR>;
   constexpr int T = S::T, R = S::R, TB = Y::TB, NT = Y::NT;
   extern __shared__ double2 smem2[];
-  double2* buf = smem2 + RegTw<M, MK>::total;
+  double2* buf = smem2 + RegTw<S, MK>::total;
   const int tid = threadIdx.x;
-  reg_stage_tw<M, MK>(reinterpret_cast<cpx*>(smem2), P, tid, NT);
+  reg_stage_tw<S, MK>(reinterpret_cast<cpx*>(smem2), P, tid, NT);
   __syncthreads();
-  FB_REG_TABLES(M, MK, smem2, P)
+  FB_REG_TABLES(S, MK, smem2, P)
   const int lane = tid % TB, j = tid / TB;
   const YTileBuf<TB> xb{buf + lane};
   auto sync = [] { __syncthreads(); };
@@ -352,10 +363,10 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
           else { re[u] = sdd * *yrow(phi, pstride, MR::off0(u)); im[u] = sdd * *yrow(phi, pstride, MR::off1(u)); }
         }
       }
-      reg_fft_passes<M, -1>(re, im, j, tw, xb, sync);
-      reg_scatter_modes<M>(re, im, j, xb);
+      reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
+      reg_scatter_modes<S>(re, im, j, xb);
       sync();
-      reg_split<M, MK>(re, im, j, s_wN, s_wQ, xb);
+      reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
       if (live) {
         double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
@@ -370,11 +381,11 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
 #pragma unroll
         for (int u = 0; u < R; ++u) { re[u] = *yrow(ps, sstride, 2 * T * u); im[u] = *yrow(ps, sstride, 2 * T * u + 1); }
       }
-      reg_scatter_modes<M>(re, im, j, xb);
+      reg_scatter_modes<S>(re, im, j, xb);
       sync();
-      reg_merge<M, MK>(re, im, j, s_wN, s_wQ, xb);
+      reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
       sync();
-      reg_fft_passes<M, +1>(re, im, j, tw, xb, sync);
+      reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
       if (live) {
         if (!MK) {
           double* p0 = yrow(base, pstride, 2 * j);
@@ -426,10 +437,10 @@ inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs
                              : reg_launch_x1<N, FWD, true>(P, src, gs, dst, gd, scale, nsm, st);
 }
 
-template <int N, bool FWD, bool WIDE, bool MK>
+template <int N, bool FWD, bool WIDE, bool MK, int RR = 16>
 inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
-  using Y = YRegShape<N, WIDE, MK>;
-  auto kern = yfft_reg_kernel<N, FWD, WIDE, MK>;
+  using Y = YRegShape<N, WIDE, MK, RR>;
+  auto kern = yfft_reg_kernel<N, FWD, WIDE, MK, RR>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
@@ -451,6 +462,11 @@ template <int N, bool FWD>
 inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, bool wide,
                                 cudaStream_t st) {
   const bool mk = (P.kind != KIND_PP);
+  if constexpr (N == 1024) {                            // 8 values per thread (see YRegShape); FLUTAS_B200_Y8=0/1 overrides
+    static const int y8 = [] { const char* e = getenv("FLUTAS_B200_Y8"); return e ? atoi(e) : FB_Y8_DEFAULT; }();
+    if (y8 && !wide && P.tw8[1])
+      return mk ? reg_launch_y1<N, FWD, false, true, 8>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, false, false, 8>(P, W, n1, n3, sg, nsm, st);
+  }
   if (RegSched<N / 2>::T >= 32 && wide)
     return mk ? reg_launch_y1<N, FWD, true, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, true, false>(P, W, n1, n3, sg, nsm, st);
   return mk ? reg_launch_y1<N, FWD, false, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, false, false>(P, W, n1, n3, sg, nsm, st);

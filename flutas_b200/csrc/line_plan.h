@@ -86,20 +86,25 @@ namespace fb {
 struct HostRegPlan {
   int N = 0, M = 0, kind = 0;
   std::vector<cpx> tw[RF_MAXPASS];
+  std::vector<cpx> tw8[RF_MAXPASS];   // pass twiddles of the 8-values-per-thread schedule (M = 512 only)
   std::vector<cpx> wN, wQ;
   std::vector<int> mode;       // mode[r] : index into the reference's lambda array for spectral row r (0-based)
   bool ok = false;
 };
 
-template <int M>
-inline void fill_reg_twiddles(HostRegPlan& hp) {
-  using S = RegSched<M>;
+template <class S>
+inline void fill_sched_twiddles(std::vector<cpx>* tw) {
   for (int q = 1; q < S::NP; ++q) {
     const int r = S::radix(q), Ns = S::ns(q);
-    hp.tw[q].resize((size_t)(r - 1) * Ns);
+    tw[q].resize((size_t)(r - 1) * Ns);
     for (int t = 1; t < r; ++t)
-      for (int k = 0; k < Ns; ++k) hp.tw[q][(size_t)(t - 1) * Ns + k] = unit_root(2.0L * t * k, (long double)Ns * r);
+      for (int k = 0; k < Ns; ++k) tw[q][(size_t)(t - 1) * Ns + k] = unit_root(2.0L * t * k, (long double)Ns * r);
   }
+}
+template <int M>
+inline void fill_reg_twiddles(HostRegPlan& hp) {
+  fill_sched_twiddles<RegSched<M>>(hp.tw);
+  if (M == 512) fill_sched_twiddles<RegSched<512, 8>>(hp.tw8);
 }
 
 inline HostRegPlan make_reg_plan(int N, int kind) {

@@ -32,19 +32,25 @@ struct RegPlan {
   int N, M, kind;
   const cpx* tw[RF_MAXPASS];   // pass q > 0: tw[q][(t-1)*Ns + k] = exp(-2 pi i t k / (Ns r)),  t = 1..r-1, k = 0..Ns-1
   int tw_count[RF_MAXPASS];
+  const cpx* tw8[RF_MAXPASS];  // same tables for the 8-values-per-thread schedule (lengths served by it, else null)
   const cpx* wN;               // [M]    exp(-2 pi i k / N)
   const cpx* wQ;               // [M+1]  exp(-i pi k / (2N))      (NN/DD only)
 };
 
-// compile-time schedule for a complex length M (power of two, 16 <= M <= 2048)
-template <int M>
+// compile-time schedule for a complex length M (power of two, 16 <= M <= 2048): RR complex values per thread,
+// T = M / RR threads per line, one first pass of radix R0 <= RR followed by radix-RR passes.
+//   RR = 16 (default): M = 16: {16}; M <= 256: {M/16, 16}; else {M/256, 16, 16}
+//   RR = 8  (twice the threads at half the registers; used where it has the same number of passes: M = 512 = 8 x 8 x 8)
+template <int M_, int RR = 16>
 struct RegSched {
-  static constexpr int R = 16;                         // complex values per thread
+  static constexpr int M = M_;
+  static constexpr int R = RR;                         // complex values per thread
   static constexpr int T = M / R;                      // threads per line
-  static constexpr int NP = (M == 16) ? 1 : (M <= 256) ? 2 : 3;
-  static constexpr int R0 = (NP == 1) ? 16 : (NP == 2) ? M / 16 : M / 256;
-  static FB_CX int radix(int q) { return q == 0 ? R0 : 16; }
-  static FB_CX int ns(int q) { return q == 0 ? 1 : (q == 1 ? R0 : R0 * 16); }
+  static constexpr int NP = (M == RR) ? 1 : (M <= RR * RR) ? 2 : 3;
+  static constexpr int R0 = (NP == 1) ? RR : (NP == 2) ? M / RR : M / (RR * RR);
+  static_assert(R0 >= 1 && R0 <= RR && T * R == M, "schedule not representable");
+  static FB_CX int radix(int q) { return q == 0 ? R0 : RR; }
+  static FB_CX int ns(int q) { return q == 0 ? 1 : (q == 1 ? R0 : R0 * RR); }
 };
 
 FB_CX bool reg_fft_supported(int N) {
@@ -128,9 +134,8 @@ FB_CX int rf_padoff(int c) { return c >= 0 ? c + (c >> 4) : -((-c) + ((-c) >> 4)
 // One Stockham pass of the T threads owning a line.  Thread j holds element j + T*u in (re[u], im[u]).
 // Not the last pass: results go to the exchange buffer (scattered), the caller synchronises and gathers.
 // Last pass: results stay in registers, again as element (= mode) j + T*u.
-template <int M, int Q, int SIGN, class XB>
+template <class S, int Q, int SIGN, class XB>
 FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) {
-  using S = RegSched<M>;
   constexpr int r = S::radix(Q), Ns = S::ns(Q), NB = S::R / r, T = S::T;
   constexpr bool last = (Q == S::NP - 1);
   // pass 0 (Ns = 1): pos = jb r + t = j r + (T r) b + t with t < r | 16: no carry from t; T r is a multiple of 16 for
@@ -177,9 +182,8 @@ FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) 
 }
 
 // positions j + T u: for T >= 16 the offset is a multiple of 16, for T < 16 the low bits are j + (T u mod 16) < 16
-template <int M, class XB>
+template <class S, class XB>
 FB_HD void reg_gather(double* re, double* im, int j, const XB& xb) {
-  using S = RegSched<M>;
   const int base = xb.base(j);
 #if defined(__CUDACC__)
 #pragma unroll
@@ -187,9 +191,8 @@ FB_HD void reg_gather(double* re, double* im, int j, const XB& xb) {
   for (int u = 0; u < S::R; ++u) xb.ld(base, rf_padoff(S::T * u), re[u], im[u]);
 }
 
-template <int M, class XB>
+template <class S, class XB>
 FB_HD void reg_scatter_modes(const double* re, const double* im, int j, const XB& xb) {
-  using S = RegSched<M>;
   const int base = xb.base(j);
 #if defined(__CUDACC__)
 #pragma unroll
@@ -199,9 +202,9 @@ FB_HD void reg_scatter_modes(const double* re, const double* im, int j, const XB
 
 // partner mode of k = j + T u in the exchange buffer: M - k (k > 0), 0 (k = 0).  T >= 16: M - j - T u is a base
 // (M - j; for j = 0 it is never dereferenced itself) minus a multiple of 16.
-template <int M, class XB>
+template <class S, class XB>
 struct RegPartner {
-  using S = RegSched<M>;
+  static constexpr int M = S::M;
   static constexpr bool CONSTOFF = (S::T % 16 == 0);
   int bm, b0;
   FB_HD RegPartner(int j, const XB& xb) : bm(CONSTOFF ? xb.base(M - j) : 0), b0(CONSTOFF ? (j == 0 ? xb.base(0) : xb.base(M - j)) : 0) {}
@@ -219,10 +222,10 @@ struct RegPartner {
 // forward split for this thread's modes k = j + T*u: (re,im)[u] <- the two spectral rows of mode k.
 // The exchange buffer holds Z (all modes of the line).  Same arithmetic as split_core (tile_fft.cuh).
 // MK: Makhoul post-twiddle (NN/DD lines); wN / wQ may point to shared memory (indexed j + T u: immediates).
-template <int M, bool MK, class XB>
+template <class S, bool MK, class XB>
 FB_HD void reg_split(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
-  using S = RegSched<M>;
-  const RegPartner<M, XB> pt(j, xb);
+  constexpr int M = S::M;
+  const RegPartner<S, XB> pt(j, xb);
   const cpx* wNj = wN + j;
   const cpx* wQj = wQ + j;
 #if defined(__CUDACC__)
@@ -253,10 +256,10 @@ FB_HD void reg_split(double* re, double* im, int j, const cpx* wN, const cpx* wQ
 
 // backward merge: (re,im)[u] holds this thread's spectral rows of mode k = j + T*u, the exchange buffer
 // holds all modes of the line; result: Z'_k (input of the inverse complex FFT).  Same arithmetic as merge_core.
-template <int M, bool MK, class XB>
+template <class S, bool MK, class XB>
 FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
-  using S = RegSched<M>;
-  const RegPartner<M, XB> pt(j, xb);
+  constexpr int M = S::M;
+  const RegPartner<S, XB> pt(j, xb);
   const cpx* wNj = wN + j;
   const cpx* wQj = wQ + j;
   const cpx* wQm = wQ + (M - j);
@@ -285,17 +288,17 @@ FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ
   }
 }
 
-// Physical rows of packed element m = j + T u of a Makhoul (NN/DD) line, T = N/32 threads per line, R = 16:
-//   u <  8 (m <  N/4): e0 = 4 m,            e1 = e0 + 2      (even elements; DD sign +)
-//   u >= 8 (m >= N/4): e0 = 2 N - 1 - 4 m,  e1 = e0 - 2      (odd elements;  DD sign -)
+// Physical rows of packed element m = j + T u of a Makhoul (NN/DD) line, T = N/(2 RR) threads per line, RR values each:
+//   u <  RR/2 (m <  N/4): e0 = 4 m,            e1 = e0 + 2      (even elements; DD sign +)
+//   u >= RR/2 (m >= N/4): e0 = 2 N - 1 - 4 m,  e1 = e0 - 2      (odd elements;  DD sign -)
 // (slot_to_elem, tile_fft.cuh, for v = 2m and 2m+1.)  So a thread needs two row bases, 4 j and 2N-1-4j, and
 // compile-time multiples of the row stride.
-template <int N>
+template <int N, int RR = 16>
 struct MkRows {
-  static constexpr int T = N / 32;
-  static FB_CX bool upper(int u) { return u >= 8; }
-  static FB_CX int off0(int u) { return u < 8 ? 4 * T * u : -4 * T * u; }
-  static FB_CX int off1(int u) { return u < 8 ? 4 * T * u + 2 : -4 * T * u - 2; }
+  static constexpr int T = N / (2 * RR);
+  static FB_CX bool upper(int u) { return u >= RR / 2; }
+  static FB_CX int off0(int u) { return u < RR / 2 ? 4 * T * u : -4 * T * u; }
+  static FB_CX int off1(int u) { return u < RR / 2 ? 4 * T * u + 2 : -4 * T * u - 2; }
   FB_HD static int base_lo(int j) { return 4 * j; }
   FB_HD static int base_hi(int j) { return 2 * N - 1 - 4 * j; }
 };
@@ -307,17 +310,16 @@ FB_HD void reg_phys_slots(int kind, int N, int m, int& e0, int& e1, double& s0, 
 }
 
 // complete forward / backward passes between gather points; SYNC is the caller's barrier functor
-template <int M, int SIGN, class XB, class SYNC>
+template <class S, int SIGN, class XB, class SYNC>
 FB_HD void reg_fft_passes(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
-  using S = RegSched<M>;
-  reg_pass<M, 0, SIGN>(re, im, j, tw[0], xb);
+  reg_pass<S, 0, SIGN>(re, im, j, tw[0], xb);
   if constexpr (S::NP > 1) {
-    sync(); reg_gather<M>(re, im, j, xb); sync();
-    reg_pass<M, 1, SIGN>(re, im, j, tw[1], xb);
+    sync(); reg_gather<S>(re, im, j, xb); sync();
+    reg_pass<S, 1, SIGN>(re, im, j, tw[1], xb);
   }
   if constexpr (S::NP > 2) {
-    sync(); reg_gather<M>(re, im, j, xb); sync();
-    reg_pass<M, 2, SIGN>(re, im, j, tw[2], xb);
+    sync(); reg_gather<S>(re, im, j, xb); sync();
+    reg_pass<S, 2, SIGN>(re, im, j, tw[2], xb);
   }
 }
 

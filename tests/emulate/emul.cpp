@@ -274,9 +274,9 @@ struct EmulXB {                          // exchange buffer of one line, padded 
   void ld(int b, int coff, double& r, double& i) const { r = re[b + coff]; i = im[b + coff]; }
 };
 
-template <int M>
+template <int M, int RR = 16>
 static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
-  using S = RegSched<M>;
+  using S = RegSched<M, RR>;
   constexpr int T = S::T, R = S::R, N = 2 * M;
   // poisoned padded buffer: a wrong padded address reads NaN (or clobbers a slot that is read later)
   std::vector<double> bre(M + M / 16 + 2, std::nan("")), bim(M + M / 16 + 2, std::nan(""));
@@ -284,17 +284,17 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
   std::vector<double> re((size_t)T * R), im((size_t)T * R);
   auto RE = [&](int j) { return re.data() + (size_t)j * R; };
   auto IM = [&](int j) { return im.data() + (size_t)j * R; };
-  const cpx* tw[RF_MAXPASS] = {nullptr, hp.tw[1].data(), hp.tw[2].data()};
+  const cpx* tw[RF_MAXPASS] = {nullptr, RR == 16 ? hp.tw[1].data() : hp.tw8[1].data(), RR == 16 ? hp.tw[2].data() : hp.tw8[2].data()};
   auto passes = [&](auto sign) {
     constexpr int SIGN = decltype(sign)::value;
-    for (int j = 0; j < T; ++j) reg_pass<M, 0, SIGN>(RE(j), IM(j), j, tw[0], xb);
+    for (int j = 0; j < T; ++j) reg_pass<S, 0, SIGN>(RE(j), IM(j), j, tw[0], xb);
     if constexpr (S::NP > 1) {
-      for (int j = 0; j < T; ++j) reg_gather<M>(RE(j), IM(j), j, xb);
-      for (int j = 0; j < T; ++j) reg_pass<M, 1, SIGN>(RE(j), IM(j), j, tw[1], xb);
+      for (int j = 0; j < T; ++j) reg_gather<S>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) reg_pass<S, 1, SIGN>(RE(j), IM(j), j, tw[1], xb);
     }
     if constexpr (S::NP > 2) {
-      for (int j = 0; j < T; ++j) reg_gather<M>(RE(j), IM(j), j, xb);
-      for (int j = 0; j < T; ++j) reg_pass<M, 2, SIGN>(RE(j), IM(j), j, tw[2], xb);
+      for (int j = 0; j < T; ++j) reg_gather<S>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) reg_pass<S, 2, SIGN>(RE(j), IM(j), j, tw[2], xb);
     }
   };
   if (fwd) {
@@ -303,7 +303,7 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
         int e0, e1; double s0, s1;
         reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
         if (hp.kind != KIND_PP && M >= 16) {               // the kernels' closed form of the same rows
-          using MR = MkRows<N>;
+          using MR = MkRows<N, RR>;
           const int b = MR::upper(u) ? MR::base_hi(j) : MR::base_lo(j);
           if (b + MR::off0(u) != e0 || b + MR::off1(u) != e1) std::abort();
           const double sg = (hp.kind == KIND_DD && MR::upper(u)) ? -1.0 : 1.0;
@@ -312,20 +312,20 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
         RE(j)[u] = s0 * in[e0]; IM(j)[u] = s1 * in[e1];
       }
     passes(std::integral_constant<int, -1>{});
-    for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
+    for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
     for (int j = 0; j < T; ++j) {
-      if (hp.kind == KIND_PP) reg_split<M, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
-      else reg_split<M, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      if (hp.kind == KIND_PP) reg_split<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      else reg_split<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
     }
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) { const int k = j + T * u; out[2 * k] = scale * RE(j)[u]; out[2 * k + 1] = scale * IM(j)[u]; }
   } else {
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) { const int k = j + T * u; RE(j)[u] = in[2 * k]; IM(j)[u] = in[2 * k + 1]; }
-    for (int j = 0; j < T; ++j) reg_scatter_modes<M>(RE(j), IM(j), j, xb);
+    for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
     for (int j = 0; j < T; ++j) {
-      if (hp.kind == KIND_PP) reg_merge<M, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
-      else reg_merge<M, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      if (hp.kind == KIND_PP) reg_merge<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      else reg_merge<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
     }
     passes(std::integral_constant<int, +1>{});
     for (int j = 0; j < T; ++j)
@@ -350,6 +350,14 @@ extern "C" int emul_reg_line_transform(int N, int kind, int fwd, const double* i
     case 1024: reg_line_emul<1024>(hp, fwd, in, out, scale); break;
     default: return 2;
   }
+  return 0;
+}
+
+// the 8-values-per-thread schedule (N = 1024)
+extern "C" int emul_reg_line_transform8(int N, int kind, int fwd, const double* in, double* out, double scale) {
+  HostRegPlan hp = make_reg_plan(N, kind);
+  if (!hp.ok || hp.M != 512) return 1;
+  reg_line_emul<512, 8>(hp, fwd, in, out, scale);
   return 0;
 }
 

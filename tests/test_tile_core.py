@@ -74,8 +74,13 @@ def test_tile_forward_matches_fftw_definition(emul, bc, n, tb, rot):
 
 # ---- register-resident transforms (reg_fft.cuh) --------------------------------------------------
 @pytest.mark.parametrize("bc", ["PP", "NN", "DD"])
-@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048])
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, (1024, 8)], ids=str)
 def test_reg_fft_matches_fftw_definition(emul, bc, n):
+    transform = emul.emul_reg_line_transform
+    if isinstance(n, tuple):                               # the 8-values-per-thread schedule of the N = 1024 y kernels
+        n = n[0]
+        emul.emul_reg_line_transform8.argtypes = emul.emul_reg_line_transform.argtypes
+        transform = emul.emul_reg_line_transform8
     rng = np.random.default_rng(7 * n + len(bc))
     nl = 3
     x = rng.uniform(-1, 1, (nl, n))
@@ -92,12 +97,12 @@ def test_reg_fft_matches_fftw_definition(emul, bc, n):
     for l in range(nl):
         out, back, back2 = np.zeros(n), np.zeros(n), np.zeros(n)
         xin = np.ascontiguousarray(x[l])
-        assert emul.emul_reg_line_transform(n, KIND[bc], 1, xin.ctypes.data_as(_dp), out.ctypes.data_as(_dp), 1.0) == 0
+        assert transform(n, KIND[bc], 1, xin.ctypes.data_as(_dp), out.ctypes.data_as(_dp), 1.0) == 0
         assert np.max(np.abs(out - ref[l, mode])) <= 5e-14 * max(1.0, np.max(np.abs(ref[l])))
-        assert emul.emul_reg_line_transform(n, KIND[bc], 0, out.ctypes.data_as(_dp), back.ctypes.data_as(_dp), 1.0) == 0
+        assert transform(n, KIND[bc], 0, out.ctypes.data_as(_dp), back.ctypes.data_as(_dp), 1.0) == 0
         assert np.max(np.abs(back - xin * norm[0] * (n + norm[1]))) <= 1e-13 * n
         sp = np.ascontiguousarray(spec[l])
-        assert emul.emul_reg_line_transform(n, KIND[bc], 0, sp.ctypes.data_as(_dp), back2.ctypes.data_as(_dp), 0.5) == 0
+        assert transform(n, KIND[bc], 0, sp.ctypes.data_as(_dp), back2.ctypes.data_as(_dp), 0.5) == 0
         assert np.max(np.abs(back2 - 0.5 * refb[l])) <= 5e-14 * max(1.0, np.max(np.abs(refb[l])))
 
 

@@ -1,13 +1,12 @@
 #!/bin/bash
-# A/B runs of kernel variants (environment variables / FLUTAS_B200_LIB builds); prints one summary line per run
 mkdir -p gpurun_out
 : > gpurun_out/ab.log
 run() { W=$1; tag=$2; shift 2; echo "== $W $tag" >> gpurun_out/ab.log; env "$@" timeout 300 python bench.py --solver-only --steps 10 --warmup 3 --workload $W 2>&1 | tail -1 >> gpurun_out/ab.log; }
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "$(tail -1 gpurun_out/pytest_gpu.log)"; grep -E "residual|FAILED|Error" gpurun_out/pytest_gpu.log | head
-
-for W in ${WORKLOADS:-C5xy}; do
-  run $W default X=1
-  run $W ynarrow FLUTAS_B200_YWIDE=0
+CS=$PWD/flutas_b200/csrc
+for W in ${WORKLOADS:-NS C2}; do
+  run $W y8-cs FLUTAS_B200_Y8=1
+  run $W y8-plain FLUTAS_B200_Y8=1 FLUTAS_B200_LIB=$CS/libflutas_b200_yplain.so
+  run $W y16-plain FLUTAS_B200_Y8=0 FLUTAS_B200_LIB=$CS/libflutas_b200_yplain.so
 done
 python - <<'PY'
 import json
