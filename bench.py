@@ -396,8 +396,10 @@ def main():
         stage_tbl[name] = {"ms": round(avg, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
     solver_stages = [k for k in ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd") if k in stage_tbl]
     dom = max(solver_stages, key=lambda k: stage_tbl[k]["ms"])
-    traffic = None
+    traffic = None                                       # per-launch DRAM bytes from the committed 1-GPU ncu capture
     try:
+        if world > 1:
+            raise LookupError("ncu captures are single-GPU")
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f).get(args.workload, {}).get(dom)
     except Exception:
