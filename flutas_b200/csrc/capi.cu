@@ -25,6 +25,9 @@
 
 using namespace fb;
 
+#ifndef FB_PIPE_DEFAULT
+#define FB_PIPE_DEFAULT 0
+#endif
 namespace {
 
 thread_local std::string g_err;
@@ -809,6 +812,55 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   LineGeom gp{1 + s1 * (1 + s2), s1, s1 * s2, n2, (long)n2 * n3l};
   LineGeom gw{0, (long)n1, (long)n1 * n2, n2, (long)n2 * n3l};
 
+  // Forward half, pipelined over k-chunks (direct-store exchange only): the y transform + NVLink stores of chunk c run on
+  // part of the SMs while the x transform of chunk c+1 runs on the rest (second stream), so the HBM-bound x stage hides
+  // behind the NVLink-bound y stage.  FLUTAS_B200_PIPE = number of chunks (0/1 = off), FLUTAS_B200_PIPE_XSM = percentage
+  // of the SMs given to the x kernels.  Measured at 2 GPUs (profiles/r01_pipe_forward_N2.log): 512^3 1.560 -> 1.521 ms,
+  // 1024^3 12.46 -> 12.57..12.84 ms: the y kernel with remote stores needs all SMs itself (its remote stores are not a pure
+  // link-bound tail), so splitting the SMs only divides the throughput -> off by default.
+  static const int pipe_chunks = [] { const char* e = getenv("FLUTAS_B200_PIPE"); return e ? atoi(e) : FB_PIPE_DEFAULT; }();
+  static const int pipe_xsm = [] { const char* e = getenv("FLUTAS_B200_PIPE_XSM"); const int v = e ? atoi(e) : 50; return v < 10 ? 10 : v > 90 ? 90 : v; }();
+  const bool pipelined = sp->p2p && pipe_chunks > 1 && pipe_chunks <= 16 && (n3l % pipe_chunks) == 0 && sp->px.use_reg && sp->py.use_reg;
+  if (pipelined) {
+    static cudaStream_t s_x = nullptr;
+    static cudaEvent_t ev_in = nullptr, ev_c[16];
+    if (!s_x) {
+      CK(cudaStreamCreateWithFlags(&s_x, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+      for (int c = 0; c < 16; ++c) CK(cudaEventCreateWithFlags(&ev_c[c], cudaEventDisableTiming));
+    }
+    struct Scoped {                                      // launch configuration of run_x / run_y for this scope
+      cudaStream_t s0; int n0;
+      Scoped(cudaStream_t s, int nsm) : s0(g_stream), n0(g_nsm) { g_stream = s; g_nsm = nsm; }
+      ~Scoped() { g_stream = s0; g_nsm = n0; }
+    };
+    const int nsm_all = g_nsm > 0 ? g_nsm : 148;
+    int nsm_x = nsm_all * pipe_xsm / 100; if (nsm_x < 1) nsm_x = 1;
+    const int nsm_y = nsm_all - nsm_x > 0 ? nsm_all - nsm_x : 1;
+    const int n3c = n3l / pipe_chunks;
+    SpecGeom sg;
+    for (int q = 0; q < FB_MAX_RANKS; ++q) sg.ptr[q] = nullptr;
+    for (int q = 0; q < P; ++q) sg.ptr[q] = sp->peer_pencil[q];
+    sg.n1l = n1l;
+    StageTimer t(ST_YF);                                 // the whole pipelined forward half is booked on the y stage
+    CK(cudaEventRecord(ev_in, g_stream));
+    CK(cudaStreamWaitEvent(s_x, ev_in, 0));
+    y_wide_request() = 1;
+    int rc = 0;
+    for (int c = 0; c < pipe_chunks && !rc; ++c) {
+      LineGeom gpc = gp, gwc = gw;
+      gpc.off0 += (long)c * n3c * gp.sk; gwc.off0 += (long)c * n3c * gw.sk;
+      gpc.nlines = gwc.nlines = (long)n2 * n3c;
+      { Scoped cfg(s_x, nsm_x); rc = run_x<true>(sp->px, pd, gpc, W1, gwc, 1.0); }
+      if (rc) break;
+      CK(cudaEventRecord(ev_c[c], s_x));
+      CK(cudaStreamWaitEvent(g_stream, ev_c[c], 0));
+      sg.koff = (long)r * (long)chunk + (long)c * n3c * (long)n1l * n2;
+      { Scoped cfg(g_stream, nsm_y); rc = run_y<true>(sp->py, W1 + (size_t)c * n3c * n1 * n2, n1, n3c, sg); }
+    }
+    y_wide_request() = 0;
+    if (rc) return rc;
+  } else {
   { StageTimer t(ST_XF); if (int rc = run_x<true>(sp->px, pd, gp, W1, gw, 1.0)) return rc; }
   {
     // y transform whose store IS the pack (NCCL) or the exchange itself (direct stores into peer pencils)
@@ -821,6 +873,7 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
     const int rc = run_y<true>(sp->py, W1, n1, n3l, sg);
     y_wide_request() = 0;
     if (rc) return rc;
+  }
   }
   {
     StageTimer t(ST_EXCH_F);
