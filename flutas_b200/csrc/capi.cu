@@ -993,10 +993,21 @@ int flutas_b200_correc(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   CK(cudaMemcpyAsync(g_coef.p, dzci, nd * sizeof(double), cudaMemcpyDefault, g_stream));
   const double rho0i = 1.0 / rho0;
   dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  // two points per thread with 16-byte accesses when every row start is 16-byte aligned (even nx, aligned bases; the pair
+  // element index parity is that of nh_u - 1 for u,v,w and 0 for p: both even only for odd nh_u, i.e. nh_u = 1 or 3)
+  static const bool vec_env = [] { const char* e = getenv("FLUTAS_B200_CORREC_VEC"); return !(e && e[0] == '0'); }();
+  const bool vec2 = vec_env && (nx % 2 == 0) && (nh_u % 2 == 1) && !((uintptr_t)fu.dev % 16) && !((uintptr_t)fv.dev % 16) &&
+                    !((uintptr_t)fw.dev % 16) && !((uintptr_t)fp.dev % 16);
   {
     StageTimer t(ST_CORREC);
-    correc_kernel<<<grd, blk, 0, g_stream>>>(g, dt * dxi, dt * dyi, dt, g_coef.as<double>() + (nh_d - 1), rho0i,
-                                             fp.dev, fu.dev, fv.dev, fw.dev);
+    if (vec2) {
+      dim3 g2((nx / 2 + 1 + 63) / 64, (ny + 3) / 4, nz);
+      correc_vec2_kernel<<<g2, blk, 0, g_stream>>>(g, dt * dxi, dt * dyi, dt, g_coef.as<double>() + (nh_d - 1), rho0i,
+                                                   fp.dev, fu.dev, fv.dev, fw.dev);
+    } else {
+      correc_kernel<<<grd, blk, 0, g_stream>>>(g, dt * dxi, dt * dyi, dt, g_coef.as<double>() + (nh_d - 1), rho0i,
+                                               fp.dev, fu.dev, fv.dev, fw.dev);
+    }
   }
   LAUNCHED();
   if (int rc = stage_out(fu)) return rc;

@@ -327,6 +327,42 @@ __global__ void __launch_bounds__(256) correc_kernel(StencilGeom g, double facto
   w[c] = __dsub_rn(w[c], __dmul_rn(__dmul_rn(__dmul_rn(dt, dzci[k]), __dsub_rn(p[q + g.sp1 * g.sp2], pc)), rho0i));
 }
 
+// correc.f90:57-60, two points per thread: every row of u,v,w,p starts 16-byte aligned when nx is even (sanity.f90:155)
+// and the base pointers are, so the pair (i, i+1) with i even -- 0-based storage element i+nh_u-1 resp. i -- is one
+// aligned 16-byte access in all four arrays.  The first pair of a row holds the halo i = 0, the last one i = nx+1: those
+// elements are loaded but never stored.  Same arithmetic per element as correc_kernel (bit-exact).
+__global__ void __launch_bounds__(256) correc_vec2_kernel(StencilGeom g, double factori, double factorj, double dt,
+                                                          const double* __restrict__ dzci, double rho0i,
+                                                          const double* __restrict__ p, double* __restrict__ u,
+                                                          double* __restrict__ v, double* __restrict__ w) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);          // even, 0 .. nx
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k), q = pidx(g, i, j, k);
+  const double2 pc = *reinterpret_cast<const double2*>(p + q);
+  const double2 py = *reinterpret_cast<const double2*>(p + q + g.sp1);
+  const double2 pz = *reinterpret_cast<const double2*>(p + q + g.sp1 * g.sp2);
+  const double px2 = (i + 2 <= g.nx + 1) ? p[q + 2] : 0.0;
+  double2 uu = *reinterpret_cast<double2*>(u + c), vv = *reinterpret_cast<double2*>(v + c), ww = *reinterpret_cast<double2*>(w + c);
+  const double fk = __dmul_rn(dt, dzci[k]);
+  const bool lo = (i >= 1), hi = (i + 1 <= g.nx);                    // which of the two points are interior
+  if (lo) {
+    uu.x = __dsub_rn(uu.x, __dmul_rn(__dmul_rn(factori, __dsub_rn(pc.y, pc.x)), rho0i));
+    vv.x = __dsub_rn(vv.x, __dmul_rn(__dmul_rn(factorj, __dsub_rn(py.x, pc.x)), rho0i));
+    ww.x = __dsub_rn(ww.x, __dmul_rn(__dmul_rn(fk, __dsub_rn(pz.x, pc.x)), rho0i));
+  }
+  if (hi) {
+    uu.y = __dsub_rn(uu.y, __dmul_rn(__dmul_rn(factori, __dsub_rn(px2, pc.y)), rho0i));
+    vv.y = __dsub_rn(vv.y, __dmul_rn(__dmul_rn(factorj, __dsub_rn(py.y, pc.y)), rho0i));
+    ww.y = __dsub_rn(ww.y, __dmul_rn(__dmul_rn(fk, __dsub_rn(pz.y, pc.y)), rho0i));
+  }
+  if (lo && hi) {
+    *reinterpret_cast<double2*>(u + c) = uu; *reinterpret_cast<double2*>(v + c) = vv; *reinterpret_cast<double2*>(w + c) = ww;
+  } else if (hi) { u[c + 1] = uu.y; v[c + 1] = vv.y; w[c + 1] = ww.y; }
+  else if (lo) { u[c] = uu.x; v[c] = vv.x; w[c] = ww.x; }
+}
+
 // source.f90:311-346 (pres_sp_src): u += f_t12*( -(pold(ip)-pold(i))*dxi )*rho0i, left to right, no FMA contraction
 __global__ void __launch_bounds__(256) pres_sp_src_kernel(StencilGeom g, double f_t12, double dxi, double dyi,
                                                           const double* __restrict__ dzci, double rho0i,
