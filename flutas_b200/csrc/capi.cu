@@ -928,10 +928,19 @@ int flutas_b200_fillps(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
   if (int rc = g_coef.reserve(nd * sizeof(double))) return rc;
   CK(cudaMemcpyAsync(g_coef.p, dzfi, nd * sizeof(double), cudaMemcpyDefault, g_stream));
   dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  static const bool vec_env = [] { const char* e = getenv("FLUTAS_B200_CORREC_VEC"); return !(e && e[0] == '0'); }();
+  const bool vec2 = vec_env && (nx % 2 == 0) && (nh_u % 2 == 1) && !((uintptr_t)fu.dev % 16) && !((uintptr_t)fv.dev % 16) &&
+                    !((uintptr_t)fw.dev % 16) && !((uintptr_t)fp.dev % 16);          // as in flutas_b200_correc
   {
     StageTimer t(ST_FILLPS);
-    fillps_kernel<<<grd, blk, 0, g_stream>>>(g, dti * dxi, dti * dyi, dti, g_coef.as<double>() + (nh_d - 1), rho0,
-                                             fu.dev, fv.dev, fw.dev, fp.dev);
+    if (vec2) {
+      dim3 g2((nx / 2 + 1 + 63) / 64, (ny + 3) / 4, nz);
+      fillps_vec2_kernel<<<g2, blk, 0, g_stream>>>(g, dti * dxi, dti * dyi, dti, g_coef.as<double>() + (nh_d - 1), rho0,
+                                                   fu.dev, fv.dev, fw.dev, fp.dev);
+    } else {
+      fillps_kernel<<<grd, blk, 0, g_stream>>>(g, dti * dxi, dti * dyi, dti, g_coef.as<double>() + (nh_d - 1), rho0,
+                                               fu.dev, fv.dev, fw.dev, fp.dev);
+    }
   }
   LAUNCHED();
   if (int rc = stage_out(fp)) return rc;

@@ -280,6 +280,41 @@ __global__ void __launch_bounds__(256) fillps_kernel(StencilGeom g, double dtidx
   p[pidx(g, i, j, k)] = __dmul_rn(val, rho0);
 }
 
+// fillps.f90:50-57, two points per thread with aligned 16-byte accesses (see correc_vec2_kernel for the alignment argument):
+// pair (i, i+1), i even; u(i-1) of the first point is the one extra scalar load.  Bit-exact with fillps_kernel.
+__global__ void __launch_bounds__(256) fillps_vec2_kernel(StencilGeom g, double dtidxi, double dtidyi, double dti,
+                                                          const double* __restrict__ dzfi, double rho0,
+                                                          const double* __restrict__ u, const double* __restrict__ v,
+                                                          const double* __restrict__ w, double* __restrict__ p) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);          // even, 0 .. nx
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  const int k = blockIdx.z + 1;
+  if (i > g.nx || j > g.ny) return;
+  const long c = uidx(g, i, j, k), q = pidx(g, i, j, k);
+  const bool lo = (i >= 1), hi = (i + 1 <= g.nx);
+  const double2 uc = *reinterpret_cast<const double2*>(u + c);
+  const double2 vc = *reinterpret_cast<const double2*>(v + c), vm = *reinterpret_cast<const double2*>(v + c - g.su1);
+  const double2 wc = *reinterpret_cast<const double2*>(w + c), wm = *reinterpret_cast<const double2*>(w + c - g.su1 * g.su2);
+  const double um = lo ? u[c - 1] : 0.0;
+  const double dz = dzfi[k];
+  double2 out;
+  {
+    const double tz = __dmul_rn(__dmul_rn(__dsub_rn(wc.x, wm.x), dti), dz);
+    const double ty = __dmul_rn(__dsub_rn(vc.x, vm.x), dtidyi);
+    const double tx = __dmul_rn(__dsub_rn(uc.x, um), dtidxi);
+    out.x = __dmul_rn(__dadd_rn(__dadd_rn(tz, ty), tx), rho0);
+  }
+  {
+    const double tz = __dmul_rn(__dmul_rn(__dsub_rn(wc.y, wm.y), dti), dz);
+    const double ty = __dmul_rn(__dsub_rn(vc.y, vm.y), dtidyi);
+    const double tx = __dmul_rn(__dsub_rn(uc.y, uc.x), dtidxi);
+    out.y = __dmul_rn(__dadd_rn(__dadd_rn(tz, ty), tx), rho0);
+  }
+  if (lo && hi) *reinterpret_cast<double2*>(p + q) = out;
+  else if (hi) p[q + 1] = out.y;
+  else if (lo) p[q] = out.x;
+}
+
 // bound.f90:858-942 for one rank owning all six faces; which faces apply is encoded in rhsb pointers
 __global__ void updt_rhs_b_kernel(StencilGeom g, const double* __restrict__ rx, double* __restrict__ p) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
