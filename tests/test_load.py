@@ -64,3 +64,37 @@ def test_device_resident_field_round_trip(tmp_path):
     api.load("r", f, (ng[0], ng[1], 8), pd, ng=ng, start=(0, 0, 8), nh=1)
     back = api.host_field(pd, (ng[0] + 2, ng[1] + 2, 10))
     assert np.array_equal(back[1:-1, 1:-1, 1:-1], g[:, :, 8:16]) and back[0, 0, 0] == -3.0
+
+
+def _load_worker(rank, world, port, path, ng):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = _global(ng, 9)
+        n3l = ng[2] // world
+        # every rank writes its z-slab of the checkpoint concurrently (no ordering, no truncation race) ...
+        blk = np.asfortranarray(g[:, :, rank * n3l:(rank + 1) * n3l])
+        api.load("w", path, blk.shape, blk, ng=ng, start=(0, 0, rank * n3l))
+        dist.barrier()
+        # ... and reads back ANOTHER rank's slab into a halo'd array: the file is decomposition independent
+        other = (rank + 1) % world
+        p = np.zeros((ng[0] + 2, ng[1] + 2, n3l + 2), order="F")
+        api.load("r", path, (ng[0], ng[1], n3l), p, ng=ng, start=(0, 0, other * n3l), nh=1)
+        assert np.array_equal(p[1:-1, 1:-1, 1:-1], g[:, :, other * n3l:(other + 1) * n3l])
+        if rank == 0:
+            assert np.array_equal(np.fromfile(path, dtype=np.float64).reshape(ng, order="F"), g)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slabs_written_by_concurrent_ranks(tmp_path, world):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_load_worker, args=(world, port, str(tmp_path / "fldp.bin"), (16, 12, 8)), nprocs=world, join=True)
