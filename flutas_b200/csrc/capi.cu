@@ -1208,7 +1208,10 @@ int flutas_b200_load(char io, const char* filename, const int ng[3], const int n
     }
   }
   close(fd);
-  if (io == 'r') { if (int rc = halo_copy(true)) return rc; }
+  if (io == 'r') {
+    if (dev) CK(cudaStreamSynchronize(g_stream));          // kernels still reading the old contents of fld on the library stream
+    if (int rc = halo_copy(true)) return rc;
+  }
   return FLUTAS_B200_OK;
 }
 

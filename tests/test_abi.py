@@ -47,3 +47,21 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("with the oracle", ""), f
+
+
+def test_header_is_plain_c_and_the_shim_binds_every_compute_entry_point():
+    """The boundary is a C ABI: the header must compile as C99 (no C++/torch types), and the Fortran shim
+    (flutas_b200/fortran/flutas_b200_shim.f90) must bind every entry point the reference's call sites need."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc:
+        subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                               os.path.join(ROOT, "include", "flutas_b200.h")])
+    shim = open(os.path.join(ROOT, "flutas_b200", "fortran", "flutas_b200_shim.f90")).read()
+    bound = set(re.findall(r"bind\(C,\s*name='(flutas_b200_\w+)'\)", shim))
+    needed = {"flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_fillps", "flutas_b200_correc",
+              "flutas_b200_chkdiv", "flutas_b200_boundp", "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src",
+              "flutas_b200_pold_update", "flutas_b200_load"}
+    assert needed <= bound, needed - bound
+    assert bound <= set(_declared_symbols()), bound - set(_declared_symbols())
