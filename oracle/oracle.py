@@ -260,3 +260,147 @@ def boundp(cbc, n, bc, nh_d, dl, dzc, p, below=None, above=None, first_rank=True
         if last_rank:
             _set_bc(p, cbc[2][1], 1, 2, bc[2][1], dzc[nh_d - 1 + n3])      # dr = dzc(n3)
     return p
+
+
+# ---------------------------------------------------------------------------------------------------
+# bounduvw: numpy restatement of src/bound.f90:17-144 with set_bc (:227-646) for an arbitrary
+# halo width, updthalo (:946-1110) and outflow (:649-773), single rank in the _DECOMP_X layout.  Groundwork for the
+# device version: this round ships the oracle and its tests only, no CUDA kernel yet.
+def _fx(nh, i):
+    """numpy index of Fortran index i of an array dimensioned (1-nh:)"""
+    return i + nh - 1
+
+
+def _plane(idir, idx):
+    s = [slice(None)] * 3
+    s[idir] = idx
+    return tuple(s)
+
+
+def set_bc_general(p, ctype, ibound, idir, centered, rvalue, dr, nh, n):
+    """set_bc(nx,ny,nz,ctype,ibound,idir,centered,rvalue,qq_d,nh_p,dr,p), src/bound.f90:227-646.
+    idir 0-based; dr[q], q = 0..nh-1; loops over q run in the reference's order (later q may overwrite earlier ones)."""
+    P = lambda i: _plane(idir, _fx(nh, i))
+    if ctype == "P":                                      # :268-318
+        for q in range(nh):
+            p[P(0 - q)] = p[P(n - q)]
+            p[P(n + 1 + q)] = p[P(1 + q)]
+        return
+    factor = [np.float64(rvalue)] * nh
+    sgn = np.float64(0.0)
+    if ctype == "D" and centered:                         # :251-256
+        factor = [np.float64(2.0) * f for f in factor]
+        sgn = np.float64(-1.0)
+    if ctype == "N":                                      # :257-268
+        factor = [(-np.float64(dr[q]) * factor[q]) if ibound == 0 else (np.float64(dr[q]) * factor[q]) for q in range(nh)]
+        sgn = np.float64(1.0)
+    for q in range(nh):
+        f = factor[q]
+        if centered:                                      # :320-431
+            if ibound == 0:
+                p[P(0 - q)] = f + sgn * p[P(1 + q)]
+            else:
+                p[P(n + 1 + q)] = f + sgn * p[P(n - q)]
+        elif ctype == "D":                                # :432-533 (face-centred component normal to the wall)
+            if ibound == 0:
+                p[P(0 - q)] = f
+            else:
+                p[P(n + q)] = f
+                p[P(n + 1 + q)] = p[P(n - 1 - q)]
+        elif ctype == "N":                                # :534-646
+            if ibound == 0:
+                p[P(0 - q)] = np.float64(1.0) * f + p[P(1 + q)]
+            else:
+                p[P(n + q)] = np.float64(1.0) * f + p[P(n - 1 - q)]
+                p[P(n + 1 + q)] = np.float64(2.0) * f + p[P(n - 1 - q)]
+
+
+def _outflow(n, idir_signed, nh_d, nh_u, dl, dzf, u, v, w):
+    """outflow, src/bound.f90:649-773: face velocity from zero divergence on an outflow boundary"""
+    nx, ny, nz = n
+    qmin = abs(1 - nh_u)
+    dx, dy = dl[0], dl[1]
+    dxi, dyi = dx ** (-1), dy ** (-1)
+    dzfi = dzf ** (-1)                                     # dzf(1-nh_d:) -> numpy index k + nh_d - 1
+    h = nh_u
+    I = lambda a, b: slice(_fx(h, a), _fx(h, b) + 1)       # Fortran range a:b
+    X = lambda i: _fx(h, i)
+    zk = lambda k: k + nh_d - 1
+    if idir_signed == 1:                                   # x, right
+        i = nx
+        dzk = dzfi[zk(1):zk(nz) + 1][None, :]
+        for q in range(qmin + 2):
+            u[X(i + q), I(1, ny), I(1, nz)] = u[X(i - 1 - q), I(1, ny), I(1, nz)] - dx * (
+                (v[X(i + q), I(1, ny), I(1, nz)] - v[X(i + q), I(0, ny - 1), I(1, nz)]) * dyi +
+                (w[X(i + q), I(1, ny), I(1, nz)] - w[X(i + q), I(1, ny), I(0, nz - 1)]) * dzk)
+    elif idir_signed == 2:                                 # y, back
+        j = ny
+        dzk = dzfi[zk(1):zk(nz) + 1][None, :]
+        for q in range(qmin + 2):
+            v[I(1, nx), X(j + q), I(1, nz)] = v[I(1, nx), X(j - 1 - q), I(1, nz)] - dy * (
+                (u[I(1, nx), X(j + q), I(1, nz)] - u[I(0, nx - 1), X(j + q), I(1, nz)]) * dxi +
+                (w[I(1, nx), X(j + q), I(1, nz)] - w[I(1, nx), X(j + q), I(0, nz - 1)]) * dzk)
+    elif idir_signed == 3:                                 # z, top
+        k = nz
+        for q in range(qmin + 2):
+            w[I(1, nx), I(1, ny), X(k + q)] = w[I(1, nx), I(1, ny), X(k - 1 - q)] - dzf[zk(k + q)] * (
+                (u[I(1, nx), I(1, ny), X(k + q)] - u[I(0, nx - 1), I(1, ny), X(k + q)]) * dxi +
+                (v[I(1, nx), I(1, ny), X(k + q)] - v[I(1, nx), I(0, ny - 1), X(k + q)]) * dyi)
+    elif idir_signed == -1:                                # x, left
+        i = 0
+        dzk = dzfi[zk(1):zk(nz) + 1][None, :]
+        for q in range(qmin + 1):
+            u[X(i - q), I(1, ny), I(1, nz)] = u[X(i + 1 + q), I(1, ny), I(1, nz)] + dx * (
+                (v[X(i + 1 + q), I(1, ny), I(1, nz)] - v[X(i + 1 + q), I(0, ny - 1), I(1, nz)]) * dyi +
+                (w[X(i + 1 + q), I(1, ny), I(1, nz)] - w[X(i + 1 + q), I(1, ny), I(0, nz - 1)]) * dzk)
+    elif idir_signed == -2:                                # y, front
+        j = 0
+        dzk = dzfi[zk(1):zk(nz) + 1][None, :]
+        for q in range(qmin + 1):
+            v[I(1, nx), X(j - q), I(1, nz)] = v[I(1, nx), X(j + 1 + q), I(1, nz)] + dy * (
+                (u[I(1, nx), X(j + 1 + q), I(1, nz)] - u[I(0, nx - 1), X(j + 1 + q), I(1, nz)]) * dxi +
+                (w[I(1, nx), X(j + 1 + q), I(1, nz)] - w[I(1, nx), X(j + 1 + q), I(0, nz - 1)]) * dzk)
+    elif idir_signed == -3:                                # z, bottom
+        k = 0
+        for q in range(qmin + 1):
+            w[I(1, nx), I(1, ny), X(k - q)] = w[I(1, nx), I(1, ny), X(k + 1 + q)] + dzf[zk(k - q)] * (
+                (u[I(1, nx), I(1, ny), X(k + 1 + q)] - u[I(0, nx - 1), I(1, ny), X(k + 1 + q)]) * dxi +
+                (v[I(1, nx), I(1, ny), X(k + 1 + q)] - v[I(1, nx), I(0, ny - 1), X(k + 1 + q)]) * dyi)
+
+
+def bounduvw(cbc, n, bc, nh_d, nh_u, isoutflow, dl, dzc, dzf, u, v, w):
+    """bounduvw(cbc,n,bc,nh_d,nh_u,halo,isoutflow,dl,dzc,dzf,u,v,w), src/bound.f90:17-144, on ONE rank.
+    cbc[ibound][idir][field] (characters), bc likewise (values), isoutflow[ibound][idir]; dzc, dzf dimensioned (1-nh_d:).
+    Periodic y / z: the rank is its own neighbour, updthalo wraps nh_u layers (:55-62) and set_bc is skipped because the
+    neighbour is not MPI_PROC_NULL; x is never divided in _DECOMP_X, so every x boundary goes through set_bc (:68-79)."""
+    nx, ny, nz = n
+    fields = (u, v, w)
+    per_y = all(cbc[b][1][f] == "P" for b in (0, 1) for f in range(3))
+    per_z = all(cbc[b][2][f] == "P" for b in (0, 1) for f in range(3))
+    for fld in fields:                                     # updthalo ind1 = 2, ind2 = 3 (:55-62)
+        if per_y:
+            set_bc_general(fld, "P", 0, 1, True, 0.0, None, nh_u, ny)
+        if per_z:
+            set_bc_general(fld, "P", 0, 2, True, 0.0, None, nh_u, nz)
+    qmin = abs(1 - nh_u)
+    zk = lambda k: k + nh_d - 1
+    for idir, nn in ((0, nx), (1, ny), (2, nz)):
+        if (idir == 1 and per_y) or (idir == 2 and per_z):
+            continue
+        for ib in (0, 1):
+            for f, fld in enumerate(fields):
+                centered = (f != idir)                     # the wall-normal component is face-centred (.false. in :68-128)
+                if idir < 2:
+                    dr = [dl[idir]] * (qmin + 1)
+                elif ib == 0:
+                    dr = [(dzc if centered else dzf)[zk(-q)] for q in range(qmin + 1)]            # :95-106
+                else:
+                    dr = [(dzc if centered else dzf)[zk(nz + q)] for q in range(qmin + 1)]        # :108-119
+                set_bc_general(fld, cbc[ib][idir][f], ib, idir, centered, bc[ib][idir][f], dr, nh_u, nn)
+    # NOTE the reference's order inside one direction is: bottom u, v, w, then top u, v, w for x and y; for z it is bottom
+    # u, v (dzc), bottom w (dzf), top u, v, top w -- the same sequence as the loops above.
+    for q in range(3):                                     # :131-141
+        for ib in (0, 1):
+            if isoutflow[ib][q]:
+                _outflow(n, (q + 1) * (-1 if ib == 0 else 1), nh_d, nh_u, dl, dzf, u, v, w)
+    return u, v, w
