@@ -156,6 +156,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+NOMINAL_HBM_GBS = 8000.0                                 # the north star's nominal figure, reported next to the measured peak
+
+
+def nvlink_figures(stage_tbl, stages, npts_loc, world, exchange):
+    """NVLink side of the roofline: bytes each GPU sends per exchange and the rate the stage that carries
+    them achieves (direct stores: the y-transform / z-solve kernels themselves; NCCL: the all-to-all)."""
+    sent = 8.0 * npts_loc * (world - 1) / world
+    nv = {"exchange": exchange, "bytes_sent_per_gpu_per_exchange": sent, "peak_GBs_per_direction": 900.0,
+          "measured_peer_copy_GBs": 770.0}
+    if exchange == "p2p":
+        for nm in ("yfft_fwd", "thomas_z"):
+            if nm in stage_tbl:
+                nv[nm + "_GBs"] = round(sent / (stage_tbl[nm]["ms"] * 1e-3) / 1e9, 1)
+    for nm in ("exchange_fwd", "exchange_bwd"):
+        if nm in stages and stages[nm][1]:
+            ms = stages[nm][0] / stages[nm][1]
+            nv[nm + "_ms"] = round(ms, 4)
+            if exchange == "nccl":
+                nv[nm + "_GBs"] = round(sent / (ms * 1e-3) / 1e9, 1)
+    return nv
+
+
 def workload_config(case, wid):
     from flutas_b200.cases import CONFIGS
     n1, n2, n3 = case.ng
@@ -324,8 +346,11 @@ def main():
                 "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                              "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT,
                                         "achieved_per_gpu": round(SOLVER_BYTES_PER_PT * value / world, 1),
-                                        "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4)},
+                                        "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4),
+                                        "frac_of_nominal_8TBs": round(SOLVER_BYTES_PER_PT * value / world / NOMINAL_HBM_GBS, 4)},
                              "stages": tbl}}
+        if world > 1:
+            line["roofline"]["nvlink"] = nvlink_figures(tbl, stages, npts_loc, world, exchange)
         if rank == 0:
             print(json.dumps(line))
         api.fftend(pl)
@@ -408,24 +433,11 @@ def main():
                 "frac": stage_tbl[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_PT[dom] * npts_loc,
                 "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT, "achieved_per_gpu": round(SOLVER_BYTES_PER_PT * value / world, 1),
-                           "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4)},
+                           "frac": round(SOLVER_BYTES_PER_PT * value / world / peak, 4),
+                           "frac_of_nominal_8TBs": round(SOLVER_BYTES_PER_PT * value / world / NOMINAL_HBM_GBS, 4)},
                 "stages": stage_tbl}
     if world > 1:
-        sent = 8.0 * npts_loc * (world - 1) / world        # bytes each GPU sends per exchange
-        nv = {"exchange": exchange, "bytes_sent_per_gpu_per_exchange": sent, "peak_GBs_per_direction": 900.0,
-              "measured_peer_copy_GBs": 770.0}
-        if exchange == "p2p":
-            # the stores go over NVLink from inside the y-transform / Thomas kernels: rate = bytes / that kernel's time
-            for nm in ("yfft_fwd", "thomas_z"):
-                if nm in stage_tbl:
-                    nv[nm + "_GBs"] = round(sent / (stage_tbl[nm]["ms"] * 1e-3) / 1e9, 1)
-        for nm in ("exchange_fwd", "exchange_bwd"):
-            if nm in stages:
-                ms = stages[nm][0] / stages[nm][1]
-                nv[nm + "_ms"] = round(ms, 4)
-                if exchange == "nccl":
-                    nv[nm + "_GBs"] = round(sent / (ms * 1e-3) / 1e9, 1)
-        roofline["nvlink"] = nv
+        roofline["nvlink"] = nvlink_figures(stage_tbl, stages, npts_loc, world, exchange)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
