@@ -404,3 +404,30 @@ def bounduvw(cbc, n, bc, nh_d, nh_u, isoutflow, dl, dzc, dzf, u, v, w):
             if isoutflow[ib][q]:
                 _outflow(n, (q + 1) * (-1 if ib == 0 else 1), nh_d, nh_u, dl, dzf, u, v, w)
     return u, v, w
+
+
+def chkdt_dti(n, dli, nh_d, nh_u, dzci, dzfi, u, v, w):
+    """The field reduction of chkdt_sp / chkdt_tw, src/chkdt.f90:62-85 = :150-173 (identical in both): the convective
+    inverse time scale dti = max over cells of (dtix, dtiy, dtiz).  The scalar formulas that follow (:92-110, :180-190) use
+    physical parameters of mod_param and stay on the host.  Oracle groundwork (no CUDA kernel yet)."""
+    nx, ny, nz = n
+    h = nh_u
+    S = lambda a, b: slice(a + h - 1, b + h)               # Fortran range a:b of a (1-nh_u:) dimension
+    c = (S(1, nx), S(1, ny), S(1, nz))
+    sh = lambda f, di, dj, dk: f[S(1 + di, nx + di), S(1 + dj, ny + dj), S(1 + dk, nz + dk)]
+    dzf = np.asarray(dzfi)[nh_d:nh_d + nz][None, None, :]  # dzfi(1:nz)
+    dzc = np.asarray(dzci)[nh_d:nh_d + nz][None, None, :]
+    q = np.float64(0.25)
+    ux = np.abs(u[c])
+    vx = q * np.abs(sh(v, 0, 0, 0) + sh(v, 0, -1, 0) + sh(v, 1, 0, 0) + sh(v, 1, -1, 0))
+    wx = q * np.abs(sh(w, 0, 0, 0) + sh(w, 0, 0, -1) + sh(w, 1, 0, 0) + sh(w, 1, 0, -1))
+    dtix = ux * dli[0] + vx * dli[1] + wx * dzf
+    uy = q * np.abs(sh(u, 0, 0, 0) + sh(u, 0, 1, 0) + sh(u, -1, 1, 0) + sh(u, -1, 0, 0))
+    vy = np.abs(v[c])
+    wy = q * np.abs(sh(w, 0, 0, 0) + sh(w, 0, 1, 0) + sh(w, 0, 1, -1) + sh(w, 0, 0, -1))
+    dtiy = uy * dli[0] + vy * dli[1] + wy * dzf
+    uz = q * np.abs(sh(u, 0, 0, 0) + sh(u, -1, 0, 0) + sh(u, -1, 0, 1) + sh(u, 0, 0, 1))
+    vz = q * np.abs(sh(v, 0, 0, 0) + sh(v, 0, -1, 0) + sh(v, 0, -1, 1) + sh(v, 0, 0, 1))
+    wz = np.abs(w[c])
+    dtiz = uz * dli[0] + vz * dli[1] + wz * dzc
+    return float(max(0.0, dtix.max(), dtiy.max(), dtiz.max()))

@@ -138,3 +138,35 @@ def test_neumann_gradient_and_outflow_is_divergence_free():
            (v[X(i), ys, zs] - v[X(i), X(0):X(n[1] - 1) + 1, zs]) / dl[1] +
            (w[X(i), ys, zs] - w[X(i), ys, X(0):X(n[2] - 1) + 1]) / dl[2])
     assert np.max(np.abs(div)) <= 1e-13
+
+
+@pytest.mark.parametrize("nh_u", [1, 3])
+def test_chkdt_reduction_matches_loop_transcription(nh_u):
+    """chkdt.f90:62-85: the numpy statement against the Fortran loop written out cell by cell"""
+    n, nh_d = (5, 4, 6), 3
+    rng = np.random.default_rng(nh_u)
+    u, v, w = (np.asfortranarray(rng.uniform(-1, 1, tuple(x + 2 * nh_u for x in n))) for _ in range(3))
+    dzci = rng.uniform(5.0, 9.0, n[2] + 2 * nh_d)
+    dzfi = rng.uniform(5.0, 9.0, n[2] + 2 * nh_d)
+    dli = (7.0, 6.0, 8.0)
+    U, V, W = FArr(u, nh_u), FArr(v, nh_u), FArr(w, nh_u)
+    zc = lambda k: dzci[k + nh_d - 1]
+    zf = lambda k: dzfi[k + nh_d - 1]
+    dti = 0.0
+    for k in range(1, n[2] + 1):
+        for j in range(1, n[1] + 1):
+            for i in range(1, n[0] + 1):
+                ux = abs(U[i, j, k])
+                vx = 0.25 * abs(V[i, j, k] + V[i, j - 1, k] + V[i + 1, j, k] + V[i + 1, j - 1, k])
+                wx = 0.25 * abs(W[i, j, k] + W[i, j, k - 1] + W[i + 1, j, k] + W[i + 1, j, k - 1])
+                dtix = ux * dli[0] + vx * dli[1] + wx * zf(k)
+                uy = 0.25 * abs(U[i, j, k] + U[i, j + 1, k] + U[i - 1, j + 1, k] + U[i - 1, j, k])
+                vy = abs(V[i, j, k])
+                wy = 0.25 * abs(W[i, j, k] + W[i, j + 1, k] + W[i, j + 1, k - 1] + W[i, j, k - 1])
+                dtiy = uy * dli[0] + vy * dli[1] + wy * zf(k)
+                uz = 0.25 * abs(U[i, j, k] + U[i - 1, j, k] + U[i - 1, j, k + 1] + U[i, j, k + 1])
+                vz = 0.25 * abs(V[i, j, k] + V[i, j - 1, k] + V[i, j - 1, k + 1] + V[i, j, k + 1])
+                wz = abs(W[i, j, k])
+                dtiz = uz * dli[0] + vz * dli[1] + wz * zc(k)
+                dti = max(dti, dtix, dtiy, dtiz)
+    assert oracle.chkdt_dti(n, dli, nh_d, nh_u, dzci, dzfi, u, v, w) == dti
