@@ -117,11 +117,28 @@ def cpu_sample(case, budget_s, threads=None):
         t_z = time.perf_counter() - t0
         return t_xy / (n1 * n2 * nk) + t_z / (n1 * nj * n3), t_xy + t_z, nk, nj
 
+    def library_fft_rate(nk):
+        """context only: the same x/y transform volume through a production FFT library (scipy.fft = pocketfft, r2c + c2c
+        instead of FluTAS's r2r kinds), all threads -- how far the oracle's own FFT is from a tuned CPU library"""
+        try:
+            import scipy.fft as sf
+            nk = max(1, min(nk, n3))
+            slab = np.asfortranarray(rng.uniform(-1, 1, (n1, n2, nk)))
+            w = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            y = sf.rfft(slab, axis=0, workers=w)
+            y = sf.fft(y, axis=1, workers=w)
+            y = sf.ifft(y, axis=1, workers=w)
+            sf.irfft(y, n=n1, axis=0, workers=w)
+            return round(1.0e-9 * n1 * n2 * nk / (time.perf_counter() - t0), 5)
+        except Exception:
+            return None
+
     per_pt, spent, nk, nj = run(1, 1)                                   # probe
     scale = max(1.0, 0.8 * budget_s / max(spent, 1e-6))
     nk2, nj2 = int(max(1, min(n3, nk * scale))), int(max(1, min(n2, nj * scale)))
     per_pt, spent, nk, nj = run(nk2, nj2)
-    return {"gpts": 1.0e-9 / per_pt, "seconds": spent,
+    return {"gpts": 1.0e-9 / per_pt, "seconds": spent, "library_fft_xy_gpts": library_fft_rate(min(nk, 64)),
             "sample": "x/y transforms on %d of %d z-planes + z solves on %d of %d y-rows of the %dx%dx%d grid, "
                       "per-point costs summed" % (nk, n3, nj, n2, n1, n2, n3),
             "cores": oracle.num_threads()}
@@ -444,6 +461,7 @@ def main():
         c = cpu_sample(case, 15.0)
         cpu = {"value": round(c["gpts"], 5), "unit": "Gpts/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
                "seconds": round(c["seconds"], 1),
+               "library_fft_xy_gpts": c.get("library_fft_xy_gpts"),
                "note": "CPU restatement of solver_cpu.f90 with its own FFT (oracle/), not FluTAS+FFTW"}
 
     line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
