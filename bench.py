@@ -4,11 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
 
 A "step" is one `solver` call (x/y transforms + z tridiagonal solve + inverse transforms) on one
-synthetic right-hand side of the named grid, device resident, in place.  `value` = grid points / step
-time (Gpts/s, whole job).  `e2e` is the same call through the C ABI with HOST (pinned) buffers, i.e.
-including the host->device and device->host copies of p.  `roofline` describes the slowest kernel of
-the solve, timed live with CUDA events on the launching stream; `cpu_baseline` is the CPU oracle
-(a restatement of solver_cpu.f90 -- NOT FluTAS+FFTW, which cannot be built here) on a bounded sample.
+synthetic right-hand side of the named grid, device resident, in place.  Default workload: NS, the north-star
+1024^3 PP/PP/NN channel grid, for every N.  `value` = grid points / step time (Gpts/s, whole job).  `e2e` is the
+same call through the C ABI with HOST (pinned) buffers, i.e. including the host->device and device->host copies of
+p.  `roofline` describes the slowest kernel of the solve, timed live with CUDA events on the launching stream.
+`parity` is measured in the same run: the CUDA pressure step against `oracle.Solver.solve` on the same bytes
+(oracle/parity.py; N > 1: the slab solver against the single-rank oracle).  `cpu_baseline` is that oracle solve (a
+restatement of solver_cpu.f90 -- NOT FluTAS+FFTW, which cannot be built here), all host cores.
+`--impl reference` times real oracle pressure steps (fillps + solver_cpu + correc) on the whole workload.
 """
 import argparse
 import json
@@ -88,84 +91,72 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle on a bounded sample of the workload (per-stage sampling, summed per point)
-def cpu_sample(case, budget_s, threads=None):
-    from oracle import oracle
-    if threads:
-        oracle.set_num_threads(threads)
-    n1, n2, n3 = case.ng
-    s = case.setup
-    rng = np.random.default_rng(0)
-    kfx, kbx, _ = oracle.find_fft(case.cbc[0])
-    kfy, kby, _ = oracle.find_fft(case.cbc[1])
-    periodic = case.cbc[2] == "PP"
-
-    def run(nk, nj):
-        """x/y transforms on nk planes, z solves on nj rows of columns; returns seconds per grid point"""
-        nk, nj = max(1, min(nk, n3)), max(1, min(nj, n2))
-        slab = np.asfortranarray(rng.uniform(-1, 1, (n1, n2, nk)))
-        t0 = time.perf_counter()
-        oracle.r2r(kfx, slab, 0)
-        oracle.r2r(kfy, slab, 1)
-        oracle.r2r(kby, slab, 1)
-        oracle.r2r(kbx, slab, 0)
-        t_xy = time.perf_counter() - t0
-        cols = np.asfortranarray(rng.uniform(-1, 1, (n1, nj, n3)))
-        lam = np.asfortranarray(s.lambdaxy[:, :nj] - 1.0e-3)          # keep every sampled column regular
-        t0 = time.perf_counter()
-        oracle.gaussel(s.a, s.b, s.c, lam, cols, periodic)
-        t_z = time.perf_counter() - t0
-        return t_xy / (n1 * n2 * nk) + t_z / (n1 * nj * n3), t_xy + t_z, nk, nj
-
-    def library_fft_rate(nk):
-        """context only: the same x/y transform volume through a production FFT library (scipy.fft = pocketfft, r2c + c2c
-        instead of FluTAS's r2r kinds), all threads -- how far the oracle's own FFT is from a tuned CPU library"""
-        try:
-            import scipy.fft as sf
-            nk = max(1, min(nk, n3))
-            slab = np.asfortranarray(rng.uniform(-1, 1, (n1, n2, nk)))
-            w = os.cpu_count() or 1
-            t0 = time.perf_counter()
-            y = sf.rfft(slab, axis=0, workers=w)
-            y = sf.fft(y, axis=1, workers=w)
-            y = sf.ifft(y, axis=1, workers=w)
-            sf.irfft(y, n=n1, axis=0, workers=w)
-            return round(1.0e-9 * n1 * n2 * nk / (time.perf_counter() - t0), 5)
-        except Exception:
-            return None
-
-    per_pt, spent, nk, nj = run(1, 1)                                   # probe
-    scale = max(1.0, 0.8 * budget_s / max(spent, 1e-6))
-    nk2, nj2 = int(max(1, min(n3, nk * scale))), int(max(1, min(n2, nj * scale)))
-    per_pt, spent, nk, nj = run(nk2, nj2)
-    return {"gpts": 1.0e-9 / per_pt, "seconds": spent, "library_fft_xy_gpts": library_fft_rate(min(nk, 64)),
-            "sample": "x/y transforms on %d of %d z-planes + z solves on %d of %d y-rows of the %dx%dx%d grid, "
-                      "per-point costs summed" % (nk, n3, nj, n2, n1, n2, n3),
-            "cores": oracle.num_threads()}
+# Reference arm: the CPU oracle (restatement of fillps.f90 / solver_cpu.f90 / correc.f90) on the WHOLE workload, all host
+# threads, real calls inside the timed region.  Under torchrun the launcher exports OMP_NUM_THREADS=1: the thread count
+# is set explicitly.
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from flutas_b200.cases import CONFIGS, Case
+    from flutas_b200.cases import Case
     from oracle import oracle
+    oracle.set_num_threads(host_threads())
     case = Case.from_config(args.workload)
-    n1, n2, n3 = case.ng
-    budget = max(1.0, min(8.0, 150.0 / (args.steps + args.warmup)))
+    s, n = case.setup, case.ng
+    n1, n2, n3 = n
+    npts = n1 * n2 * n3
+    u, v, w = case.velocity()
+    p = case.new_p()
+    solver = oracle.Solver(n, case.cbc[0], case.cbc[1])
+
+    def fillps():
+        oracle.fillps(n, case.nh_d, case.nh_u, s.dli, s.dzfi, case.dti, case.rho0, u, v, w, p)
+        oracle.updt_rhs_b(n, s.rhsbx, s.rhsby, s.rhsbz, p)
+
+    def solve():
+        solver.solve(s.lambdaxy, s.a, s.b, s.c, case.cbc[2], p)
+
+    fillps()
+    rhs = p.copy(order="F")
     for _ in range(args.warmup):
-        cpu_sample(case, budget)
-    vals, t0 = [], time.perf_counter()
+        p[...] = rhs
+        solve()
+    t_solve = []
+    t_wall0 = time.perf_counter()
     for _ in range(args.steps):
-        vals.append(cpu_sample(case, budget))
-    wall = time.perf_counter() - t0
-    gpts = float(np.mean([v["gpts"] for v in vals]))
+        p[...] = rhs                                   # same right-hand side every step (not timed: the GPU arm solves in place too)
+        t0 = time.perf_counter()
+        solve()
+        t_solve.append(time.perf_counter() - t0)
+    wall = time.perf_counter() - t_wall0
+    # the rest of the pressure step, a few repetitions: fillps + updt_rhs_b and correc (on the last solution)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.correc(n, case.nh_d, case.nh_u, s.dli, s.dzci, case.dt, case.rho0, case.boundp(p), u, v, w)
+    t_correc = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fillps()
+    t_fillps = (time.perf_counter() - t0) / reps
+    ms = 1e3 * float(np.mean(t_solve))
+    gpts = npts / (ms * 1e-3) / 1e9
+    sample = "%d full oracle.Solver.solve calls on the %dx%dx%d grid (no sampling)" % (args.steps, n1, n2, n3)
     line = {"impl": "reference", "metric": "poisson_solve_throughput", "value": gpts, "unit": "Gpts/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * n1 * n2 * n3 / (gpts * 1e9), "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(case, args.workload),
-            "cpu_baseline": {"value": gpts, "unit": "Gpts/s", "cores": vals[-1]["cores"], "kind": "port",
-                             "sample": vals[-1]["sample"],
+            "ms_per_pressure_step": ms + 1e3 * (t_fillps + t_correc),
+            "pressure_step": "fillps + updt_rhs_b %.1f ms, solver %.1f ms, boundp + correc %.1f ms" % (1e3 * t_fillps, ms, 1e3 * t_correc),
+            "cpu_baseline": {"value": gpts, "unit": "Gpts/s", "cores": oracle.num_threads(), "kind": "port",
+                             "sample": sample,
                              "note": "CPU restatement of solver_cpu.f90 with its own FFT (oracle/), not FluTAS+FFTW: "
                                      "no Fortran/MPI/FFTW toolchain in this image"},
             "e2e": {"value": gpts, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,8 +201,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="NS")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the oracle run (parity + cpu_baseline keys become null): kernel A/B timing only")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--solver-only", action="store_true",
                     help="time only the solver on a device-generated RHS (large shapes: no host-side velocity fields, "
@@ -251,6 +243,7 @@ def main():
     npts = n1 * n2 * n3g                                # whole job
     npts_loc = n1 * n2 * n3
     exchange = None
+    parity = None
     if args.solver_only:
         ud = vd = wd = None
         dzfi, dzci = s.dzfi, s.dzci
@@ -274,6 +267,13 @@ def main():
         rhs0 = pd.clone()
     else:
         ud, vd, wd = (api.device_field(f) for f in (u, v, w))
+        if world == 1 and not args.no_parity:
+            # parity of the whole pressure step against the CPU oracle on the same bytes (also the cpu_baseline figure)
+            from oracle import oracle, parity as oparity
+            parity = oparity.pressure_step_parity(case, api, oracle, threads=host_threads(), host_fields=(u, v, w),
+                                                  dev_fields=(ud, vd, wd))
+            parity["ok"] = bool(parity["rhs_bit_exact"] and parity["err"] <= 1e-12 and parity["divmax"] <= 1e-12)
+            parity["bar"] = "err <= 1e-12, divmax <= 1e-12, right-hand side bit-exact"
         del u, v, w
         pd = api.device_field(np.zeros((n1 + 2, n2 + 2, n3 + 2), order="F"))
     pl, nf = api.fftini(n, n, (case.cbc[0], case.cbc[1]))
@@ -294,14 +294,24 @@ def main():
                 exchange = "nccl"
         if exchange == "nccl":
             comm.use_nccl_alltoall()
+        comm.use_halo_exchange()                         # z-halo planes of boundp (updthalo, bound.f90:946-1110)
+        if not args.no_parity and not args.solver_only:
+            # the slab solver against the single-rank oracle on the same bytes, every run (+ barrier time-outs)
+            from oracle import oracle, parity as oparity
+            parity = oparity.slab_solver_parity(case, api, comm, oracle, pl, nf, threads=host_threads())
+            parity["ok"] = bool(parity["err"] <= 1e-12 and parity["p2p_barrier_timeouts"] == 0)
+            parity["bar"] = "err <= 1e-12, no cross-GPU barrier time-out"
+    k0 = rank * n3
+    rhsbx = np.asfortranarray(s.rhsbx[:, k0:k0 + n3, :])     # boundary constants of this rank's slab (bound.f90:829-944)
+    rhsby = np.asfortranarray(s.rhsby[:, k0:k0 + n3, :])
+    dzc_loc = np.ascontiguousarray(s.dzc[k0:k0 + n3 + 2 * case.nh_d])
 
     def fill():
         if args.solver_only:
             pd.copy_(rhs0)
             return
         api.fillps(*n, case.nh_d, case.nh_u, *s.dli, dzfi, case.dti, case.rho0, ud, vd, wd, pd)
-        if world == 1:
-            api.updt_rhs_b(*n, case.cbc, s.rhsbx, s.rhsby, s.rhsbz, pd)
+        api.updt_rhs_b(*n, case.cbc, rhsbx, rhsby, s.rhsbz, pd)      # z faces: ranks 0 and N-1 only (library gates them)
 
     def solve(p=None):
         p = pd if p is None else p
@@ -357,8 +367,8 @@ def main():
         line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
                 "scaling": "strong", "dtype": "f64", "data": "synthetic (device-generated uniform RHS, solver only)",
-                "config": dict(workload_config(case, args.workload),
-                               decomposition=("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU"),
+                "config": workload_config(case, args.workload),
+                "decomposition": ("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU",
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                              "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT,
@@ -387,8 +397,7 @@ def main():
     for _ in range(nps):
         fill()
         solve()
-        if world == 1:                                   # ghost cells of p on the device (boundp, bound.f90:146)
-            api.boundp(case.cbc, n, bc0, case.nh_d, 1, s.dl, s.dzc, s.dzf, pd)
+        api.boundp(case.cbc, n, bc0, case.nh_d, 1, s.dl, dzc_loc, dzc_loc, pd)     # ghost cells of p (bound.f90:146); N > 1: z halo over NCCL
         api.correc(*n, case.nh_d, case.nh_u, *s.dli, dzci, case.dt, case.rho0, pd, ud, vd, wd)
     p1.record()
     barrier()
@@ -457,20 +466,24 @@ def main():
         roofline["nvlink"] = nvlink_figures(stage_tbl, stages, npts_loc, world, exchange)
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        c = cpu_sample(case, 15.0)
-        cpu = {"value": round(c["gpts"], 5), "unit": "Gpts/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
-               "seconds": round(c["seconds"], 1),
-               "library_fft_xy_gpts": c.get("library_fft_xy_gpts"),
+    if parity is not None and parity.get("oracle_solve_s"):
+        # the oracle solve of the parity run: ONE full solver_cpu restatement call on the whole workload, all host threads
+        cpu = {"value": round(npts / parity["oracle_solve_s"] / 1e9, 5), "unit": "Gpts/s", "cores": parity["oracle_threads"],
+               "kind": "port", "sample": "1 full oracle.Solver.solve call on the %dx%dx%d grid (the parity run; no sampling)" % ng,
+               "seconds": parity["oracle_solve_s"],
                "note": "CPU restatement of solver_cpu.f90 with its own FFT (oracle/), not FluTAS+FFTW"}
+    if parity is not None:
+        parity = {k: v for k, v in parity.items() if not k.startswith("_")}
 
     line = {"metric": "poisson_solve_throughput", "value": round(value, 3), "unit": "Gpts/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(case, args.workload), decomposition=("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU"),
+            "config": workload_config(case, args.workload),
+            "decomposition": ("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU",
+            "parity": parity,
             "ms_per_pressure_step": round(ms_pressure_step, 4),
-            "pressure_step": ("fillps + updt_rhs_b + solver + boundp + correc, device resident" if world == 1 else
-                              "fillps + solver + correc, device resident (boundp's z-halo exchange not included)"),
+            "pressure_step": "fillps + updt_rhs_b + solver + boundp + correc, device resident" +
+                             ("" if world == 1 else " (boundp's z-halo planes through NCCL send/recv)"),
             "e2e": {"value": round(e2e_val, 4), "unit": "Gpts/s", "h2d_bytes_per_step": pcount * 8,
                     "d2h_bytes_per_step": pcount * 8, "ms_per_step": round(e2e_mean, 3),
                     "path": "flutas_b200_solver with a pinned host p (H2D + 5 kernels + D2H)"},

@@ -7,7 +7,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SO = os.path.join(CSRC, "libflutas_b200.so")
 SOURCES = ["capi.cu", "fft_p2_x.cu", "fft_p2_y.cu", "fft_reg_x_fwd.cu", "fft_reg_x_bwd.cu", "fft_reg_y_fwd.cu",
            "fft_reg_y_bwd.cu"]
-HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "thomas_uni.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h", "reg_fft.cuh", "fft_reg.cuh", "fft_reg.h"]
+HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "thomas_uni.cuh", "thomas_ref.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h", "reg_fft.cuh", "fft_reg.cuh", "fft_reg.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -22,6 +22,10 @@
 #include "thomas_reg.cuh"
 #include "thomas_uni.cuh"
 #include "thomas_tile.cuh"
+#include "thomas_ref.cuh"
+
+#include <algorithm>
+#include <cmath>
 
 using namespace fb;
 
@@ -193,10 +197,26 @@ struct SolverPlan {
   bool cached_periodic = false;
   const double* key_lam = nullptr;
   std::vector<double> key_a, key_b, key_c;
-  double key_lam_samples[3] = {0, 0, 0};
+  std::vector<double> key_lam_sample;
   bool cache_valid = false;
   int thomas_mode = 0;           // 0 = auto, 1 = force generic (tests)
   ThomasArgs z_uniform{};        // scalar coefficients when the z grid is exactly uniform (thomas_reg.cuh)
+  unsigned long long cache_gen = 0;   // bumped whenever the cached coefficients are rebuilt
+  std::vector<double> h_a, h_b, h_c;  // host copies of a, b, c (selection threshold of the reference-order columns)
+  // reference-order solve of the ill-conditioned columns (thomas_ref.cuh)
+  struct RefFix {
+    const double* key_lam = nullptr;
+    long key_ncol = 0;
+    int key_nz = 0, key_singular = -1;
+    bool key_periodic = false;
+    unsigned long long key_gen = 0;
+    double key_tol = -1.0;
+    int nsel = 0;
+    DevBuf col, lam, pin, z, d, piv, p2, den, F;
+    RefTables T{};
+  } ref;
+  unsigned long long lam_win_gen = 0;
+  int lam_win_rank = -1, lam_win_n1l = 0;
   // slab (multi-GPU) state
   DevBuf sendrecv, pencil, lam_win;
   bool p2p = false;
@@ -208,6 +228,7 @@ struct SolverPlan {
   void* peer_base[FB_MAX_RANKS] = {};
   unsigned long long** d_peer_flags = nullptr;
   int* d_err = nullptr;
+  int* h_err = nullptr;          // pinned mirror of d_err, refreshed behind every barrier
   unsigned long long epoch = 0;
 };
 
@@ -314,13 +335,19 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
     same = (int)sp->key_a.size() == nz && !memcmp(sp->key_a.data(), a, sizeof(double) * nz) &&
            !memcmp(sp->key_b.data(), b, sizeof(double) * nz) && !memcmp(sp->key_c.data(), c, sizeof(double) * nz);
   }
-  if (same && !lam_dev) {
-    const long last = (long)n1 * n2 - 1;
-    same = sp->key_lam_samples[0] == lambdaxy[0] && sp->key_lam_samples[1] == lambdaxy[last / 2] &&
-           sp->key_lam_samples[2] == lambdaxy[last];
+  // host lambdaxy: pointer + a strided sample of 256 entries (a caller that refills the same buffer, or a recycled
+  // address of a Python temporary, is caught unless it agrees on all of them; flutas_b200_solver_invalidate is the contract)
+  std::vector<double> lam_sample;
+  if (!lam_dev) {
+    const long nl_ = (long)n1 * n2, step = nl_ > 256 ? nl_ / 256 : 1;
+    for (long q = 0; q < nl_; q += step) lam_sample.push_back(lambdaxy[q]);
+    lam_sample.push_back(lambdaxy[nl_ - 1]);
+    if (same) same = (lam_sample.size() == sp->key_lam_sample.size()) &&
+                     !memcmp(lam_sample.data(), sp->key_lam_sample.data(), lam_sample.size() * sizeof(double));
   }
   if (same) return 0;
   sp->cache_valid = false;
+  sp->cache_gen += 1;
   const size_t nl = (size_t)n1 * n2;
   if (int rc = sp->lam_raw.reserve(nl * sizeof(double))) return rc;
   if (int rc = sp->lam_int.reserve(nl * sizeof(double))) return rc;
@@ -350,16 +377,14 @@ int cache_coefficients(SolverPlan* sp, int nz, const double* lambdaxy, const dou
     CK(cudaMemcpy(hb.data(), b, nz * sizeof(double), cudaMemcpyDefault));
     CK(cudaMemcpy(hc.data(), c, nz * sizeof(double), cudaMemcpyDefault));
     thomas_detect_uniform(nz, ha.data(), hb.data(), hc.data(), periodic, sp->z_uniform);
+    sp->h_a.swap(ha); sp->h_b.swap(hb); sp->h_c.swap(hc);
   }
   sp->cached_nz = nz;
   sp->cached_periodic = periodic;
   sp->key_lam = lambdaxy;
   if (!abc_dev) { sp->key_a.assign(a, a + nz); sp->key_b.assign(b, b + nz); sp->key_c.assign(c, c + nz); }
   else { sp->key_a.clear(); sp->key_b.clear(); sp->key_c.clear(); }
-  if (!lam_dev) {
-    const long last = (long)nl - 1;
-    sp->key_lam_samples[0] = lambdaxy[0]; sp->key_lam_samples[1] = lambdaxy[last / 2]; sp->key_lam_samples[2] = lambdaxy[last];
-  }
+  sp->key_lam_sample = lam_sample;
   sp->cache_valid = true;
   return 0;
 }
@@ -376,7 +401,105 @@ __global__ void scatter_cols_kernel(long ncol, int nz, const double* __restrict_
   og.ptr[q][og.koff + col + ncol * (long)(k - q * og.n3l)] = W[idx];
 }
 
+// Selection threshold of the reference-order columns: |lambda| < 4 max(|a|,|c|) * g_ref_tol (thomas_ref.cuh).
+// FLUTAS_B200_REF_TOL / flutas_b200_debug_ref_tol override it; 0 switches the fix-up off.
+double g_ref_tol = [] { const char* e = getenv("FLUTAS_B200_REF_TOL"); return e ? atof(e) : 1.0e-5; }();
+constexpr int REF_MAX_COLUMNS = 8192;
+constexpr size_t REF_MAX_SMEM = 200 * 1024;
+
+size_t ref_smem_per_warp(int nz) { return (3 * (size_t)RefShape(nz).doubles() + 96) * sizeof(double); }
+
+// (re)builds the tables of the selected columns for the z stage described by (lam, ncol, nz): selection on the host
+// from a copy of the eigenvalues, factors on the device in the reference's operation order (once per plan / layout)
+int ensure_ref(SolverPlan* sp, long ncol, int nz, const double* lam, bool periodic, int singular) {
+  SolverPlan::RefFix& rf = sp->ref;
+  if (rf.key_lam == lam && rf.key_ncol == ncol && rf.key_nz == nz && rf.key_periodic == periodic &&
+      rf.key_singular == singular && rf.key_gen == sp->cache_gen && rf.key_tol == g_ref_tol) return 0;
+  rf.key_lam = lam; rf.key_ncol = ncol; rf.key_nz = nz; rf.key_periodic = periodic; rf.key_singular = singular;
+  rf.key_gen = sp->cache_gen; rf.key_tol = g_ref_tol;
+  rf.nsel = 0;
+  if (!(g_ref_tol > 0.0) || (int)sp->h_a.size() != nz || ref_smem_per_warp(nz) > REF_MAX_SMEM || ncol > 0x7fffffffL) return 0;
+  double amax = 0.0;
+  for (int k = 0; k < nz; ++k) amax = std::max(amax, std::max(std::fabs(sp->h_a[k]), std::fabs(sp->h_c[k])));
+  const double thr = 4.0 * amax * g_ref_tol;
+  std::vector<double> hl((size_t)ncol);
+  CK(cudaMemcpyAsync(hl.data(), lam, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  std::vector<int> sel;
+  for (long q = 0; q < ncol; ++q)
+    if (std::fabs(hl[q]) < thr) sel.push_back((int)q);
+  if ((int)sel.size() > REF_MAX_COLUMNS) {                 // keep the most ill-conditioned ones
+    std::nth_element(sel.begin(), sel.begin() + REF_MAX_COLUMNS, sel.end(),
+                     [&](int x, int y) { return std::fabs(hl[x]) < std::fabs(hl[y]); });
+    sel.resize(REF_MAX_COLUMNS);
+    std::sort(sel.begin(), sel.end());
+  }
+  const int ns = (int)sel.size();
+  if (ns == 0) return 0;
+  std::vector<double> sl(ns);
+  std::vector<unsigned char> pin(ns);
+  for (int q = 0; q < ns; ++q) { sl[q] = hl[sel[q]]; pin[q] = (singular && sl[q] == 0.0) ? 1 : 0; }
+  const size_t tab = (size_t)ns * nz * sizeof(double);
+  if (int rc = rf.col.reserve(ns * sizeof(int))) return rc;
+  if (int rc = rf.lam.reserve(ns * sizeof(double))) return rc;
+  if (int rc = rf.pin.reserve(ns)) return rc;
+  if (int rc = rf.z.reserve(tab)) return rc;
+  if (int rc = rf.d.reserve(tab)) return rc;
+  if (int rc = rf.F.reserve(tab)) return rc;
+  if (int rc = rf.piv.reserve(ns * sizeof(double))) return rc;
+  if (periodic) {
+    if (int rc = rf.p2.reserve(tab)) return rc;
+    if (int rc = rf.den.reserve(ns * sizeof(double))) return rc;
+  }
+  CK(cudaMemcpyAsync(rf.col.p, sel.data(), ns * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(rf.lam.p, sl.data(), ns * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(rf.pin.p, pin.data(), ns, cudaMemcpyHostToDevice, g_stream));
+  RefTables& T = rf.T;
+  T.nsel = ns; T.nz = nz; T.m = periodic ? nz - 1 : nz; T.periodic = periodic ? 1 : 0;
+  const double* abc = sp->abc.as<double>();               // a | b | c exactly as passed by the caller
+  T.a = abc; T.b = abc + nz; T.c = abc + 2 * nz;
+  T.col = rf.col.as<int>(); T.lam = rf.lam.as<double>(); T.pin = rf.pin.as<unsigned char>();
+  T.z = rf.z.as<double>(); T.d = rf.d.as<double>(); T.piv = rf.piv.as<double>();
+  T.p2 = periodic ? rf.p2.as<double>() : nullptr; T.den = periodic ? rf.den.as<double>() : nullptr;
+  ref_factor_kernel<<<(unsigned)((ns + 63) / 64), 64, 0, g_stream>>>(T);
+  LAUNCHED();
+  CK(cudaStreamSynchronize(g_stream));                     // sel / sl / pin leave scope
+  rf.nsel = ns;
+  return 0;
+}
+
+int run_z_main(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular);
+
+// z stage = [reference-order solve of the ill-conditioned columns into a side buffer] + main kernel (all columns, in
+// place or scattered to the peers) + [scatter of the side buffer over the main kernel's result]
 int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
+  if (int rc = ensure_ref(sp, ncol, nz, lam, periodic, singular)) return rc;
+  SolverPlan::RefFix& rf = sp->ref;
+  if (rf.nsel) {
+    const size_t per = ref_smem_per_warp(nz);
+    int warps = (int)(REF_MAX_SMEM / per);
+    warps = warps > 4 ? 4 : warps;
+    static size_t configured = 0;
+    if (per * warps > configured) {
+      CK(cudaFuncSetAttribute(ref_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per * warps)));
+      configured = per * warps;
+    }
+    ref_solve_kernel<<<(unsigned)((rf.nsel + warps - 1) / warps), 32 * warps, per * warps, g_stream>>>(rf.T, ncol, W, rf.F.as<double>());
+    LAUNCHED();
+  }
+  if (int rc = run_z_main(sp, ncol, nz, lam, W, out, periodic, singular)) return rc;
+  if (rf.nsel) {
+    ColGeom og;
+    if (out) og = *out;
+    else { for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = W; og.n3l = nz; og.koff = 0; }
+    const long cnt = (long)rf.nsel * nz;
+    ref_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(rf.T, ncol, rf.F.as<double>(), og);
+    LAUNCHED();
+  }
+  return 0;
+}
+
+int run_z_main(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
   const double* abc = sp->abc.as<double>();
   bool done = false;
   static const bool uni_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_UNI"); return !(e && e[0] == '0'); }();
@@ -439,7 +562,7 @@ struct P2PBlob {                       // what one rank publishes to the others
 // cross-GPU barrier through flag words in peer memory: rank r stores `epoch` into slot r of every
 // peer's flag array, then waits until all slots of its own array have reached `epoch`.
 __global__ void p2p_barrier_kernel(int rank, int nranks, unsigned long long epoch, unsigned long long* own,
-                                   unsigned long long* const* peers, int* err) {
+                                   unsigned long long* const* peers, int* err, long long limit) {
   const int q = threadIdx.x;
   if (q >= nranks) return;
   __threadfence_system();
@@ -449,7 +572,7 @@ __global__ void p2p_barrier_kernel(int rank, int nranks, unsigned long long epoc
   do {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(own + q) : "memory");
     if (v >= epoch) break;
-    if (clock64() - t0 > 4000000000LL) { atomicAdd(err, 1); break; }   // ~2 s: never hang the GPU
+    if (clock64() - t0 > limit) { atomicAdd(err, 1); break; }          // never hang the GPU: the host sees `err`
   } while (true);
 }
 
@@ -596,11 +719,13 @@ int flutas_b200_fftend(void* arrplan[4]) {
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
+  for (DevBuf* b : {&sp->ref.col, &sp->ref.lam, &sp->ref.pin, &sp->ref.z, &sp->ref.d, &sp->ref.piv, &sp->ref.p2, &sp->ref.den, &sp->ref.F}) b->release();
   for (int q = 0; q < FB_MAX_RANKS; ++q)
     if (sp->peer_base[q] && sp->peer_base[q] != sp->p2p_alloc) cudaIpcCloseMemHandle(sp->peer_base[q]);
   if (sp->p2p_alloc) cudaFree(sp->p2p_alloc);
   if (sp->d_peer_flags) cudaFree(sp->d_peer_flags);
   if (sp->d_err) cudaFree(sp->d_err);
+  if (sp->h_err) cudaFreeHost(sp->h_err);
   sp->magic = 0;
   delete sp;
   for (int q = 0; q < 4; ++q) { delete (PlanHandle*)arrplan[q]; arrplan[q] = nullptr; }
@@ -629,6 +754,12 @@ int flutas_b200_debug_thomas_mode(void* const arrplan[4], int mode) {
   if (!sp) return fail(FLUTAS_B200_ERR_ARG, "not a flutas_b200 plan");
   g_z_uniform_ok = (mode != 3);                          // 3 = register kernel with coefficient tables even on a uniform grid
   sp->thomas_mode = (mode == 3) ? 0 : mode;
+  return FLUTAS_B200_OK;
+}
+
+// test hook: selection tolerance of the reference-order columns (0 = off; a huge value selects every column up to the cap)
+int flutas_b200_debug_ref_tol(double tol) {
+  g_ref_tol = tol;
   return FLUTAS_B200_OK;
 }
 
@@ -735,6 +866,7 @@ int flutas_b200_p2p_attach(void* const arrplan[4], const void* blobs) {
   if (!sp->d_peer_flags) CK(cudaMalloc(&sp->d_peer_flags, FB_MAX_RANKS * sizeof(void*)));
   CK(cudaMemcpy(sp->d_peer_flags, sp->peer_flags, FB_MAX_RANKS * sizeof(void*), cudaMemcpyHostToDevice));
   if (!sp->d_err) { CK(cudaMalloc(&sp->d_err, sizeof(int))); CK(cudaMemset(sp->d_err, 0, sizeof(int))); }
+  if (!sp->h_err) { CK(cudaHostAlloc((void**)&sp->h_err, sizeof(int), cudaHostAllocDefault)); *sp->h_err = 0; }
   sp->epoch = 0;
   sp->p2p = true;
   return FLUTAS_B200_OK;
@@ -750,10 +882,19 @@ int flutas_b200_p2p_errors(void* const arrplan[4]) {
   return v;
 }
 
+// A peer that has not arrived after FLUTAS_B200_P2P_TIMEOUT_S seconds (default 10; SM clock taken as 2 GHz) makes the
+// barrier give up and count an error.  The count is mirrored into pinned host memory right behind every barrier, so
+// the NEXT solver_slab call on the plan (and flutas_b200_p2p_errors at any time) fails instead of returning stale data.
 static int p2p_barrier(SolverPlan* sp) {
+  static const long long limit = [] {
+    const char* e = getenv("FLUTAS_B200_P2P_TIMEOUT_S");
+    const double sec = e ? atof(e) : 10.0;
+    return (long long)((sec > 0.01 ? sec : 0.01) * 2.0e9);
+  }();
   sp->epoch += 1;
-  p2p_barrier_kernel<<<1, 32, 0, g_stream>>>(g_rank, g_nranks, sp->epoch, sp->peer_flags[g_rank], sp->d_peer_flags, sp->d_err);
+  p2p_barrier_kernel<<<1, 32, 0, g_stream>>>(g_rank, g_nranks, sp->epoch, sp->peer_flags[g_rank], sp->d_peer_flags, sp->d_err, limit);
   LAUNCHED();
+  if (sp->h_err) CK(cudaMemcpyAsync(sp->h_err, sp->d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   return 0;
 }
 
@@ -778,10 +919,14 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   const bool xysing = (sp->bcxy[0] != 'D' && sp->bcxy[2] != 'D');
   const int singular = (zsing && xysing) ? 1 : 0;
 
-  const bool was_valid = sp->cache_valid;
+  if (sp->p2p && sp->h_err && *sp->h_err)
+    return fail(FLUTAS_B200_ERR_CUDA, "solver_slab: %d cross-GPU barrier time-out(s) in an earlier solve on this plan -- a peer did not "
+                "arrive within the limit (FLUTAS_B200_P2P_TIMEOUT_S); the pressure of that solve is invalid", *sp->h_err);
   if (int rc = cache_coefficients(sp, ng3, lambdaxy_global, a, b, c, periodic)) return rc;
   const size_t chunk = (size_t)n1l * n2 * n3l, nloc = chunk * P;
-  if (!was_valid || !sp->cache_valid || sp->lam_win.cap < (size_t)n1l * n2 * sizeof(double)) {
+  if (sp->lam_win_gen != sp->cache_gen || sp->lam_win_rank != r || sp->lam_win_n1l != n1l ||
+      sp->lam_win.cap < (size_t)n1l * n2 * sizeof(double)) {
+    sp->lam_win_gen = sp->cache_gen; sp->lam_win_rank = r; sp->lam_win_n1l = n1l;
     if (int rc = sp->lam_win.reserve((size_t)n1l * n2 * sizeof(double))) return rc;
     // this rank's x rows of the permuted eigenvalues: lam_win(i_l, ry) = lam_int(r*n1l + i_l, ry); constant until the
     // coefficient cache is invalidated
@@ -943,6 +1088,8 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   if (host_p) {
     CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
+    if (sp->p2p && sp->h_err && *sp->h_err)
+      return fail(FLUTAS_B200_ERR_CUDA, "solver_slab: cross-GPU barrier time-out (%d): a peer did not arrive; p is invalid", *sp->h_err);
   }
   return FLUTAS_B200_OK;
 }
@@ -1012,8 +1159,13 @@ int flutas_b200_updt_rhs_b(int nx, int ny, int nz, const char cbc[6], const doub
     LAUNCHED();
   }
   if (cbc[4] != 'P' || cbc[5] != 'P') {
-    updt_rhs_b_z_kernel<<<(unsigned)((cz / 2 + 255) / 256), 256, 0, g_stream>>>(g, rz, fp.dev);
-    LAUNCHED();
+    // z-slab decomposition (flutas_b200_init): the z faces belong to ranks 0 and nranks-1 only -- on the others the
+    // neighbour is a rank, not MPI_PROC_NULL (bound.f90:915,929); x and y are never decomposed in this layout
+    const int sides = (g_nranks == 1) ? 3 : ((g_rank == 0 ? 1 : 0) | (g_rank == g_nranks - 1 ? 2 : 0));
+    if (sides) {
+      updt_rhs_b_z_kernel<<<(unsigned)((cz / 2 + 255) / 256), 256, 0, g_stream>>>(g, rz, fp.dev, sides);
+      LAUNCHED();
+    }
   }
   if (int rc = stage_out(fp)) return rc;
   if (fp.staged) CK(cudaStreamSynchronize(g_stream));

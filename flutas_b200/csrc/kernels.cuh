@@ -335,13 +335,14 @@ __global__ void updt_rhs_b_y_kernel(StencilGeom g, const double* __restrict__ ry
     p[pidx(g, i, ny, k)] += ry[idx + (long)nx * nz];
   }
 }
-__global__ void updt_rhs_b_z_kernel(StencilGeom g, const double* __restrict__ rz, double* __restrict__ p) {
+// sides: bit 0 = this rank owns the bottom wall (bottom == MPI_PROC_NULL, bound.f90:915), bit 1 = the top wall (:929)
+__global__ void updt_rhs_b_z_kernel(StencilGeom g, const double* __restrict__ rz, double* __restrict__ p, int sides) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nx = g.nx, ny = g.ny, nz = g.nz;
   if (idx < (long)nx * ny) {
     const int i = (int)(idx % nx) + 1, j = (int)(idx / nx) + 1;
-    p[pidx(g, i, j, 1)] += rz[idx];
-    p[pidx(g, i, j, nz)] += rz[idx + (long)nx * ny];
+    if (sides & 1) p[pidx(g, i, j, 1)] += rz[idx];
+    if (sides & 2) p[pidx(g, i, j, nz)] += rz[idx + (long)nx * ny];
   }
 }
 

@@ -38,6 +38,7 @@ def load():
     L.flutas_b200_solver_invalidate.argtypes = [C.POINTER(vp)]
     L.flutas_b200_debug_thomas_mode.argtypes = [C.POINTER(vp), ci]
     L.flutas_b200_debug_generic_fft.argtypes = [ci]
+    L.flutas_b200_debug_ref_tol.argtypes = [cd]
     L.flutas_b200_fillps.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp]
     L.flutas_b200_updt_rhs_b.argtypes = [ci] * 3 + [cc, vp, vp, vp, vp]
     L.flutas_b200_correc.argtypes = [ci] * 5 + [cd] * 3 + [vp, cd, cd, vp, vp, vp, vp, vp]

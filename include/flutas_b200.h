@@ -107,8 +107,10 @@ int flutas_b200_fillps(int nx, int ny, int nz, int nh_d, int nh_u, double dxi, d
                        const double *dzfi, double dti, double rho0, const double *u, const double *v,
                        const double *w, double *p);
 
-/* updt_rhs_b, src/bound.f90:829-944, for a rank that owns all six faces (cell-centred).
- * cbc(0:1,3) as six characters; rhsbx(ny,nz,0:1), rhsby(nx,nz,0:1), rhsbz(nx,ny,0:1). */
+/* updt_rhs_b, src/bound.f90:829-944 (cell-centred).  cbc(0:1,3) as six characters; rhsbx(ny,nz,0:1), rhsby(nx,nz,0:1),
+ * rhsbz(nx,ny,0:1) with the LOCAL sizes.  On a z-slab decomposition (flutas_b200_init with nranks > 1) the x and y
+ * faces are applied on every rank and the z faces only where the reference's neighbour is MPI_PROC_NULL (:915,929):
+ * the bottom one on rank 0, the top one on rank nranks-1. */
 int flutas_b200_updt_rhs_b(int nx, int ny, int nz, const char cbc[6], const double *rhsbx,
                            const double *rhsby, const double *rhsbz, double *p);
 

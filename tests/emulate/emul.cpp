@@ -433,3 +433,55 @@ extern "C" int emul_reg_mode_index(int N, int kind, int* mode) {
   std::memcpy(mode, hp.mode.data(), sizeof(int) * (size_t)N);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// reference-order solve of the ill-conditioned columns (flutas_b200/csrc/thomas_ref.cuh): same selection rule as
+// capi.cu's ensure_ref, same per-lane phase functions as ref_solve_kernel run serially over the 32 lanes of a warp.
+// Overwrites the selected columns of W (ncol x nz); returns the number of selected columns.
+#include "../../flutas_b200/csrc/thomas_ref.cuh"
+
+extern "C" int emul_thomas_ref(int nz, long ncol, int periodic, int singular, const double* a, const double* b,
+                               const double* c, const double* lam, double* W, double tol) {
+  double amax = 0.0;
+  for (int k = 0; k < nz; ++k) amax = std::fmax(amax, std::fmax(std::fabs(a[k]), std::fabs(c[k])));
+  const double thr = 4.0 * amax * tol;
+  std::vector<int> sel;
+  for (long q = 0; q < ncol; ++q) if (std::fabs(lam[q]) < thr) sel.push_back((int)q);
+  const int ns = (int)sel.size();
+  if (!ns) return 0;
+  std::vector<double> sl(ns), z((size_t)ns * nz), d((size_t)ns * nz), piv(ns), p2((size_t)ns * nz), den(ns);
+  std::vector<unsigned char> pin(ns);
+  for (int q = 0; q < ns; ++q) { sl[q] = lam[sel[q]]; pin[q] = (singular && sl[q] == 0.0) ? 1 : 0; }
+  RefTables R;
+  R.nsel = ns; R.nz = nz; R.m = periodic ? nz - 1 : nz; R.periodic = periodic;
+  R.a = a; R.b = b; R.c = c; R.col = sel.data(); R.lam = sl.data(); R.pin = pin.data();
+  R.z = z.data(); R.d = d.data(); R.piv = piv.data(); R.p2 = p2.data(); R.den = den.data();
+  for (int q = 0; q < ns; ++q) ref_factor(R, q);
+  const RefShape S(nz);
+  std::vector<double> p(S.doubles(), std::nan("")), zs(S.doubles(), std::nan("")), ds(S.doubles(), std::nan(""));
+  double PA[32], PB[32], IN[32];
+  const int n = nz, m = R.m;
+  for (int q = 0; q < ns; ++q) {
+    const long col = sel[q];
+    for (int l = 0; l < n; ++l) {
+      const int o = S.at(l);
+      p[o] = W[col + ncol * (long)l];
+      if (l < m - 1) { zs[o] = z[(size_t)q * n + l]; ds[o] = d[(size_t)q * n + l]; }
+    }
+    for (int lane = 0; lane < 32; ++lane) ref_fwd_local(R, S, p.data(), zs.data(), lane, PA, PB);
+    ref_chain_up(PA, PB, IN, 0.0);
+    for (int lane = 0; lane < 32; ++lane) ref_fwd_final(R, S, p.data(), zs.data(), lane, IN[lane]);
+    const double xm = ref_last_row(R, S, p.data(), q, pin[q] && !periodic);
+    for (int lane = 0; lane < 32; ++lane) ref_bwd_local(R, S, p.data(), ds.data(), lane, PA, PB);
+    ref_chain_down(PA, PB, IN, xm);
+    for (int lane = 0; lane < 32; ++lane) ref_bwd_final(R, S, p.data(), ds.data(), lane, IN[lane]);
+    if (periodic) {
+      const double pn = ref_closure(R, S, p.data(), q, pin[q] != 0);
+      for (int l = 0; l < m; ++l) W[col + ncol * (long)l] = FB_XADD(p[S.at(l)], FB_XMUL(p2[(size_t)q * n + l], pn));
+      W[col + ncol * (long)(n - 1)] = pn;
+    } else {
+      for (int l = 0; l < n; ++l) W[col + ncol * (long)l] = p[S.at(l)];
+    }
+  }
+  return ns;
+}

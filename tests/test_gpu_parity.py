@@ -101,6 +101,28 @@ def test_solver_matches_oracle(name, ng, cbc, lengths, gr, device, generic_fft):
     assert err <= TOL, err
 
 
+@pytest.mark.parametrize("name,ng,cbc,lengths,gr", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("ref_tol", [0.0, 1.0e300], ids=["ref-off", "ref-all"])
+def test_reference_order_columns(name, ng, cbc, lengths, gr, ref_tol):
+    """thomas_ref.cuh: the z stage with the reference-order fix-up switched off and with EVERY column routed through it
+    (up to its cap of 8192 columns) must both meet the parity bar on these (well-conditioned) cases."""
+    case = Case(ng, cbc, lengths, gr=gr, seed=4242 + len(name), name=name)
+    s = case.setup
+    u, v, w = case.velocity()
+    rhs_p = case.new_p()
+    oracle.fillps(ng, case.nh_d, case.nh_u, s.dli, s.dzfi, case.dti, case.rho0, u, v, w, rhs_p)
+    rhs = rhs_p[1:-1, 1:-1, 1:-1].copy(order="F")
+    pref = rhs_p.copy(order="F")
+    oracle.Solver(ng, cbc[0], cbc[1]).solve(s.lambdaxy, s.a, s.b, s.c, cbc[2], pref)
+    lib.check(lib.load().flutas_b200_debug_ref_tol(ref_tol))
+    try:
+        p = _solve_gpu(case, rhs, device=True)
+    finally:
+        lib.load().flutas_b200_debug_ref_tol(1.0e-5)
+    err = gauge_rel_err(p[1:-1, 1:-1, 1:-1], pref[1:-1, 1:-1, 1:-1], case.singular)
+    assert err <= TOL, err
+
+
 @pytest.mark.parametrize("nh_u", [1, 3])
 @pytest.mark.parametrize("cbc", [("PP", "PP", "PP"), ("PP", "PP", "NN"), ("NN", "NN", "NN"), ("DD", "NN", "PP")],
                          ids=lambda c: "".join(c))

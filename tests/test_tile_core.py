@@ -21,10 +21,10 @@ def emul():
     so = os.path.join(HERE, "emulate", "libemul.so")
     deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f)
                     for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "reg_fft.cuh", "thomas_uni.cuh",
-                              "thomas_hier.cuh")]
+                              "thomas_hier.cuh", "thomas_ref.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+        subprocess.check_call([cxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.emul_line_transform.argtypes = [C.c_int] * 6 + [_dp, _dp, C.c_double]
     L.emul_mode_index.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
