@@ -274,7 +274,7 @@ int run_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst, Li
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "xfft_reg launch failed: %s", cudaGetErrorString(e));
     return 0;
   }
-  if (g_fft_level != 1 && p2_tile_width(lp.d.N)) {
+  if (g_fft_level != 1 && p2_tile_width(lp.d.N) && !kind_is_iv(lp.d.kind)) {   // (types IV: generic tile kernels only)
     cudaError_t e = p2_run_x(FWD, lp.d, src, gs, dst, gd, scale, g_stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "xfft_p2 launch failed: %s", cudaGetErrorString(e));
@@ -304,7 +304,7 @@ int run_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& sg)
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_reg launch failed: %s", cudaGetErrorString(e));
     return 0;
   }
-  if (g_fft_level != 1 && p2_tile_width(lp.d.N)) {
+  if (g_fft_level != 1 && p2_tile_width(lp.d.N) && !kind_is_iv(lp.d.kind)) {
     cudaError_t e = p2_run_y(FWD, lp.d, W, n1, n3, sg, g_stream);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) return fail(FLUTAS_B200_ERR_CUDA, "yfft_p2 launch failed: %s", cudaGetErrorString(e));
@@ -681,8 +681,8 @@ int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], c
     return fail(FLUTAS_B200_ERR_UNSUPPORTED, "only cell-centred ('c') transforms are on this path (FluTAS passes 'c','c','c')");
   const int kx = kind_from_bc(bcxy[0], bcxy[1]), ky = kind_from_bc(bcxy[2], bcxy[3]);
   if (kx < 0 || ky < 0)
-    return fail(FLUTAS_B200_ERR_UNSUPPORTED, "pressure BC pair %c%c/%c%c: only PP, NN, DD are available on the GPU path "
-                "(same restriction as src/fft.f90:879-883)", bcxy[0], bcxy[1], bcxy[2], bcxy[3]);
+    return fail(FLUTAS_B200_ERR_UNSUPPORTED, "pressure BC pair %c%c/%c%c: the transform table of src/fft.f90:233-291 has "
+                "PP, NN, DD, ND, DN only (sanity.f90:212-222)", bcxy[0], bcxy[1], bcxy[2], bcxy[3]);
   if (int rc = ensure_device()) return rc;
   SolverPlan* sp = new SolverPlan();
   sp->n1 = n_x[0]; sp->n2 = n_y[1];

@@ -17,18 +17,24 @@ namespace fb {
 template <int TB, bool ROT, bool FWD>
 __device__ __forceinline__ void tile_transform(double* tile, const LinePlan& P, const cpx* wM, int lane, int worker,
                                                int nworkers) {
+  const bool iv = kind_is_iv(P.kind);                     // ND / DN (REDFT11 / RODFT11): pre- and post-twiddle instead of a split
+  const TileAcc<TB, ROT> acc{tile, P.M, lane};
   if (FWD) {
+    if (iv) { iv_pre<true>(P.M, P.kind, P.wQ, P.pos, worker, nworkers, acc); __syncthreads(); }
     for (int q = 0; q < P.npass; ++q) {
       fft_pass<TB, ROT, true>(tile, P, wM, q, lane, worker, nworkers);
       __syncthreads();
     }
-    split_fwd<TB, ROT>(tile, P, lane, worker, nworkers);
+    if (iv) iv_post<true>(P.M, P.kind, P.wN, P.pos, worker, nworkers, acc);
+    else split_fwd<TB, ROT>(tile, P, lane, worker, nworkers);
   } else {
-    merge_bwd<TB, ROT>(tile, P, lane, worker, nworkers);
+    if (iv) iv_pre<false>(P.M, P.kind, P.wQ, P.pos, worker, nworkers, acc);
+    else merge_bwd<TB, ROT>(tile, P, lane, worker, nworkers);
     for (int q = P.npass - 1; q >= 0; --q) {
       __syncthreads();
       fft_pass<TB, ROT, false>(tile, P, wM, q, lane, worker, nworkers);
     }
+    if (iv) { __syncthreads(); iv_post<false>(P.M, P.kind, P.wN, P.pos, worker, nworkers, acc); }
   }
   __syncthreads();
 }

@@ -34,6 +34,8 @@ inline int kind_from_bc(char b0, char b1) {
   if (b0 == 'P' && b1 == 'P') return KIND_PP;
   if (b0 == 'N' && b1 == 'N') return KIND_NN;
   if (b0 == 'D' && b1 == 'D') return KIND_DD;
+  if (b0 == 'N' && b1 == 'D') return KIND_ND;             // REDFT11 both ways (src/fft.f90:256-259)
+  if (b0 == 'D' && b1 == 'N') return KIND_DN;             // RODFT11 both ways (:260-263)
   return -1;
 }
 
@@ -53,10 +55,17 @@ inline HostLinePlan make_line_plan(int N, int kind) {
   for (int r : hp.radix) { prod *= r; hp.sub.push_back(M / prod); }
   hp.wM.resize(M > 0 ? M : 1);
   for (int k = 0; k < M; ++k) hp.wM[k] = unit_root(2.0L * k, (long double)M);
-  hp.wN.resize(M / 2 + 1);
-  for (int k = 0; k <= M / 2; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
-  hp.wQ.resize(M + 1);
-  for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  if (kind_is_iv(kind)) {                                 // post-twiddle e^{-i pi k/N}, pre-twiddle e^{-i pi (4m+1)/(4N)}
+    hp.wN.resize(M);
+    for (int k = 0; k < M; ++k) hp.wN[k] = unit_root((long double)k, (long double)N);
+    hp.wQ.resize(M + 1);
+    for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root(4.0L * k + 1.0L, 4.0L * N);
+  } else {
+    hp.wN.resize(M / 2 + 1);
+    for (int k = 0; k <= M / 2; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
+    hp.wQ.resize(M + 1);
+    for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  }
   hp.pos.resize(M);
   for (int k = 0; k < M; ++k) {                           // k = t0 + r0 (t1 + r1 (t2 + ...)) -> sum t_q sub_q
     int kk = k, p = 0;
@@ -68,6 +77,7 @@ inline HostLinePlan make_line_plan(int N, int kind) {
     const int r = hp.pos[k];
     int q0 = k, q1 = (k == 0) ? M : N - k;                // part 0 / part 1 content (see split_fwd)
     if (kind == KIND_DD) { q0 = N - 1 - q0; q1 = N - 1 - q1; }
+    if (kind_is_iv(kind)) { q0 = 2 * k; q1 = N - 1 - 2 * k; }   // rows (Y_{2k}, Y_{N-1-2k}), see iv_post
     hp.mode[r] = q0;
     hp.mode[M + r] = q1;
   }
@@ -123,9 +133,14 @@ inline HostRegPlan make_reg_plan(int N, int kind) {
   }
   const int M = hp.M;
   hp.wN.resize(M);
-  for (int k = 0; k < M; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
   hp.wQ.resize(M + 1);
-  for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  if (kind_is_iv(kind)) {
+    for (int k = 0; k < M; ++k) hp.wN[k] = unit_root((long double)k, (long double)N);
+    for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root(4.0L * k + 1.0L, 4.0L * N);
+  } else {
+    for (int k = 0; k < M; ++k) hp.wN[k] = unit_root(2.0L * k, (long double)N);
+    for (int k = 0; k <= M; ++k) hp.wQ[k] = unit_root((long double)k, 2.0L * N);
+  }
   hp.mode.resize(N);
   for (int r = 0; r < N; ++r) hp.mode[r] = reg_mode_index(N, kind, r);
   hp.ok = true;

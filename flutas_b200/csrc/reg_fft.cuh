@@ -60,6 +60,7 @@ FB_CX bool reg_fft_supported(int N) {
 // which FFTW mode (index into the reference's eigenvalue array, 0-based) sits in spectral row r
 FB_HD int reg_mode_index(int N, int kind, int r) {
   const int M = N / 2, k = r >> 1;
+  if (kind_is_iv(kind)) return (r & 1) ? N - 1 - 2 * k : 2 * k;     // rows (Y_{2k}, Y_{N-1-2k})
   int q = (r & 1) ? ((k == 0) ? M : N - k) : k;
   if (kind == KIND_DD) q = N - 1 - q;
   return q;

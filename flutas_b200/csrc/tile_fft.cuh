@@ -33,7 +33,13 @@ namespace fb {
 
 struct cpx { double x, y; };
 
-enum LineKind { KIND_PP = 0, KIND_NN = 1, KIND_DD = 2 };
+// PP: R2HC/HC2R; NN: REDFT10/01, DD: RODFT10/01 (Makhoul through the real FFT); ND: REDFT11, DN: RODFT11 (types IV:
+// one transform for both directions, src/fft.f90:256-263), computed as  z_m = x_{2m} + i x_{N-1-2m},
+// v_m = z_m e^{-i pi (4m+1)/(4N)}, V = FFT_{N/2}(v), w_k = V_k e^{-i pi k/N}, Y_{2k} = 2 Re w_k, Y_{N-1-2k} = -2 Im w_k;
+// RODFT11(x)_k = (-1)^k REDFT11(reversed x)_k.
+enum LineKind { KIND_PP = 0, KIND_NN = 1, KIND_DD = 2, KIND_ND = 3, KIND_DN = 4 };
+FB_CX bool kind_is_iv(int kind) { return kind == KIND_ND || kind == KIND_DN; }
+FB_CX bool kind_is_makhoul(int kind) { return kind == KIND_NN || kind == KIND_DD; }
 enum { FB_MAX_PASS = 12 };
 
 // Device-visible description of one transform length/kind (tables live in global memory).
@@ -73,6 +79,12 @@ FB_HD int taddr(int m, int part, int M, int lane) {
 FB_HD void elem_to_slot(int kind, int N, int e, int& m, int& part, double& sgn) {
   int v = e;
   sgn = 1.0;
+  if (kind_is_iv(kind)) {                      // type IV: z_m = x_{2m} + i x_{N-1-2m}; DN: the line reversed
+    const bool odd = (e & 1);
+    m = odd ? (N - 1 - e) >> 1 : e >> 1;
+    part = (odd != (kind == KIND_DN)) ? 1 : 0;
+    return;
+  }
   if (kind != KIND_PP) {                       // Makhoul: v(n)=x(2n), v(N-1-n)=x(2n+1)  (fft.f90:431-444)
     v = (e & 1) ? (N - 1 - (e >> 1)) : (e >> 1);
     if (kind == KIND_DD && (e & 1)) sgn = -1.0;   // DST-II/III via sign flip of odd inputs (fft.f90:417-428,859-875)
@@ -179,6 +191,12 @@ struct TileAcc {
 FB_HD void slot_to_elem(int kind, int N, int v, int& e, double& sgn) {
   e = v;
   sgn = 1.0;
+  if (kind_is_iv(kind)) {
+    const int m = v >> 1;
+    const bool second = ((v & 1) != 0) != (kind == KIND_DN);
+    e = second ? N - 1 - 2 * m : 2 * m;
+    return;
+  }
   if (kind != KIND_PP) {
     e = (2 * v < N) ? 2 * v : 2 * (N - 1 - v) + 1;
     if (kind == KIND_DD && (e & 1)) sgn = -1.0;
@@ -393,6 +411,39 @@ FB_HD void merge_core(int M, int kind, const cpx* wN, const cpx* wQ, const int* 
     const double tr = -ci, ti = cr;                                       // i * (.)
     dst.st(pk, sr + tr, si + ti);
     dst.st(pj, sr - tr, -(si - ti));
+  }
+}
+
+// ---- type IV (ND / DN): no split -- a pre-twiddle before and a post-twiddle after the complex FFT, both directions.
+// wQ[m] = e^{-i pi (4m+1)/(4N)}, wN[k] = e^{-i pi k/N} (M entries each for these kinds).
+// iv_pre (natural slot order): slot m <- z_m wQ[m]; BWD: the spectrum sits digit-reversed (slot pos[m]), the row pair is
+// (Y_{2m}, Y_{N-1-2m}) (DN: swapped), and the DIT passes that follow compute the +i transform: feed conj(v).
+template <bool FWD, class ACC>
+FB_HD void iv_pre(int M, int kind, const cpx* wQ, const int* pos, int worker, int nworkers, const ACC& acc) {
+  for (int m = worker; m < M; m += nworkers) {
+    const int sl = FWD ? m : pos[m];
+    double zr, zi;
+    acc.ld(sl, zr, zi);
+    if (!FWD && kind == KIND_DN) { const double t = zr; zr = zi; zi = t; }
+    const cpx w = wQ[m];
+    const double vr = zr * w.x - zi * w.y, vi = zr * w.y + zi * w.x;
+    acc.st(sl, vr, FWD ? vi : -vi);
+  }
+}
+// iv_post: FWD: mode k sits at slot pos[k] (DIF output); BWD: at slot k, conjugated (DIT of the conjugate).
+// (a, b) = (2 Re w, -2 Im w): FWD rows (Y_{2k}, Y_{N-1-2k}); BWD elements (x_{2k}, x_{N-1-2k}); DN: second sign +, and the
+// physical pair is stored swapped (the tile's part 0 is element N-1-2k of a reversed line).
+template <bool FWD, class ACC>
+FB_HD void iv_post(int M, int kind, const cpx* wN, const int* pos, int worker, int nworkers, const ACC& acc) {
+  for (int k = worker; k < M; k += nworkers) {
+    const int sl = FWD ? pos[k] : k;
+    double vr, vi;
+    acc.ld(sl, vr, vi);
+    if (!FWD) vi = -vi;
+    const cpx w = wN[k];
+    const double a = 2.0 * (vr * w.x - vi * w.y), b = -2.0 * (vr * w.y + vi * w.x);
+    if (kind == KIND_DN) { if (FWD) acc.st(sl, a, -b); else acc.st(sl, -b, a); }
+    else acc.st(sl, a, b);
   }
 }
 

@@ -51,9 +51,10 @@ int flutas_b200_synchronize(void);
 
 /* fftini, src/fft.f90:24-157.  n_x, n_y: x- and y-pencil sizes (mod_common_mpi); bcxy(0:1,2) as four
  * characters x0,x1,y0,y1; c_or_f(2).  Fills arrplan(2,2) (Fortran order: fwd-x, bwd-x, fwd-y, bwd-y)
- * with opaque handles and normfft exactly as :71,87,125,150.  Supported: 'c' with PP, NN, DD
- * (the set the reference's own GPU path supports, src/fft.f90:879-883) and even lengths whose half
- * factors into 2,3,5. */
+ * with opaque handles and normfft exactly as :71,87,125,150.  Supported: 'c' with every BC pair of the
+ * reference's table (src/fft.f90:233-291: PP -> R2HC/HC2R, NN -> REDFT10/01, DD -> RODFT10/01,
+ * ND -> REDFT11, DN -> RODFT11; the reference's own GPU path stops at PP/NN/DD, :879-883) and even
+ * lengths whose half factors into 2,3,5. */
 int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], const char c_or_f[2],
                        void *arrplan[4], double *normfft);
 
