@@ -303,6 +303,15 @@ def main():
             parity = oparity.slab_solver_parity(case, api, comm, oracle, pl, nf, threads=host_threads())
             parity["ok"] = bool(parity["err"] <= 1e-12 and parity["p2p_barrier_timeouts"] == 0)
             parity["bar"] = "err <= 1e-12, no cross-GPU barrier time-out"
+    slab_schedule = None
+    if world > 1 and exchange == "p2p" and not os.environ.get("FLUTAS_B200_PIPE"):
+        # plan-time measurement of the forward-half pipelining (x transform of k-chunk c+1 under the y transform + NVLink
+        # stores of chunk c), collectively on all ranks; FLUTAS_B200_PIPE=<chunks> pins it instead
+        tune_p = torch.zeros((n3 + 2, n2 + 2, n1 + 2), dtype=torch.float64, device="cuda")
+        best, times = comm.autotune(lambda: comm.solver(n, pl, nf, lam_win, s.a, s.b, s.c, case.cbc[2], "ccc", tune_p))
+        del tune_p
+        slab_schedule = {"pipe_chunks": best[0], "pipe_xsm_pct": best[1],
+                         "candidates_ms": {"%d/%d" % k: round(v, 4) for k, v in times.items()}}
     k0 = rank * n3
     rhsbx = np.asfortranarray(s.rhsbx[:, k0:k0 + n3, :])     # boundary constants of this rank's slab (bound.f90:829-944)
     rhsby = np.asfortranarray(s.rhsby[:, k0:k0 + n3, :])
@@ -371,6 +380,7 @@ def main():
                 "scaling": "strong", "dtype": "f64", "data": "synthetic (device-generated uniform RHS, solver only)",
                 "config": workload_config(case, args.workload),
                 "decomposition": ("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU",
+                "slab_schedule": slab_schedule,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                              "solver": {"bytes_per_pt": SOLVER_BYTES_PER_PT,
@@ -482,6 +492,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(case, args.workload),
             "decomposition": ("z-slabs over %d GPUs, exchange=%s" % (world, exchange)) if world > 1 else "single GPU",
+            "slab_schedule": slab_schedule,
             "parity": parity,
             "ms_per_pressure_step": round(ms_pressure_step, 4),
             "pressure_step": "fillps + updt_rhs_b + solver + boundp + correc, device resident" +

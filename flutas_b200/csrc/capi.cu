@@ -548,6 +548,10 @@ int run_z_main(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, 
 }
 
 // ---- multi-GPU slab exchange ------------------------------------------------------------------
+// schedule knobs of flutas_b200_solver_slab (flutas_b200_slab_config; defaults from the environment)
+int g_pipe_chunks = [] { const char* e = getenv("FLUTAS_B200_PIPE"); return e ? atoi(e) : FB_PIPE_DEFAULT; }();
+int g_pipe_xsm = [] { const char* e = getenv("FLUTAS_B200_PIPE_XSM"); return e ? atoi(e) : 50; }();
+int g_zcopy = [] { const char* e = getenv("FLUTAS_B200_ZCOPY"); return e ? atoi(e) : -1; }();
 flutas_b200_alltoall_fn g_a2a = nullptr;
 void* g_a2a_ctx = nullptr;
 flutas_b200_halo_fn g_halo = nullptr;
@@ -819,6 +823,17 @@ int flutas_b200_set_alltoall(flutas_b200_alltoall_fn fn, void* ctx) {
   return FLUTAS_B200_OK;
 }
 
+// Schedule of the slab solver: pipe_chunks = number of k-chunks of the pipelined forward half (x transform of chunk c+1
+// under the y transform + NVLink stores of chunk c; 0/1 = off), pipe_xsm_pct = share of the SMs given to the x kernels,
+// zcopy = 1 / 0 forces the copy-engine / fused backward exchange (-1 = the built-in rule).  A negative value leaves a
+// knob unchanged.  All ranks must use the same values (the host layer tunes them collectively: SlabComm.autotune).
+int flutas_b200_slab_config(int pipe_chunks, int pipe_xsm_pct, int zcopy) {
+  if (pipe_chunks >= 0) g_pipe_chunks = pipe_chunks;
+  if (pipe_xsm_pct >= 0) g_pipe_xsm = pipe_xsm_pct;
+  if (zcopy >= -1 && zcopy <= 1) g_zcopy = zcopy;
+  return FLUTAS_B200_OK;
+}
+
 size_t flutas_b200_p2p_handle_bytes(void) { return sizeof(P2PBlob); }
 
 // Allocates this rank's exchange memory [pencil | recv | flags] and returns its IPC handle in `blob`.
@@ -963,8 +978,8 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   // of the SMs given to the x kernels.  Measured at 2 GPUs (profiles/r01_pipe_forward_N2.log): 512^3 1.560 -> 1.521 ms,
   // 1024^3 12.46 -> 12.57..12.84 ms: the y kernel with remote stores needs all SMs itself (its remote stores are not a pure
   // link-bound tail), so splitting the SMs only divides the throughput -> off by default.
-  static const int pipe_chunks = [] { const char* e = getenv("FLUTAS_B200_PIPE"); return e ? atoi(e) : FB_PIPE_DEFAULT; }();
-  static const int pipe_xsm = [] { const char* e = getenv("FLUTAS_B200_PIPE_XSM"); const int v = e ? atoi(e) : 50; return v < 10 ? 10 : v > 90 ? 90 : v; }();
+  const int pipe_chunks = g_pipe_chunks;
+  const int pipe_xsm = g_pipe_xsm < 10 ? 10 : g_pipe_xsm > 90 ? 90 : g_pipe_xsm;
   const bool pipelined = sp->p2p && pipe_chunks > 1 && pipe_chunks <= 16 && (n3l % pipe_chunks) == 0 && sp->px.use_reg && sp->py.use_reg;
   if (pipelined) {
     static cudaStream_t s_x = nullptr;
@@ -1037,7 +1052,7 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   // of ~512 entries.  Hence (b) when a tile touches more than 600 remote pages.  That rule rests on ONE data point and (b)
   // has been verified for correctness and timed at 2 GPUs only (the round's GPU budget ended there);
   // FLUTAS_B200_ZCOPY = 0 / 1 forces either mode.
-  static const int zcopy_env = [] { const char* e = getenv("FLUTAS_B200_ZCOPY"); return e ? atoi(e) : -1; }();
+  const int zcopy_env = g_zcopy;
   const size_t lvl_stride = (size_t)n1l * n2 * sizeof(double), page = (size_t)2 << 20;
   const size_t remote_levels = (size_t)(ng3 - n3l);
   const size_t remote_pages = lvl_stride >= page ? remote_levels : (remote_levels * lvl_stride + page - 1) / page;

@@ -109,9 +109,11 @@ constexpr size_t xfft_reg_smem() {
   return (size_t)RegTw<RegSched<M>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
 }
 
-template <int N, bool FWD, bool MK>
+// KC: 0 = periodic (R2HC / HC2R), 1 = Makhoul (NN / DD), 2 = types IV (ND / DN)
+template <int N, bool FWD, int KC>
 __global__ void __launch_bounds__(256, 2)
 xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* __restrict__ dst, LineGeom gd, double scale) {
+  constexpr bool MK = (KC == 1), IV = (KC == 2);
   constexpr int M = N / 2;
   using S = RegSched<M>;
   constexpr int T = S::T, R = S::R;
@@ -134,7 +136,8 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
     if (WARP) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + lw), "n"(T) : "memory");
   };
-  const int kind = MK ? P.kind : (int)KIND_PP;
+  const int kind = (MK || IV) ? P.kind : (int)KIND_PP;
+  const bool dn = IV && (P.kind == KIND_DN);
   const long nlines = gs.nlines;
   const long ngroups = (nlines + LG - 1) / LG;
   const long gstride = WARP ? (long)gridDim.x * 8 : (long)gridDim.x;
@@ -147,7 +150,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   const long el0 = (long)(reinterpret_cast<uintptr_t>(FWD ? (const void*)src : (const void*)dst) / 8) + gph.off0;
   const bool al1 = even_strides && ((el0 + 1) % 2 == 0);       // element 1 of every line is 16-byte aligned
   const bool al0 = even_strides && (el0 % 2 == 0);             // element 0 is
-  const bool shift = !MK && al1;
+  const bool shift = !MK && !IV && al1;
   // DCT/DST lines: the Makhoul permutation makes per-thread accesses 32 bytes apart, so the physical side is
   // read / written in natural order as aligned 16-byte pairs and permuted through the line's exchange buffer.
   const bool viabuf = MK && (al0 || al1);
@@ -184,7 +187,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
           if (u == R - 1 && j == T - 1) { re[u] = ps[N - 1]; im[u] = ps[0]; }
           else { const double2 v = pa[m]; re[u] = v.x; im[u] = v.y; }
         }
-      } else if (!MK) {
+      } else if (!MK && !IV) {
 #pragma unroll
         for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
       } else if (viabuf) {
@@ -213,10 +216,15 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
           re[u] = s0 * ps[e0]; im[u] = s1 * ps[e1];
         }
       }
+      if (IV) reg_iv_pre<S, false>(re, im, j, P.wQ);
       reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
-      reg_scatter_modes<S>(re, im, j, xb);
-      sync();
-      reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+      if (IV) {
+        reg_iv_post<S, true>(re, im, j, s_wN, dn);
+      } else {
+        reg_scatter_modes<S>(re, im, j, xb);
+        sync();
+        reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+      }
       if (live) {
         double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
 #pragma unroll
@@ -225,12 +233,17 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
     } else {
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
 #pragma unroll
-      for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = v.x; im[u] = v.y; }
-      reg_scatter_modes<S>(re, im, j, xb);
-      sync();
-      reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
-      sync();
+      for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = dn ? v.y : v.x; im[u] = dn ? v.x : v.y; }
+      if (IV) {
+        reg_iv_pre<S, true>(re, im, j, P.wQ);
+      } else {
+        reg_scatter_modes<S>(re, im, j, xb);
+        sync();
+        reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
+        sync();
+      }
       reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
+      if (IV) reg_iv_post<S, false>(re, im, j, s_wN, dn);
       if (viabuf) {                                    // packed element m = slot m, then read back in natural order
         reg_scatter_modes<S>(re, im, j, xb);
         sync();
@@ -260,7 +273,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
             if (u == R - 1 && j == T - 1) { pd[N - 1] = scale * re[u]; pd[0] = scale * im[u]; }
             else pa[m] = make_double2(scale * re[u], scale * im[u]);
           }
-        } else if (!MK) {
+        } else if (!MK && !IV) {
 #pragma unroll
           for (int u = 0; u < R; ++u) { const int m = j + T * u; pd[2 * m] = scale * re[u]; pd[2 * m + 1] = scale * im[u]; }
         } else {
@@ -304,9 +317,10 @@ __device__ __forceinline__ double* yrow(double* p, unsigned sbytes, int c) {
   return reinterpret_cast<double*>(c >= 0 ? q + (size_t)sbytes * (unsigned)c : q - (size_t)sbytes * (unsigned)(-c));
 }
 
-template <int N, bool FWD, bool WIDE, bool MK, int RR>
-__global__ void __launch_bounds__(YRegShape<N, WIDE, MK, RR>::NT, YRegShape<N, WIDE, MK, RR>::MINB)
+template <int N, bool FWD, bool WIDE, int KC, int RR>
+__global__ void __launch_bounds__(YRegShape<N, WIDE, KC == 1, RR>::NT, YRegShape<N, WIDE, KC == 1, RR>::MINB)
 yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom sg) {
+  constexpr bool MK = (KC == 1), IV = (KC == 2);
   constexpr int M = N / 2;
   using S = RegSched<M, RR>;
   using Y = YRegShape<N, WIDE, MK, RR>;
@@ -322,6 +336,7 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
   const YTileBuf<TB> xb{buf + lane};
   auto sync = [] { __syncthreads(); };
   const double sdd = (MK && P.kind == KIND_DD) ? -1.0 : 1.0;   // DST-II/III through the DCT: odd physical elements change sign
+  const bool dn = IV && (P.kind == KIND_DN);
   const unsigned sstride = (unsigned)sg.n1l * 8u, pstride = (unsigned)n1 * 8u;      // row strides in bytes (< 4 GB)
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int ti = (int)(tile % ntile_i);
@@ -350,7 +365,16 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
     }
     double re[R], im[R];
     if (FWD) {
-      if (!MK) {
+      if (IV) {                                              // z_m = x_{2m} + i x_{N-1-2m}, m = j + T u (DN: the two swapped)
+        const double* pe = yrow(base, pstride, 2 * j);
+        const double* po = yrow(base, pstride, N - 1 - 2 * j);
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const double a = *yrow(pe, pstride, 2 * T * u), b = *yrow(po, pstride, -2 * T * u);
+          re[u] = dn ? b : a; im[u] = dn ? a : b;
+        }
+        reg_iv_pre<S, false>(re, im, j, P.wQ);
+      } else if (!MK) {
         const double* p0 = yrow(base, pstride, 2 * j);
 #pragma unroll
         for (int u = 0; u < R; ++u) { re[u] = *yrow(p0, pstride, 2 * T * u); im[u] = *yrow(p0, pstride, 2 * T * u + 1); }
@@ -364,9 +388,13 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
         }
       }
       reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
-      reg_scatter_modes<S>(re, im, j, xb);
-      sync();
-      reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+      if (IV) {
+        reg_iv_post<S, true>(re, im, j, s_wN, dn);
+      } else {
+        reg_scatter_modes<S>(re, im, j, xb);
+        sync();
+        reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+      }
       if (live) {
         double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
@@ -379,15 +407,31 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
       {
         const double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
-        for (int u = 0; u < R; ++u) { re[u] = *yrow(ps, sstride, 2 * T * u); im[u] = *yrow(ps, sstride, 2 * T * u + 1); }
+        for (int u = 0; u < R; ++u) {
+          const double a = *yrow(ps, sstride, 2 * T * u), b = *yrow(ps, sstride, 2 * T * u + 1);
+          re[u] = dn ? b : a; im[u] = dn ? a : b;
+        }
       }
-      reg_scatter_modes<S>(re, im, j, xb);
-      sync();
-      reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
-      sync();
+      if (IV) {
+        reg_iv_pre<S, true>(re, im, j, P.wQ);
+      } else {
+        reg_scatter_modes<S>(re, im, j, xb);
+        sync();
+        reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
+        sync();
+      }
       reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
+      if (IV) reg_iv_post<S, false>(re, im, j, s_wN, dn);
       if (live) {
-        if (!MK) {
+        if (IV) {                                            // packed element k -> (x_{2k}, x_{N-1-2k}); DN: (x_{N-1-2k}, x_{2k})
+          double* pe = yrow(base, pstride, 2 * j);
+          double* po = yrow(base, pstride, N - 1 - 2 * j);
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            *yrow(pe, pstride, 2 * T * u) = dn ? im[u] : re[u];
+            *yrow(po, pstride, -2 * T * u) = dn ? re[u] : im[u];
+          }
+        } else if (!MK) {
           double* p0 = yrow(base, pstride, 2 * j);
 #pragma unroll
           for (int u = 0; u < R; ++u) { *yrow(p0, pstride, 2 * T * u) = re[u]; *yrow(p0, pstride, 2 * T * u + 1) = im[u]; }
@@ -407,13 +451,13 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
 }
 
 
-template <int N, bool FWD, bool MK>
+template <int N, bool FWD, int KC>
 inline cudaError_t reg_launch_x1(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                                  int nsm, cudaStream_t st) {
   constexpr int M = N / 2, T = RegSched<M>::T;
   constexpr int LPB = 256 / T;                         // lines per block per iteration
-  const size_t smem = xfft_reg_smem<N, MK>();
-  auto kern = xfft_reg_kernel<N, FWD, MK>;
+  const size_t smem = xfft_reg_smem<N, KC == 1>();
+  auto kern = xfft_reg_kernel<N, FWD, KC>;
   static int per_sm = 0;                               // configured once per process (one device per process)
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -433,14 +477,15 @@ inline cudaError_t reg_launch_x1(const RegPlan& P, const double* src, LineGeom g
 template <int N, bool FWD>
 inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                                 int nsm, cudaStream_t st) {
-  return (P.kind == KIND_PP) ? reg_launch_x1<N, FWD, false>(P, src, gs, dst, gd, scale, nsm, st)
-                             : reg_launch_x1<N, FWD, true>(P, src, gs, dst, gd, scale, nsm, st);
+  if (kind_is_iv(P.kind)) return reg_launch_x1<N, FWD, 2>(P, src, gs, dst, gd, scale, nsm, st);
+  return (P.kind == KIND_PP) ? reg_launch_x1<N, FWD, 0>(P, src, gs, dst, gd, scale, nsm, st)
+                             : reg_launch_x1<N, FWD, 1>(P, src, gs, dst, gd, scale, nsm, st);
 }
 
-template <int N, bool FWD, bool WIDE, bool MK, int RR = 16>
+template <int N, bool FWD, bool WIDE, int KC, int RR = 16>
 inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, cudaStream_t st) {
-  using Y = YRegShape<N, WIDE, MK, RR>;
-  auto kern = yfft_reg_kernel<N, FWD, WIDE, MK, RR>;
+  using Y = YRegShape<N, WIDE, KC == 1, RR>;
+  auto kern = yfft_reg_kernel<N, FWD, WIDE, KC, RR>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Y::smem);
@@ -461,15 +506,21 @@ inline cudaError_t reg_launch_y1(const RegPlan& P, double* W, int n1, long n3, c
 template <int N, bool FWD>
 inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, const SpecGeom& sg, int nsm, bool wide,
                                 cudaStream_t st) {
-  const bool mk = (P.kind != KIND_PP);
+  const int kc = kind_is_iv(P.kind) ? 2 : (P.kind != KIND_PP) ? 1 : 0;
   if constexpr (N == 1024) {                            // 8 values per thread (see YRegShape); FLUTAS_B200_Y8=0/1 overrides
     static const int y8 = [] { const char* e = getenv("FLUTAS_B200_Y8"); return e ? atoi(e) : FB_Y8_DEFAULT; }();
     if (y8 && !wide && P.tw8[1])
-      return mk ? reg_launch_y1<N, FWD, false, true, 8>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, false, false, 8>(P, W, n1, n3, sg, nsm, st);
+      return kc == 2 ? reg_launch_y1<N, FWD, false, 2, 8>(P, W, n1, n3, sg, nsm, st)
+           : kc == 1 ? reg_launch_y1<N, FWD, false, 1, 8>(P, W, n1, n3, sg, nsm, st)
+                     : reg_launch_y1<N, FWD, false, 0, 8>(P, W, n1, n3, sg, nsm, st);
   }
   if (RegSched<N / 2>::T >= 32 && wide)
-    return mk ? reg_launch_y1<N, FWD, true, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, true, false>(P, W, n1, n3, sg, nsm, st);
-  return mk ? reg_launch_y1<N, FWD, false, true>(P, W, n1, n3, sg, nsm, st) : reg_launch_y1<N, FWD, false, false>(P, W, n1, n3, sg, nsm, st);
+    return kc == 2 ? reg_launch_y1<N, FWD, true, 2>(P, W, n1, n3, sg, nsm, st)
+         : kc == 1 ? reg_launch_y1<N, FWD, true, 1>(P, W, n1, n3, sg, nsm, st)
+                   : reg_launch_y1<N, FWD, true, 0>(P, W, n1, n3, sg, nsm, st);
+  return kc == 2 ? reg_launch_y1<N, FWD, false, 2>(P, W, n1, n3, sg, nsm, st)
+       : kc == 1 ? reg_launch_y1<N, FWD, false, 1>(P, W, n1, n3, sg, nsm, st)
+                 : reg_launch_y1<N, FWD, false, 0>(P, W, n1, n3, sg, nsm, st);
 }
 
 }  // namespace fb

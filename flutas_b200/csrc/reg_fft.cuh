@@ -289,6 +289,38 @@ FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ
   }
 }
 
+// ---- types IV (ND / DN: REDFT11 / RODFT11, the same transform in both directions; tile_fft.cuh has the algebra) ----
+// pre-twiddle of this thread's packed elements m = j + T u (wQ[m] = e^{-i pi (4m+1)/(4N)}); CONJ: the inverse-sign passes
+// that follow then compute the conjugate of the forward transform
+template <class S, bool CONJ>
+FB_HD void reg_iv_pre(double* re, double* im, int j, const cpx* wQ) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) {
+    const cpx w = wQ[j + S::T * u];
+    const double vr = re[u] * w.x - im[u] * w.y, vi = re[u] * w.y + im[u] * w.x;
+    re[u] = vr; im[u] = CONJ ? -vi : vi;
+  }
+}
+// post-twiddle of this thread's modes k = j + T u (wN[k] = e^{-i pi k/N}): (a, b) = (2 Re w, -2 Im w).
+// Forward: rows (2k, 2k+1) <- (Y_{2k}, Y_{N-1-2k}) = (a, b), DN: (a, -b).  Backward (CONJ input): the physical pair of
+// packed element k, ND: (x_{2k}, x_{N-1-2k}) = (a, b); DN (reversed line): (x_{N-1-2k}, x_{2k}) = (-b, a).
+template <class S, bool FWD>
+FB_HD void reg_iv_post(double* re, double* im, int j, const cpx* wN, bool dn) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int u = 0; u < S::R; ++u) {
+    const double vr = re[u], vi = FWD ? im[u] : -im[u];
+    const cpx w = wN[j + S::T * u];
+    const double a = 2.0 * (vr * w.x - vi * w.y), b = -2.0 * (vr * w.y + vi * w.x);
+    if (!dn) { re[u] = a; im[u] = b; }
+    else if (FWD) { re[u] = a; im[u] = -b; }
+    else { re[u] = -b; im[u] = a; }
+  }
+}
+
 // Physical rows of packed element m = j + T u of a Makhoul (NN/DD) line, T = N/(2 RR) threads per line, RR values each:
 //   u <  RR/2 (m <  N/4): e0 = 4 m,            e1 = e0 + 2      (even elements; DD sign +)
 //   u >= RR/2 (m >= N/4): e0 = 2 N - 1 - 4 m,  e1 = e0 - 2      (odd elements;  DD sign -)

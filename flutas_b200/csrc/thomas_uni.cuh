@@ -167,6 +167,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                : "memory");
 }
 
+// 1-D bulk copy global -> shared, completion counted on the same mbarrier (bytes: multiple of 16, 16-byte aligned both sides)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 template <int L, int TI, int MINB>
 __global__ void __launch_bounds__(512 / MINB, MINB)
 thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const __grid_constant__ CUtensorMap tmap,
@@ -183,7 +191,8 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
   double* pcrA = ex + 6 * (size_t)st;
   double* pcrB = pcrA + 3 * (size_t)st;
   double* X = pcrB + 3 * (size_t)st;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(X + st);
+  double* lam_s = X + st;                                 // [TI] eigenvalues of the tile in flight, 16-byte aligned
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(lam_s + TI);
   const int lane = tid % TI, s = tid / TI;
   const int k0 = s * L;
   const bool one_chunk = (og.n3l % L) == 0;
@@ -191,15 +200,18 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
   if (one_chunk) { const int q = k0 / og.n3l; obase = og.ptr[q] + og.koff + ncol * (long)(k0 - q * og.n3l); }
   const unsigned tile_bytes = (unsigned)nz * TI * sizeof(double);
 
+  // The tile's eigenvalues ride on the same mbarrier as the tile (one 1-D bulk copy of <= 128 bytes).  r02 source-level
+  // profile of the previous version, which prefetched lambda of the NEXT tile into a register with __ldg: the register was
+  // spilled, so every thread stalled a full DRAM latency on `LDG -> STL` at the top of each iteration (13.6 % of all
+  // stall samples, the largest single site; the mbarrier wait itself: 0 %).
   auto fetch = [&](long tile) {                            // one thread: whole tile, completion counted in bytes on `bar`
     if (tid == 0 && tile < ntiles) {
-      mbar_expect_tx(bar, tile_bytes);                     // (out-of-range columns of a ragged last tile are zero-filled and counted)
-      for (int r = 0; r < nz; r += box_rows) tma_load_2d(tile_s + (size_t)r * TI, &tmap, (int)(tile * TI), r, bar);
+      const long c0 = tile * TI;
+      const unsigned lam_bytes = (unsigned)((ncol - c0 < TI ? ncol - c0 : TI) * sizeof(double));   // ncol is even: multiple of 16
+      mbar_expect_tx(bar, tile_bytes + lam_bytes);         // (out-of-range columns of a ragged last tile are zero-filled and counted)
+      for (int r = 0; r < nz; r += box_rows) tma_load_2d(tile_s + (size_t)r * TI, &tmap, (int)c0, r, bar);
+      bulk_load_1d(lam_s, lam + c0, lam_bytes, bar);
     }
-  };
-  auto lam_of = [&](long tile) {                           // dead lanes of a ragged last tile: any regular column
-    const long col = tile * TI + lane;
-    return (col < ncol) ? __ldg(lam + col) : -1.0;
   };
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -207,18 +219,16 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
   }
   __syncthreads();
   long tile = blockIdx.x;
-  double lm_next = 0.0;
-  if (tile < ntiles) { fetch(tile); lm_next = lam_of(tile); }
+  if (tile < ntiles) fetch(tile);
 
   for (unsigned it = 0; tile < ntiles; tile += gridDim.x, ++it) {
     const long col = tile * TI + lane;
     const bool live = col < ncol;
-    const double lm = lm_next;
-    if (tile + gridDim.x < ntiles) lm_next = lam_of(tile + gridDim.x);
-    const bool pin = T.singular && live && (lm == 0.0);
-    if (tid < 2 * TI) TU::build(tab, T, lm, lane, tid / TI);           // overlaps the wait for the tile
     double v[L];
     mbar_wait(bar, it & 1u);
+    const double lm = live ? lam_s[lane] : -1.0;           // dead lanes of a ragged last tile: any regular column
+    const bool pin = T.singular && live && (lm == 0.0);
+    if (tid < 2 * TI) TU::build(tab, T, lm, lane, tid / TI);
     {
       const double* ts = tile_s + (size_t)k0 * TI + lane;
 #pragma unroll
@@ -398,7 +408,7 @@ inline cudaError_t thomas_uni_tma_launch(long ncol, const ThomasArgs& T, const d
   const int threads = TI * T.S;
   const int box_rows = T.nz < 256 ? T.nz : 256;
   if (T.nz % box_rows) return cudaErrorInvalidValue;
-  const size_t smem = ((size_t)T.nz * TI + TU::tab_doubles() + 13 * (size_t)T.S * TI + 2) * sizeof(double);
+  const size_t smem = ((size_t)T.nz * TI + TU::tab_doubles() + 13 * (size_t)T.S * TI + TI + 2) * sizeof(double);
   const long ntiles = (ncol + TI - 1) / TI;
   CUtensorMap map;
   cudaError_t e = thomas_uni_tensor_map(W, ncol, T.nz, TI, box_rows, &map);
@@ -605,7 +615,7 @@ inline int thomas_uni_run(long ncol, int nz, const double* lam, const double* W,
   cudaError_t e = cudaSuccess;
   // TMA tile loads need a 16-byte aligned base and row pitch (ncol even); FLUTAS_B200_THOMAS_TMA=0 keeps the cp.async kernel
   static const bool tma_env = [] { const char* e = getenv("FLUTAS_B200_THOMAS_TMA"); return !(e && e[0] == '0'); }();
-  if (tma_env && (ncol % 2) == 0 && (reinterpret_cast<uintptr_t>(W) % 16) == 0) {
+  if (tma_env && (ncol % 2) == 0 && (reinterpret_cast<uintptr_t>(W) % 16) == 0 && (reinterpret_cast<uintptr_t>(lam) % 16) == 0) {
     switch (L) {
       case 4: e = thomas_uni_tma_launch<4, 16, 1>(ncol, T, lam, W, og, nsm, st); break;
       case 8: e = thomas_uni_tma_launch<8, 16, 1>(ncol, T, lam, W, og, nsm, st); break;

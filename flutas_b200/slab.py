@@ -96,8 +96,8 @@ class SlabComm:
     def gather_lambda(self, lam_window):
         import torch
         key = (lam_window.__array_interface__["data"][0], lam_window.shape)
-        if key in self._lam_cache:
-            return self._lam_cache[key]
+        if key in self._lam_cache:                       # the cache holds a reference to the window: its address cannot be recycled
+            return self._lam_cache[key][1]
         backend = self.dist.get_backend(self.group)
         t = torch.from_numpy(np.ascontiguousarray(lam_window.T))            # (ng2/P, ng1), C order
         if backend == "nccl":
@@ -105,7 +105,7 @@ class SlabComm:
         parts = [torch.empty_like(t) for _ in range(self.nranks)]
         self.dist.all_gather(parts, t, group=self.group)
         full = np.asfortranarray(torch.cat(parts, dim=0).cpu().numpy().T)    # (ng1, ng2)
-        self._lam_cache[key] = full
+        self._lam_cache[key] = (lam_window, full)
         return full
 
     def use_nccl_alltoall(self):
@@ -162,6 +162,33 @@ class SlabComm:
     def p2p_errors(self, arrplan):
         return _lib.load().flutas_b200_p2p_errors(arrplan.h)
 
+    def configure(self, pipe_chunks=-1, pipe_xsm_pct=-1, zcopy=-1):
+        """schedule knobs of the slab solver (flutas_b200_slab_config); the same values on every rank"""
+        _lib.check(_lib.load().flutas_b200_slab_config(int(pipe_chunks), int(pipe_xsm_pct), int(zcopy)))
+
+    def autotune(self, solve, candidates=((0, 50), (2, 30), (4, 30), (4, 50)), reps=3):
+        """Plan-time measurement (the counterpart of FFTW_MEASURE): runs `solve()` under each (pipe_chunks, pipe_xsm_pct)
+        candidate, timed on the device, max over ranks, and keeps the fastest on ALL ranks.  Returns (choice, {cand: ms})."""
+        import torch
+        times = {}
+        for cand in candidates:
+            self.configure(cand[0], cand[1])
+            solve()                                          # first call of a configuration: streams / events are created
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                solve()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            times[cand] = float(t.item())
+        best = min(times, key=times.get)
+        self.configure(best[0], best[1])
+        return best, times
+
     def solver(self, n_local, arrplan, normfft, lam_window, a, b, c, bcz, c_or_f, p):
         """Collective `solver` on this rank's slab; same argument meaning as the reference's solver_gpu call."""
         lam_full = self.gather_lambda(lam_window)
@@ -169,6 +196,8 @@ class SlabComm:
         nn = (C.c_int * 3)(*n_local)
         _lib.check(_lib.load().flutas_b200_solver_slab(nn, arrplan.h, normfft, api._ptr(lam_full), api._ptr(a), api._ptr(b),
                                                        api._ptr(c), bcz.encode(), "".join(c_or_f).encode(), api._ptr(p)))
+        # a cross-GPU barrier that timed out in an EARLIER solve makes this call fail (the library mirrors its error word to
+        # pinned host memory behind every barrier); p2p_errors() reports it right away at the price of a stream sync
         return p
 
     def chkdiv(self, *args):

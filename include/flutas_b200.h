@@ -96,6 +96,13 @@ int flutas_b200_p2p_export(void *const arrplan[4], const int n_local[3], void *b
 int flutas_b200_p2p_attach(void *const arrplan[4], const void *blobs);
 int flutas_b200_p2p_errors(void *const arrplan[4]);
 
+/* Schedule of the slab solver (optional; every rank must pass the same values).  pipe_chunks: the forward half runs
+ * pipelined over that many k-chunks -- the x transform of chunk c+1 on part of the SMs while the y transform + NVLink
+ * stores of chunk c use the rest (0 or 1 = off); pipe_xsm_pct: share of the SMs given to the x kernels (10..90);
+ * zcopy: 1 = backward exchange through the copy engines, 0 = fused into the z kernel's stores, -1 = built-in rule.
+ * A negative pipe_* value leaves that knob unchanged.  Defaults: FLUTAS_B200_PIPE / _PIPE_XSM / _ZCOPY or off/50/-1. */
+int flutas_b200_slab_config(int pipe_chunks, int pipe_xsm_pct, int zcopy);
+
 /* solver on a z-slab: as flutas_b200_solver, with n = the LOCAL interior size (ng1, ng2, ng3/nranks) and
  * lambdaxy_global = lambdaxy(ng1, ng2) for the whole x-y plane (the shim all-gathers the (ng1, ng2/nranks)
  * windows initsolver produces on each rank, src/initsolver.f90:87-93; done once).  Collective. */

@@ -33,14 +33,20 @@ static void run(const HostLinePlan& hp, int nworkers, int fwd, const double* in,
     for (int w = 0; w < nworkers; ++w)
       for (int lane = 0; lane < TB; ++lane) fn(lane, w);
   };
+  const bool iv = kind_is_iv(P.kind);                     // same phase order as tile_transform (kernels.cuh)
+  auto acc = [&](int lane) { return TileAcc<TB, ROT>{tile.data(), P.M, lane}; };
   if (fwd) {
+    if (iv) phase([&](int lane, int w) { iv_pre<true>(P.M, P.kind, P.wQ, P.pos, w, nworkers, acc(lane)); });
     for (int q = 0; q < P.npass; ++q)
       phase([&](int lane, int w) { fft_pass<TB, ROT, true>(tile.data(), P, P.wM, q, lane, w, nworkers); });
-    phase([&](int lane, int w) { split_fwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
+    if (iv) phase([&](int lane, int w) { iv_post<true>(P.M, P.kind, P.wN, P.pos, w, nworkers, acc(lane)); });
+    else phase([&](int lane, int w) { split_fwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
   } else {
-    phase([&](int lane, int w) { merge_bwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
+    if (iv) phase([&](int lane, int w) { iv_pre<false>(P.M, P.kind, P.wQ, P.pos, w, nworkers, acc(lane)); });
+    else phase([&](int lane, int w) { merge_bwd<TB, ROT>(tile.data(), P, lane, w, nworkers); });
     for (int q = P.npass - 1; q >= 0; --q)
       phase([&](int lane, int w) { fft_pass<TB, ROT, false>(tile.data(), P, P.wM, q, lane, w, nworkers); });
+    if (iv) phase([&](int lane, int w) { iv_post<false>(P.M, P.kind, P.wN, P.pos, w, nworkers, acc(lane)); });
   }
   // store phase
   for (int L = 0; L < TB; ++L)
@@ -368,7 +374,7 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
       for (int u = 0; u < R; ++u) {
         int e0, e1; double s0, s1;
         reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
-        if (hp.kind != KIND_PP && M >= 16) {               // the kernels' closed form of the same rows
+        if (kind_is_makhoul(hp.kind) && M >= 16) {         // the kernels' closed form of the same rows
           using MR = MkRows<N, RR>;
           const int b = MR::upper(u) ? MR::base_hi(j) : MR::base_lo(j);
           if (b + MR::off0(u) != e0 || b + MR::off1(u) != e1) std::abort();
@@ -377,23 +383,39 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
         }
         RE(j)[u] = s0 * in[e0]; IM(j)[u] = s1 * in[e1];
       }
+    const bool iv = kind_is_iv(hp.kind), dn = (hp.kind == KIND_DN);
+    if (iv) for (int j = 0; j < T; ++j) reg_iv_pre<S, false>(RE(j), IM(j), j, hp.wQ.data());
     passes(std::integral_constant<int, -1>{});
-    for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
-    for (int j = 0; j < T; ++j) {
-      if (hp.kind == KIND_PP) reg_split<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
-      else reg_split<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+    if (iv) {
+      for (int j = 0; j < T; ++j) reg_iv_post<S, true>(RE(j), IM(j), j, hp.wN.data(), dn);
+    } else {
+      for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) {
+        if (hp.kind == KIND_PP) reg_split<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+        else reg_split<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      }
     }
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) { const int k = j + T * u; out[2 * k] = scale * RE(j)[u]; out[2 * k + 1] = scale * IM(j)[u]; }
   } else {
     for (int j = 0; j < T; ++j)
-      for (int u = 0; u < R; ++u) { const int k = j + T * u; RE(j)[u] = in[2 * k]; IM(j)[u] = in[2 * k + 1]; }
-    for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
-    for (int j = 0; j < T; ++j) {
-      if (hp.kind == KIND_PP) reg_merge<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
-      else reg_merge<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      for (int u = 0; u < R; ++u) {
+        const int k = j + T * u;
+        const bool dn = (hp.kind == KIND_DN);
+        RE(j)[u] = dn ? in[2 * k + 1] : in[2 * k]; IM(j)[u] = dn ? in[2 * k] : in[2 * k + 1];
+      }
+    const bool iv = kind_is_iv(hp.kind);
+    if (iv) {
+      for (int j = 0; j < T; ++j) reg_iv_pre<S, true>(RE(j), IM(j), j, hp.wQ.data());
+    } else {
+      for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
+      for (int j = 0; j < T; ++j) {
+        if (hp.kind == KIND_PP) reg_merge<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+        else reg_merge<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
+      }
     }
     passes(std::integral_constant<int, +1>{});
+    if (iv) for (int j = 0; j < T; ++j) reg_iv_post<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.kind == KIND_DN);
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) {
         int e0, e1; double s0, s1;

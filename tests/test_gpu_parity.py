@@ -40,8 +40,7 @@ def _solve_gpu(case, rhs, device=False, z_mode=0, generic_fft=False):
     return p
 
 
-@pytest.mark.parametrize("path", [f for f in golden_files() if "ndp" not in f and "pdn" not in f],
-                         ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
 @pytest.mark.parametrize("z_mode", [0, 3, 2, 1], ids=["zreg", "zreg-tables", "ztile", "zgeneric"])
 def test_solver_matches_golden(path, z_mode):
     case, rhs, pgold = load_golden(path)
@@ -54,8 +53,8 @@ def test_solver_matches_golden(path, z_mode):
 
 
 def test_unsupported_bc_fails_loudly():
-    with pytest.raises(lib.FlutasB200Error, match="only PP, NN, DD"):
-        api.fftini((8, 8, 8), (8, 8, 8), ("ND", "PP"))
+    with pytest.raises(lib.FlutasB200Error, match="PP, NN, DD, ND, DN only"):
+        api.fftini((8, 8, 8), (8, 8, 8), ("PN", "PP"))          # not a pair of src/fft.f90:233-291
     with pytest.raises(lib.FlutasB200Error, match="factors into 2,3,5"):
         api.fftini((14, 8, 8), (14, 8, 8), ("PP", "PP"))
 
@@ -77,6 +76,12 @@ CASES = [
     ("p2d", (2048, 64, 4), ("NN", "PP", "NN"), (2.0, 1.0, 1.0), 0.0),
     ("p2e", (72, 2048, 4), ("PP", "NN", "NN"), (2.0, 1.0, 1.0), 0.0),
     ("p2f", (1000, 128, 6), ("DD", "PP", "PP"), (2.0, 1.0, 1.0), 0.0),
+    # ND / DN pressure BCs: REDFT11 / RODFT11 (src/fft.f90:256-263), register kernels (32..2048) and tile kernels (others)
+    ("nd-x", (64, 48, 16), ("ND", "PP", "NN"), (1.0, 2.0, 1.0), 0.0),
+    ("dn-y", (32, 128, 8), ("PP", "DN", "DD"), (2.0, 1.0, 1.0), 0.0),
+    ("nd-dn", (40, 72, 12), ("DN", "ND", "NN"), (1.0, 1.0, 1.0), 1.0),
+    ("nd1024", (1024, 32, 4), ("ND", "DN", "PP"), (4.0, 1.0, 1.0), 0.0),
+    ("dn2048", (16, 2048, 4), ("NN", "DN", "NN"), (1.0, 4.0, 1.0), 0.0),
     # exactly uniform z grids (lz/nz a binary fraction): the shared-LU z kernel (thomas_uni.cuh), L = 32 / 16 / 32 periodic
     ("uni1024", (16, 24, 1024), ("PP", "PP", "NN"), (1.0, 1.0, 1.0), 0.0),
     ("uni512", (40, 16, 512), ("NN", "PP", "DD"), (1.0, 1.0, 2.0), 0.0),

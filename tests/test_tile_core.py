@@ -11,7 +11,7 @@ import pytest
 from oracle import oracle
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-KIND = {"PP": 0, "NN": 1, "DD": 2}
+KIND = {"PP": 0, "NN": 1, "DD": 2, "ND": 3, "DN": 4}
 _dp = C.POINTER(C.c_double)
 
 
@@ -39,7 +39,7 @@ def _mode(emul, n, bc):
     return np.array(mode[:])
 
 
-@pytest.mark.parametrize("bc", ["PP", "NN", "DD"])
+@pytest.mark.parametrize("bc", ["PP", "NN", "DD", "ND", "DN"])
 @pytest.mark.parametrize("n", [2, 4, 6, 8, 10, 12, 16, 30, 32, 64, 72, 100, 128, 256, 512, 1024])
 @pytest.mark.parametrize("tb,rot", [(16, 0), (16, 1), (8, 1), (8, 0), (4, 1)])
 def test_tile_forward_matches_fftw_definition(emul, bc, n, tb, rot):
@@ -74,7 +74,7 @@ def test_tile_forward_matches_fftw_definition(emul, bc, n, tb, rot):
 
 
 # ---- register-resident transforms (reg_fft.cuh) --------------------------------------------------
-@pytest.mark.parametrize("bc", ["PP", "NN", "DD"])
+@pytest.mark.parametrize("bc", ["PP", "NN", "DD", "ND", "DN"])
 @pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, (1024, 8)], ids=str)
 def test_reg_fft_matches_fftw_definition(emul, bc, n):
     transform = emul.emul_reg_line_transform
