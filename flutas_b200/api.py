@@ -161,6 +161,28 @@ def boundp(cbc, n, bc, nh_d, nh_p, dl, dzc, dzf, p):
     return p
 
 
+def bounduvw(cbc, n, bc, nh_d, nh_u, isoutflow, dl, dzc, dzf, u, v, w):
+    """bounduvw(cbc,n,bc,nh_d,nh_u,halo,isoutflow,dl,dzc,dzf,u,v,w), src/bound.f90:17 (no `halo` MPI datatypes).
+    cbc[ibound][idir][field] characters, bc[ibound][idir][field] values, isoutflow[ibound][idir] booleans."""
+    _use_torch_stream()
+    cc = "".join(cbc[ib][d][f] for f in range(3) for d in range(3) for ib in range(2))       # Fortran order (0:1,3,3)
+    bv = (C.c_double * 18)(*[float(bc[ib][d][f]) for f in range(3) for d in range(3) for ib in range(2)])
+    io = (C.c_int * 6)(*[1 if isoutflow[ib][d] else 0 for d in range(3) for ib in range(2)])
+    nn = (C.c_int * 3)(*n)
+    dlv = (C.c_double * 3)(*[float(x) for x in dl])
+    _lib.check(_lib.load().flutas_b200_bounduvw(cc.encode(), nn, bv, nh_d, nh_u, io, dlv, _ptr(dzc), _ptr(dzf),
+                                                _ptr(u), _ptr(v), _ptr(w)))
+
+
+def chkdt(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzci, dzfi, u, v, w):
+    """the field reduction of chkdt_sp / chkdt_tw (src/chkdt.f90:150-173): this rank's max(dtix, dtiy, dtiz)"""
+    _use_torch_stream()
+    dti = C.c_double()
+    _lib.check(_lib.load().flutas_b200_chkdt(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, _ptr(dzci), _ptr(dzfi), _ptr(u), _ptr(v),
+                                             _ptr(w), C.byref(dti)))
+    return dti.value
+
+
 def chkdiv(nx, ny, nz, dxi, dyi, dzi, nh_d, nh_u, dzfi, u, v, w):
     _use_torch_stream()
     tot, mx = C.c_double(), C.c_double()

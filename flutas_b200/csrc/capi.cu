@@ -23,6 +23,7 @@
 #include "thomas_uni.cuh"
 #include "thomas_tile.cuh"
 #include "thomas_ref.cuh"
+#include "bounduvw.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1462,6 +1463,154 @@ int flutas_b200_boundp(const char cbc[6], const int n[3], const double bc[6], in
   }
   if (int rc = stage_out(fp)) return rc;
   if (fp.staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+// bounduvw(cbc,n,bc,nh_d,nh_u,halo,isoutflow,dl,dzc,dzf,u,v,w), src/bound.f90:17-144, in the reference's step order:
+// updthalo along y and z for u, v, w (:55-62), set_bc on the x faces, the y faces, the z faces this rank owns (:68-128),
+// then outflow (:131-141).  z-slab decomposition: the z halo layers (nh_u planes per side) go through the callback of
+// flutas_b200_set_halo_exchange; x and y are never decomposed in this layout.
+int flutas_b200_bounduvw(const char cbc[18], const int n[3], const double bc[18], int nh_d, int nh_u, const int isoutflow[6],
+                         const double dl[3], const double* dzc, const double* dzf, double* u, double* v, double* w) {
+  if (int rc = ensure_device()) return rc;
+  if (!cbc || !n || !bc || !isoutflow || !dl || !dzc || !dzf || !u || !v || !w) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (nh_u < 1 || nh_u > FB_MAX_HALO) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "bounduvw: halo width %d (1..%d)", nh_u, (int)FB_MAX_HALO);
+  if (nh_d < nh_u) return fail(FLUTAS_B200_ERR_ARG, "bounduvw: nh_d = %d < nh_u = %d", nh_d, nh_u);
+  for (int q = 0; q < 18; ++q)
+    if (cbc[q] != 'P' && cbc[q] != 'D' && cbc[q] != 'N') return fail(FLUTAS_B200_ERR_ARG, "bad boundary type '%c'", cbc[q]);
+  const int nx = n[0], ny = n[1], nz = n[2], nh = nh_u;
+  if (nx < nh + 1 || ny < nh + 1 || nz < nh + 1) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "bounduvw: grid smaller than the halo");
+  const HaloField g = halo_field(nx, ny, nz, nh);
+  const size_t count = (size_t)g.s[2] * (nz + 2 * nh);
+  FieldRef f[3];
+  double* in[3] = {u, v, w};
+  for (int q = 0; q < 3; ++q)
+    if (int rc = stage_in(f[q], q, in[q], count, true)) return rc;
+  auto C = [&](int ib, int idir, int fld) { return cbc[ib + 2 * (idir + 3 * fld)]; };          // cbc(0:1,3,3), Fortran order
+  auto B = [&](int ib, int idir, int fld) { return bc[ib + 2 * (idir + 3 * fld)]; };
+  auto periodic = [&](int idir) {
+    for (int ib = 0; ib < 2; ++ib) for (int fld = 0; fld < 3; ++fld) if (C(ib, idir, fld) != 'P') return false;
+    return true;
+  };
+  const bool py = periodic(1), pz = periodic(2);
+  const int P = g_nranks, r = g_rank;
+  auto launch_bc = [&](double* p, int idir, int ib, int mode, double sgn, const BcFactor& fac) -> int {
+    const int da = (idir == 0) ? 1 : 0, db = (idir == 2) ? 1 : 2;
+    const long cnt = (long)(g.n[da] + 2 * nh) * (g.n[db] + 2 * nh);
+    set_bc_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(p, g, idir, ib, mode, sgn, fac);
+    LAUNCHED();
+    return 0;
+  };
+  // set_bc (:238-266): factor and sign from the boundary type; dr[q] only matters for Neumann
+  auto set_bc = [&](double* p, char type, int ib, int idir, bool centered, double value, const double* dr) -> int {
+    BcFactor fac;
+    double sgn = 0.0;
+    for (int q = 0; q < nh; ++q) fac.f[q] = value;
+    if (type == 'P') return launch_bc(p, idir, ib, BC_WRAP, 0.0, fac);
+    if (type == 'D' && centered) { for (int q = 0; q < nh; ++q) fac.f[q] = 2.0 * fac.f[q]; sgn = -1.0; }
+    if (type == 'N') { for (int q = 0; q < nh; ++q) fac.f[q] = (ib == 0) ? -dr[q] * fac.f[q] : dr[q] * fac.f[q]; sgn = 1.0; }
+    const int mode = centered ? BC_CENTERED : (type == 'D') ? BC_FACE_D : BC_FACE_N;
+    return launch_bc(p, idir, ib, mode, sgn, fac);
+  };
+  // 1. updthalo along y, then z, field by field (:55-62)
+  const BcFactor none{};
+  const size_t plane = (size_t)g.s[2];
+  int lo = -1, hi = -1;
+  if (P > 1) { lo = (r > 0) ? r - 1 : (pz ? P - 1 : -1); hi = (r < P - 1) ? r + 1 : (pz ? 0 : -1); }
+  if (P > 1 && !g_halo) return fail(FLUTAS_B200_ERR_ARG, "bounduvw on %d ranks needs flutas_b200_set_halo_exchange", P);
+  for (int q = 0; q < 3; ++q) {
+    double* p = f[q].dev;
+    if (py) { if (int rc = launch_bc(p, 1, 0, BC_WRAP, 0.0, none)) return rc; }
+    if (P == 1) { if (pz) { if (int rc = launch_bc(p, 2, 0, BC_WRAP, 0.0, none)) return rc; } }
+    else if (g_halo(g_halo_ctx, p + plane * nh, p + plane * nz, p, p + plane * (nz + nh), plane * nh, lo, hi, (void*)g_stream))
+      return fail(FLUTAS_B200_ERR_CUDA, "halo exchange callback failed");
+  }
+  // z metrics at the walls for Neumann values: dr(q) = dzc(-q) / dzf(-q) / dzc(n3+q) / dzf(n3+q) (:95-119)
+  std::vector<double> hzc, hzf;
+  bool need_dr = false;
+  if (!pz) for (int ib = 0; ib < 2; ++ib) for (int fld = 0; fld < 3; ++fld) if (C(ib, 2, fld) == 'N' && B(ib, 2, fld) != 0.0) need_dr = true;
+  const size_t nd = (size_t)nz + 2 * nh_d;
+  if (need_dr) {
+    hzc.resize(nd); hzf.resize(nd);
+    CK(cudaMemcpyAsync(hzc.data(), dzc, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+    CK(cudaMemcpyAsync(hzf.data(), dzf, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  double dr[FB_MAX_HALO];
+  // 2. x faces (left = right = MPI_PROC_NULL in this layout), 3. y faces unless periodic, 4. z faces this rank owns
+  for (int idir = 0; idir < 3; ++idir) {
+    if ((idir == 1 && py) || (idir == 2 && pz)) continue;
+    for (int ib = 0; ib < 2; ++ib) {
+      if (idir == 2 && P > 1 && ((ib == 0 && r != 0) || (ib == 1 && r != P - 1))) continue;
+      for (int fld = 0; fld < 3; ++fld) {
+        const bool centered = (fld != idir);
+        for (int q = 0; q < nh; ++q) {
+          if (idir < 2) dr[q] = dl[idir];
+          else if (!need_dr) dr[q] = 1.0;                   // multiplies a zero value (or is unused)
+          else dr[q] = (centered ? hzc : hzf)[(size_t)((ib == 0 ? -q : nz + q) + nh_d - 1)];
+        }
+        if (int rc = set_bc(f[fld].dev, C(ib, idir, fld), ib, idir, centered, B(ib, idir, fld), dr)) return rc;
+      }
+    }
+  }
+  // 5. outflow (:131-141)
+  bool any_out = false;
+  for (int q = 0; q < 6; ++q) any_out = any_out || (isoutflow[q] != 0);
+  if (any_out) {
+    const double* dzf_dev = dzf;
+    if (!on_device(dzf)) {
+      if (int rc = g_coef.reserve(nd * sizeof(double))) return rc;
+      CK(cudaMemcpyAsync(g_coef.p, dzf, nd * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+      dzf_dev = g_coef.as<double>();
+    }
+    for (int q = 0; q < 3; ++q)
+      for (int ib = 0; ib < 2; ++ib) {
+        if (!isoutflow[ib + 2 * q]) continue;
+        if (q == 2 && P > 1 && ((ib == 0 && r != 0) || (ib == 1 && r != P - 1))) continue;   // top / bottom == MPI_PROC_NULL
+        if ((q == 1 && py) || (q == 2 && pz)) continue;                                          // neighbour is a rank, not a wall
+        const int da = (q == 0) ? 1 : 0, db = (q == 2) ? 1 : 2;
+        const long cnt = (long)g.n[da] * g.n[db];
+        outflow_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(g, (q + 1) * (ib == 0 ? -1 : 1), nh_d, dl[0], dl[1], dzf_dev,
+                                                                           f[0].dev, f[1].dev, f[2].dev);
+        LAUNCHED();
+      }
+  }
+  for (int q = 0; q < 3; ++q) if (int rc = stage_out(f[q])) return rc;
+  if (f[0].staged || f[1].staged || f[2].staged) CK(cudaStreamSynchronize(g_stream));
+  return FLUTAS_B200_OK;
+}
+
+// The field reduction of chkdt_sp / chkdt_tw (src/chkdt.f90:62-85 = :150-173): this rank's max over cells of the three
+// convective inverse time scales.  The caller all-reduces (MPI_MAX, :92,183) and applies the scalar formulas (:93-110,
+// :184-196: `if(dti.eq.0) dti = 1`, viscous / gravity limits, dtmax) exactly as the reference does.  Synchronous.
+int flutas_b200_chkdt(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u, const double* dzci,
+                      const double* dzfi, const double* u, const double* v, const double* w, double* dti) {
+  (void)dzi;
+  if (int rc = ensure_device()) return rc;
+  if (!dzci || !dzfi || !u || !v || !w || !dti) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  if (nh_u < 1 || nh_d < 1) return fail(FLUTAS_B200_ERR_ARG, "halo widths must be >= 1");
+  const HaloField g = halo_field(nx, ny, nz, nh_u);
+  const size_t count = (size_t)g.s[2] * (nz + 2 * nh_u);
+  FieldRef fu, fv, fw;
+  if (int rc = stage_in(fu, 0, u, count, true)) return rc;
+  if (int rc = stage_in(fv, 1, v, count, true)) return rc;
+  if (int rc = stage_in(fw, 2, w, count, true)) return rc;
+  const size_t nd = (size_t)nz + 2 * nh_d;
+  if (int rc = g_coef.reserve(2 * nd * sizeof(double))) return rc;
+  CK(cudaMemcpyAsync(g_coef.p, dzci, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+  CK(cudaMemcpyAsync(g_coef.as<double>() + nd, dzfi, nd * sizeof(double), cudaMemcpyDefault, g_stream));
+  dim3 blk(64, 4, 1), grd((nx + 63) / 64, (ny + 3) / 4, nz);
+  const long nparts = (long)grd.x * grd.y * grd.z;
+  if (int rc = g_red.reserve(((size_t)nparts + 2) * sizeof(double))) return rc;
+  double* part = g_red.as<double>();
+  chkdt_kernel<<<grd, blk, 0, g_stream>>>(g, nh_d, dxi, dyi, g_coef.as<double>(), g_coef.as<double>() + nd, fu.dev, fv.dev, fw.dev, part);
+  LAUNCHED();
+  max_final_kernel<<<1, 256, 0, g_stream>>>(nparts, part, part + nparts);
+  LAUNCHED();
+  double res = 0.0;
+  CK(cudaMemcpyAsync(&res, part + nparts, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  *dti = res;
   return FLUTAS_B200_OK;
 }
 

@@ -48,6 +48,8 @@ def load():
     L.flutas_b200_pres_tw_src.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] + [cd] * 3 + [vp] * 6
     L.flutas_b200_pold_update.argtypes = [ci] * 4 + [vp, vp]
     L.flutas_b200_load.argtypes = [C.c_char, cc, ip, ip, ip, ci, vp]
+    L.flutas_b200_bounduvw.argtypes = [cc, ip, _dp, ci, ci, ip, _dp, vp, vp, vp, vp, vp]
+    L.flutas_b200_chkdt.argtypes = [ci] * 3 + [cd] * 3 + [ci] * 2 + [vp] * 5 + [_dp]
     L.flutas_b200_set_halo_exchange.argtypes = [vp, vp]
     L.flutas_b200_set_alltoall.argtypes = [vp, vp]
     L.flutas_b200_p2p_handle_bytes.restype = C.c_size_t
@@ -78,5 +80,5 @@ EXPORTS = [
     "flutas_b200_profile_stage_name", "flutas_b200_profile_read", "flutas_b200_set_alltoall",
     "flutas_b200_p2p_handle_bytes", "flutas_b200_p2p_export", "flutas_b200_p2p_attach", "flutas_b200_p2p_errors",
     "flutas_b200_solver_slab", "flutas_b200_slab_config", "flutas_b200_boundp", "flutas_b200_set_halo_exchange",
-    "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src", "flutas_b200_pold_update", "flutas_b200_load",
+    "flutas_b200_bounduvw", "flutas_b200_chkdt", "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src", "flutas_b200_pold_update", "flutas_b200_load",
 ]

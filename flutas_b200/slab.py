@@ -200,6 +200,15 @@ class SlabComm:
         # pinned host memory behind every barrier); p2p_errors() reports it right away at the price of a stream sync
         return p
 
+    def chkdt(self, *args):
+        """the chkdt field reduction + MPI_ALLREDUCE(MAX) of src/chkdt.f90:92,183 (NCCL all-reduce)"""
+        import torch
+        dti = api.chkdt(*args)
+        dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([dti], dtype=torch.float64, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
     def chkdiv(self, *args):
         """chkdiv + the two MPI_ALLREDUCE of src/chkdiv.f90:64-65"""
         import torch

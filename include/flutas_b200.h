@@ -177,6 +177,21 @@ typedef int (*flutas_b200_halo_fn)(void *ctx, const double *send_lo, const doubl
                                    double *recv_hi, size_t count, int lo, int hi, void *stream);
 int flutas_b200_set_halo_exchange(flutas_b200_halo_fn fn, void *ctx);
 
+/* bounduvw, src/bound.f90:17-144 (+ set_bc :227-646, updthalo :946-1110, outflow :649-773): ghost cells of the staggered
+ * velocity for any halo width nh_u (1 = 'cen', 3 = 'fll'; up to 8).  cbc(0:1,3,3) as 18 characters and bc(0:1,3,3) as 18
+ * values in Fortran storage order (side, direction, component); isoutflow(0:1,3) as six ints (0 / non-zero);
+ * dl(3); dzc, dzf(1-nh_d:).  The reference's `halo` argument (MPI datatypes) has no counterpart.  Same step order as the
+ * reference, so edges and corners are bit-identical.  On a z-slab decomposition the nh_u z-halo planes per side travel
+ * through the flutas_b200_set_halo_exchange callback; the z walls and z outflow are applied on ranks 0 / nranks-1 only. */
+int flutas_b200_bounduvw(const char cbc[18], const int n[3], const double bc[18], int nh_d, int nh_u, const int isoutflow[6],
+                         const double dl[3], const double *dzc, const double *dzf, double *u, double *v, double *w);
+
+/* chkdt_sp / chkdt_tw, src/chkdt.f90:24-199: the field reduction only (:62-85 = :150-173) -- this rank's maximum of the
+ * convective inverse time scales dtix, dtiy, dtiz.  The caller all-reduces it (MPI_MAX, :92,183) and evaluates the scalar
+ * formulas with its physical parameters (:93-110, :184-196) as the reference does.  Synchronous. */
+int flutas_b200_chkdt(int nx, int ny, int nz, double dxi, double dyi, double dzi, int nh_d, int nh_u, const double *dzci,
+                      const double *dzfi, const double *u, const double *v, const double *w, double *dti);
+
 /* Optional per-stage device timing (CUDA events on the library stream), the counterpart of the
  * reference's named profiler clocks (src/profiler.f90:103-205; labels "SOLVER", "CORREC", ...).
  * Stage ids 0..count-1 have names ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd", "fillps",

@@ -87,6 +87,38 @@ def main():
         if rank == 0:
             print("slab boundp x%d %-5s %s: %s" % (world, name, "/".join(cbc), "bit-exact" if flag.item() == 0 else "MISMATCH"), flush=True)
         ok = ok and flag.item() == 0
+        # bounduvw (nh_u = 1 and 3) and the chkdt reduction on the slabs: bit-exact against the single-rank numpy oracle
+        for nh in (1, 3):
+            if n3l < nh + 1:
+                continue
+            nh_d = 3
+            sh = (n1 + 2 * nh, n2 + 2 * nh, n3 + 2 * nh)
+            rngv = np.random.default_rng(11 + nh)
+            full = [np.asfortranarray(rngv.uniform(-1, 1, sh)) for _ in range(3)]
+            dzc3 = rngv.uniform(0.05, 0.15, n3 + 2 * nh_d)
+            dzf3 = rngv.uniform(0.05, 0.15, n3 + 2 * nh_d)
+            vt = ["PP" if c == "PP" else "DD" for c in cbc]                   # no-slip walls where the pressure is not periodic
+            vcbc = [[[d[ib]] * 3 for d in vt] for ib in (0, 1)]
+            vbc = [[[0.0] * 3 for _ in range(3)] for _ in range(2)]
+            if vt[2] == "DD":
+                vbc[1][2][0] = 1.5                                             # moving top wall
+            iso = [[False] * 3, [False] * 3]
+            ref = [f.copy(order="F") for f in full]
+            oracle.bounduvw(vcbc, ng, vbc, nh_d, nh, iso, s.dl, dzc3, dzf3, *ref)
+            mine = [np.asfortranarray(f[:, :, k0:k0 + n3l + 2 * nh].copy()) for f in full]
+            md3 = [api.device_field(f) for f in mine]
+            dzc_l = np.ascontiguousarray(dzc3[k0:k0 + n3l + 2 * nh_d])
+            dzf_l = np.ascontiguousarray(dzf3[k0:k0 + n3l + 2 * nh_d])
+            api.bounduvw(vcbc, nl, vbc, nh_d, nh, iso, s.dl, dzc_l, dzf_l, *md3)
+            torch.cuda.synchronize()
+            same = all(np.array_equal(api.host_field(t, m.shape), r[:, :, k0:k0 + n3l + 2 * nh]) for t, m, r in zip(md3, mine, ref))
+            dti_ref = oracle.chkdt_dti(ng, s.dli, nh_d, nh, 1.0 / dzc3, 1.0 / dzf3, *ref)
+            dti = comm.chkdt(n1, n2, n3l, *s.dli, nh_d, nh, np.ascontiguousarray(1.0 / dzc_l), np.ascontiguousarray(1.0 / dzf_l), *md3)
+            flag = torch.tensor([0 if (same and dti == dti_ref) else 1], device="cuda")
+            dist.all_reduce(flag)
+            if rank == 0:
+                print("slab bounduvw nh=%d + chkdt x%d %-5s: %s" % (nh, world, name, "bit-exact" if flag.item() == 0 else "MISMATCH"), flush=True)
+            ok = ok and flag.item() == 0
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
