@@ -316,13 +316,15 @@ def main():
     rhsbx = np.asfortranarray(s.rhsbx[:, k0:k0 + n3, :])     # boundary constants of this rank's slab (bound.f90:829-944)
     rhsby = np.asfortranarray(s.rhsby[:, k0:k0 + n3, :])
     dzc_loc = np.ascontiguousarray(s.dzc[k0:k0 + n3 + 2 * case.nh_d])
+    # the boundary-constant arrays are uploaded once, like the fields (a device-resident time loop does the same)
+    rhsb_dev = tuple(api.device_field(np.asfortranarray(a)) for a in (rhsbx, rhsby, s.rhsbz))
 
     def fill():
         if args.solver_only:
             pd.copy_(rhs0)
             return
         api.fillps(*n, case.nh_d, case.nh_u, *s.dli, dzfi, case.dti, case.rho0, ud, vd, wd, pd)
-        api.updt_rhs_b(*n, case.cbc, rhsbx, rhsby, s.rhsbz, pd)      # z faces: ranks 0 and N-1 only (library gates them)
+        api.updt_rhs_b(*n, case.cbc, *rhsb_dev, pd)                  # z faces: ranks 0 and N-1 only (library gates them)
 
     def solve(p=None):
         p = pd if p is None else p

@@ -665,6 +665,15 @@ void* flutas_b200_alloc(size_t bytes) {
   if (cudaMalloc(&p, bytes) != cudaSuccess) { fail(FLUTAS_B200_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); return nullptr; }
   return p;
 }
+// managed memory: valid on the host (un-ported Fortran routines keep working on the same arrays, pages migrate) and on
+// the device (every entry point of this library then runs in place, asynchronously) -- what the reference's GPU build uses
+// for all its fields (main__single_phase.f90:157-163)
+void* flutas_b200_alloc_managed(size_t bytes) {
+  if (ensure_device()) return nullptr;
+  void* p = nullptr;
+  if (cudaMallocManaged(&p, bytes, cudaMemAttachGlobal) != cudaSuccess) { fail(FLUTAS_B200_ERR_CUDA, "cudaMallocManaged(%zu) failed", bytes); return nullptr; }
+  return p;
+}
 void flutas_b200_free(void* p) { if (p) cudaFree(p); }
 int flutas_b200_memcpy(void* dst, const void* src, size_t bytes) {
   if (int rc = ensure_device()) return rc;
@@ -1161,20 +1170,29 @@ int flutas_b200_updt_rhs_b(int nx, int ny, int nz, const char cbc[6], const doub
   double* rx = g_coef.as<double>();
   double* ry = rx + cx;
   double* rz = ry + cy;
-  CK(cudaMemcpyAsync(rx, rhsbx, cx * sizeof(double), cudaMemcpyDefault, g_stream));
-  CK(cudaMemcpyAsync(ry, rhsby, cy * sizeof(double), cudaMemcpyDefault, g_stream));
-  CK(cudaMemcpyAsync(rz, rhsbz, cz * sizeof(double), cudaMemcpyDefault, g_stream));
   // periodic directions contribute nothing (bc_rhs factor = 0, initsolver.f90:263-294); skipping the
-  // launch there is a bit-exact no-op (+0.0)
+  // launch there is a bit-exact no-op (+0.0).  Boundary arrays that already live on the device are used in place
+  // (a device-resident time loop uploads them once); host arrays are staged, and only for the directions that need them.
+  auto face_array = [&](const double* src, double* stage, size_t cnt, const double** out) -> int {
+    if (on_device(src)) { *out = src; return 0; }
+    CK(cudaMemcpyAsync(stage, src, cnt * sizeof(double), cudaMemcpyDefault, g_stream));
+    *out = stage;
+    return 0;
+  };
+  const double *dx_ = nullptr, *dy_ = nullptr, *dz_ = nullptr;
   if (cbc[0] != 'P' || cbc[1] != 'P') {
-    updt_rhs_b_kernel<<<(unsigned)((cx / 2 + 255) / 256), 256, 0, g_stream>>>(g, rx, fp.dev);
+    if (int rc = face_array(rhsbx, rx, cx, &dx_)) return rc;
+    updt_rhs_b_kernel<<<(unsigned)((cx / 2 + 255) / 256), 256, 0, g_stream>>>(g, dx_, fp.dev);
     LAUNCHED();
   }
   if (cbc[2] != 'P' || cbc[3] != 'P') {
-    updt_rhs_b_y_kernel<<<(unsigned)((cy / 2 + 255) / 256), 256, 0, g_stream>>>(g, ry, fp.dev);
+    if (int rc = face_array(rhsby, ry, cy, &dy_)) return rc;
+    updt_rhs_b_y_kernel<<<(unsigned)((cy / 2 + 255) / 256), 256, 0, g_stream>>>(g, dy_, fp.dev);
     LAUNCHED();
   }
   if (cbc[4] != 'P' || cbc[5] != 'P') {
+    if (int rc = face_array(rhsbz, rz, cz, &dz_)) return rc;
+    const double* rz = dz_;
     // z-slab decomposition (flutas_b200_init): the z faces belong to ranks 0 and nranks-1 only -- on the others the
     // neighbour is a rank, not MPI_PROC_NULL (bound.f90:915,929); x and y are never decomposed in this layout
     const int sides = (g_nranks == 1) ? 3 : ((g_rank == 0 ? 1 : 0) | (g_rank == g_nranks - 1 ? 2 : 0));

@@ -30,6 +30,8 @@ def load():
     L.flutas_b200_set_stream.argtypes = [vp]
     L.flutas_b200_alloc.restype = vp
     L.flutas_b200_alloc.argtypes = [C.c_size_t]
+    L.flutas_b200_alloc_managed.restype = vp
+    L.flutas_b200_alloc_managed.argtypes = [C.c_size_t]
     L.flutas_b200_free.argtypes = [vp]
     L.flutas_b200_memcpy.argtypes = [vp, vp, C.c_size_t]
     L.flutas_b200_fftini.argtypes = [ip, ip, cc, cc, C.POINTER(vp), _dp]
@@ -73,7 +75,7 @@ def check(rc):
 
 EXPORTS = [
     "flutas_b200_version", "flutas_b200_last_error", "flutas_b200_init", "flutas_b200_set_stream",
-    "flutas_b200_alloc", "flutas_b200_free", "flutas_b200_memcpy", "flutas_b200_synchronize",
+    "flutas_b200_alloc", "flutas_b200_alloc_managed", "flutas_b200_free", "flutas_b200_memcpy", "flutas_b200_synchronize",
     "flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_solver_invalidate",
     "flutas_b200_fillps", "flutas_b200_updt_rhs_b", "flutas_b200_correc", "flutas_b200_chkdiv",
     "flutas_b200_launch_count", "flutas_b200_profile_enable", "flutas_b200_profile_stage_count",

@@ -44,7 +44,8 @@ int flutas_b200_set_stream(void *cuda_stream);
 
 /* Device memory for fields (the reference uses CUDA managed arrays, main__single_phase.f90:157-163;
  * a gfortran host maps these with c_f_pointer). */
-void *flutas_b200_alloc(size_t bytes);
+void *flutas_b200_alloc(size_t bytes);              /* device memory (cudaMalloc)                                        */
+void *flutas_b200_alloc_managed(size_t bytes);      /* managed memory: host code may touch it too (cudaMallocManaged)    */
 void flutas_b200_free(void *ptr);
 int flutas_b200_memcpy(void *dst, const void *src, size_t bytes);   /* any direction, synchronous */
 int flutas_b200_synchronize(void);

@@ -62,6 +62,15 @@ def test_header_is_plain_c_and_the_shim_binds_every_compute_entry_point():
     bound = set(re.findall(r"bind\(C,\s*name='(flutas_b200_\w+)'\)", shim))
     needed = {"flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_fillps", "flutas_b200_correc",
               "flutas_b200_chkdiv", "flutas_b200_boundp", "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src",
-              "flutas_b200_pold_update", "flutas_b200_load"}
+              "flutas_b200_pold_update", "flutas_b200_load", "flutas_b200_updt_rhs_b", "flutas_b200_solver_slab",
+              "flutas_b200_p2p_export", "flutas_b200_p2p_attach", "flutas_b200_set_halo_exchange", "flutas_b200_bounduvw",
+              "flutas_b200_chkdt", "flutas_b200_init", "flutas_b200_alloc_managed"}
+    for mod in ("mod_fft", "mod_solver_cpu", "mod_solver_gpu", "mod_fillps", "mod_correc", "mod_chkdiv"):
+        assert re.search(r"^module %s\b" % mod, shim, re.M), mod          # the main's `use` lines resolve unchanged
+    for proc in ("solver_cpu(n,arrplan,normfft,lambdaxy,a,b,c,bcz,c_or_f,p)",
+                 "updt_rhs_b(nx,ny,nz,c_or_f,cbc,nh_p,rhsbx,rhsby,rhsbz,p)",
+                 "bounduvw(cbc,n,bc,nh_d,nh_u,halo,isoutflow,dl,dzc,dzf,u,v,w)",
+                 "chkdt_sp(nx,ny,nz,dxi,dyi,dzi,nh_d,nh_u,dzci,dzfi,u,v,w,dtmax)"):
+        assert "subroutine " + proc in shim, proc                            # the reference's argument lists
     assert needed <= bound, needed - bound
     assert bound <= set(_declared_symbols()), bound - set(_declared_symbols())
