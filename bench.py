@@ -28,7 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_PT = {"xfft_fwd": 16, "yfft_fwd": 16, "thomas_z": 16, "yfft_bwd": 16, "xfft_bwd": 16,
-                    "fillps": 32, "correc": 56}
+                    "fillps": 32, "correc": 56,
+                    "thomas_z_corr": 16}                 # second local sweep of the distributed z solve (N > 1 only)
 SOLVER_BYTES_PER_PT = 80
 
 
@@ -167,12 +168,21 @@ def run_reference(args, rank, world):
 NOMINAL_HBM_GBS = 8000.0                                 # the north star's nominal figure, reported next to the measured peak
 
 
-def nvlink_figures(stage_tbl, stages, npts_loc, world, exchange):
-    """NVLink side of the roofline: bytes each GPU sends per exchange and the rate the stage that carries
-    them achieves (direct stores: the y-transform / z-solve kernels themselves; NCCL: the all-to-all)."""
+def nvlink_figures(stage_tbl, stages, npts_loc, world, exchange, ncol=None):
+    """NVLink side of the roofline.  Transpose path: bytes each GPU sends per exchange and the rate the stage
+    that carries them achieves (direct stores: the y-transform / z-solve kernels themselves; NCCL: the all-to-all).
+    Distributed z solve: only boundary planes cross the link -- 32 bytes per column per solve."""
+    nv = {"exchange": exchange, "peak_GBs_per_direction": 900.0, "measured_peer_copy_GBs": 770.0}
+    if "z_interface" in stages and stages["z_interface"][1]:
+        nv["z_path"] = "distributed z solve (dz.cuh): no all-to-all transposes"
+        nv["z_interface_ms"] = round(stages["z_interface"][0] / stages["z_interface"][1], 4)
+        if ncol:
+            nv["bytes_sent_per_gpu_per_solve"] = 32.0 * ncol * (world - 1) / world
+            nv["bytes_a_transpose_pair_would_send"] = 16.0 * npts_loc * (world - 1) / world
+        return nv
     sent = 8.0 * npts_loc * (world - 1) / world
-    nv = {"exchange": exchange, "bytes_sent_per_gpu_per_exchange": sent, "peak_GBs_per_direction": 900.0,
-          "measured_peer_copy_GBs": 770.0}
+    nv["z_path"] = "two fused all-to-all transposes"
+    nv["bytes_sent_per_gpu_per_exchange"] = sent
     if exchange == "p2p":
         for nm in ("yfft_fwd", "thomas_z"):
             if nm in stage_tbl:
@@ -310,8 +320,10 @@ def main():
         tune_p = torch.zeros((n3 + 2, n2 + 2, n1 + 2), dtype=torch.float64, device="cuda")
         best, times = comm.autotune(lambda: comm.solver(n, pl, nf, lam_win, s.a, s.b, s.c, case.cbc[2], "ccc", tune_p))
         del tune_p
-        slab_schedule = {"pipe_chunks": best[0], "pipe_xsm_pct": best[1],
-                         "candidates_ms": {"%d/%d" % k: round(v, 4) for k, v in times.items()}}
+        slab_schedule = {"distributed_z": bool(best[0]), "pipe_chunks": best[1], "pipe_xsm_pct": best[2],
+                         "candidates_ms": {"dz=%d pipe=%d/%d" % k: round(v, 4) for k, v in times.items()},
+                         "note": "distributed_z: z stage = two local sweeps around a 2N x 2N interface system per column, no "
+                                 "all-to-all transposes (flutas_b200/csrc/dz.cuh); else the fused-transpose path"}
     k0 = rank * n3
     rhsbx = np.asfortranarray(s.rhsbx[:, k0:k0 + n3, :])     # boundary constants of this rank's slab (bound.f90:829-944)
     rhsby = np.asfortranarray(s.rhsby[:, k0:k0 + n3, :])
@@ -391,7 +403,7 @@ def main():
                                         "frac_of_nominal_8TBs": round(SOLVER_BYTES_PER_PT * value / world / NOMINAL_HBM_GBS, 4)},
                              "stages": tbl}}
         if world > 1:
-            line["roofline"]["nvlink"] = nvlink_figures(tbl, stages, npts_loc, world, exchange)
+            line["roofline"]["nvlink"] = nvlink_figures(tbl, stages, npts_loc, world, exchange, n1 * n2)
         if rank == 0:
             print(json.dumps(line))
         api.fftend(pl)
@@ -407,12 +419,19 @@ def main():
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nps = max(3, min(args.steps, 10))
     bc0 = np.zeros((3, 2))
-    p0.record()
-    for _ in range(nps):
+
+    def pressure_step():
         fill()
         solve()
         api.boundp(case.cbc, n, bc0, case.nh_d, 1, s.dl, dzc_loc, dzc_loc, pd)     # ghost cells of p (bound.f90:146); N > 1: z halo over NCCL
         api.correc(*n, case.nh_d, case.nh_u, *s.dli, dzci, case.dt, case.rho0, pd, ud, vd, wd)
+
+    pressure_step()                                      # untimed: first use of the halo exchange creates its NCCL channels
+    barrier()
+    api.profile_read()
+    p0.record()
+    for _ in range(nps):
+        pressure_step()
     p1.record()
     barrier()
     ms_pressure_step = p0.elapsed_time(p1) / nps
@@ -459,7 +478,7 @@ def main():
             continue
         gbs = ALG_BYTES_PER_PT[name] * npts_loc / (avg * 1e-3) / 1e9
         stage_tbl[name] = {"ms": round(avg, 4), "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)}
-    solver_stages = [k for k in ("xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd") if k in stage_tbl]
+    solver_stages = [k for k in ("xfft_fwd", "yfft_fwd", "thomas_z", "thomas_z_corr", "yfft_bwd", "xfft_bwd") if k in stage_tbl]
     dom = max(solver_stages, key=lambda k: stage_tbl[k]["ms"])
     traffic = None                                       # per-launch DRAM bytes from the committed 1-GPU ncu capture
     try:
@@ -477,7 +496,7 @@ def main():
                            "frac_of_nominal_8TBs": round(SOLVER_BYTES_PER_PT * value / world / NOMINAL_HBM_GBS, 4)},
                 "stages": stage_tbl}
     if world > 1:
-        roofline["nvlink"] = nvlink_figures(stage_tbl, stages, npts_loc, world, exchange)
+        roofline["nvlink"] = nvlink_figures(stage_tbl, stages, npts_loc, world, exchange, n1 * n2)
 
     cpu = None
     if parity is not None and parity.get("oracle_solve_s"):

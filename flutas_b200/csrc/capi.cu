@@ -24,6 +24,7 @@
 #include "thomas_tile.cuh"
 #include "thomas_ref.cuh"
 #include "bounduvw.cuh"
+#include "dz.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -66,9 +67,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // optional per-stage timing with CUDA events on the library stream (bench.py's live roofline numbers)
-enum Stage { ST_XF = 0, ST_YF, ST_Z, ST_YB, ST_XB, ST_FILLPS, ST_CORREC, ST_EXCH_F, ST_EXCH_B, ST_COUNT };
+enum Stage { ST_XF = 0, ST_YF, ST_Z, ST_YB, ST_XB, ST_FILLPS, ST_CORREC, ST_EXCH_F, ST_EXCH_B, ST_ZC, ST_ZI, ST_COUNT };
 const char* const g_stage_names[ST_COUNT] = {"xfft_fwd", "yfft_fwd", "thomas_z", "yfft_bwd", "xfft_bwd",
-                                             "fillps", "correc", "exchange_fwd", "exchange_bwd"};
+                                             "fillps", "correc", "exchange_fwd", "exchange_bwd", "thomas_z_corr", "z_interface"};
 struct StageRec { int id; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::vector<StageRec> g_prof_recs;
@@ -218,6 +219,19 @@ struct SolverPlan {
   } ref;
   unsigned long long lam_win_gen = 0;
   int lam_win_rank = -1, lam_win_n1l = 0;
+  // distributed z solve (dz.cuh)
+  struct DzState {
+    bool ok = false;
+    unsigned long long gen = ~0ull;
+    int n3l = 0, rank = -1, P = 0;
+    double tol = -1.0;
+    ThomasArgs uni{};
+    double ca = 0.0, cc = 0.0;
+    int nsel = 0;
+    DzOwn own{};
+    DevBuf sel_dev, sel_lam_own;
+    int last_used = 0;           // 1: the last solver_slab call on this plan ran the distributed z solve
+  } dz;
   // slab (multi-GPU) state
   DevBuf sendrecv, pencil, lam_win;
   bool p2p = false;
@@ -553,6 +567,7 @@ int run_z_main(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, 
 int g_pipe_chunks = [] { const char* e = getenv("FLUTAS_B200_PIPE"); return e ? atoi(e) : FB_PIPE_DEFAULT; }();
 int g_pipe_xsm = [] { const char* e = getenv("FLUTAS_B200_PIPE_XSM"); return e ? atoi(e) : 50; }();
 int g_zcopy = [] { const char* e = getenv("FLUTAS_B200_ZCOPY"); return e ? atoi(e) : -1; }();
+int g_dz = [] { const char* e = getenv("FLUTAS_B200_DZ"); return e ? atoi(e) : 1; }();   // distributed z solve where the shape allows it
 flutas_b200_alltoall_fn g_a2a = nullptr;
 void* g_a2a_ctx = nullptr;
 flutas_b200_halo_fn g_halo = nullptr;
@@ -733,6 +748,7 @@ int flutas_b200_fftend(void* arrplan[4]) {
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
+  for (DevBuf* b : {&sp->dz.sel_dev, &sp->dz.sel_lam_own}) b->release();
   for (DevBuf* b : {&sp->ref.col, &sp->ref.lam, &sp->ref.pin, &sp->ref.z, &sp->ref.d, &sp->ref.piv, &sp->ref.p2, &sp->ref.den, &sp->ref.F}) b->release();
   for (int q = 0; q < FB_MAX_RANKS; ++q)
     if (sp->peer_base[q] && sp->peer_base[q] != sp->p2p_alloc) cudaIpcCloseMemHandle(sp->peer_base[q]);
@@ -844,6 +860,20 @@ int flutas_b200_slab_config(int pipe_chunks, int pipe_xsm_pct, int zcopy) {
   return FLUTAS_B200_OK;
 }
 
+// which z stage the last flutas_b200_solver_slab call on this plan used: 1 = distributed (dz.cuh), 0 = transposes
+int flutas_b200_slab_last_distributed(void* const arrplan[4]) {
+  SolverPlan* sp = plan_of(arrplan);
+  return sp ? sp->dz.last_used : 0;
+}
+
+// 1 (default): on a slab decomposition with direct NVLink exchange and an exactly uniform z grid the z stage runs as a
+// distributed tridiagonal solve (dz.cuh) and the two all-to-all transposes disappear; 0: always transpose.  Same value on
+// every rank.
+int flutas_b200_slab_distributed_z(int on) {
+  g_dz = on ? 1 : 0;
+  return FLUTAS_B200_OK;
+}
+
 size_t flutas_b200_p2p_handle_bytes(void) { return sizeof(P2PBlob); }
 
 // Allocates this rank's exchange memory [pencil | recv | flags] and returns its IPC handle in `blob`.
@@ -907,6 +937,11 @@ int flutas_b200_p2p_errors(void* const arrplan[4]) {
   return v;
 }
 
+
+}  // extern "C"
+
+namespace {
+
 // A peer that has not arrived after FLUTAS_B200_P2P_TIMEOUT_S seconds (default 10; SM clock taken as 2 GHz) makes the
 // barrier give up and count an error.  The count is mirrored into pinned host memory right behind every barrier, so
 // the NEXT solver_slab call on the plan (and flutas_b200_p2p_errors at any time) fails instead of returning stale data.
@@ -922,6 +957,181 @@ static int p2p_barrier(SolverPlan* sp) {
   if (sp->h_err) CK(cudaMemcpyAsync(sp->h_err, sp->d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
   return 0;
 }
+
+// true when the distributed z solve can serve this plan / decomposition (the same answer on every rank)
+bool dz_shape_ok(const SolverPlan* sp, int n1, int n2, int n3l, int P) {
+  const long ncol = (long)n1 * n2;
+  return g_dz && sp->p2p && sp->thomas_mode == 0 && g_z_uniform_ok && sp->z_uniform.uniform && P >= 2 && P <= FB_DZ_MAXG &&
+         n3l % 16 == 0 && n3l / 16 >= 2 && n3l / 16 <= 32 && (ncol % 2) == 0 && (ncol % P) == 0 && ((ncol / P) % 2) == 0;
+}
+
+struct DzLayout {                 // offsets (doubles) inside every rank's [pencil | recv] exchange allocation
+  long ncol, ncol_own;
+  size_t oYF, oYL, oPF, oPL, oQF, oQL, oXP, oXN;     // pencil region
+  size_t oGATH, oOVR;                                 // recv region
+};
+DzLayout dz_layout(long ncol, int P, int nsel, int ng3) {
+  DzLayout L;
+  L.ncol = ncol; L.ncol_own = ncol / P;
+  L.oYF = 0; L.oYL = (size_t)ncol; L.oPF = 2 * (size_t)ncol; L.oPL = 3 * (size_t)ncol; L.oQF = 4 * (size_t)ncol;
+  L.oQL = 5 * (size_t)ncol; L.oXP = 6 * (size_t)ncol; L.oXN = 7 * (size_t)ncol;
+  L.oGATH = 0; L.oOVR = (size_t)nsel * ng3 + ((size_t)nsel * ng3 & 1);
+  return L;
+}
+DzPeers dz_peers(double* const* base, int P, size_t off) {
+  DzPeers d;
+  for (int q = 0; q < FB_DZ_MAXG; ++q) d.p[q] = (q < P) ? base[q] + off : nullptr;
+  return d;
+}
+
+// once per plan / coefficient generation: local block description, the reference-order column list, and the
+// right-hand-side independent interface coefficients p, q (two local solves on unit right-hand sides)
+int dz_setup(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, bool periodic, int singular) {
+  SolverPlan::DzState& dz = sp->dz;
+  if (dz.gen == sp->cache_gen && dz.n3l == n3l && dz.rank == r && dz.P == P && dz.tol == g_ref_tol) return 0;
+  dz.gen = sp->cache_gen; dz.n3l = n3l; dz.rank = r; dz.P = P; dz.tol = g_ref_tol;
+  dz.ok = false;
+  const int ng3 = n3l * P, k0 = r * n3l;
+  const long ncol = (long)n1 * n2;
+  const size_t nloc = (size_t)ncol * n3l;
+  if ((int)sp->h_a.size() != ng3) return 0;
+  if (!thomas_detect_uniform(n3l, sp->h_a.data() + k0, sp->h_b.data() + k0, sp->h_c.data() + k0, false, dz.uni)) return 0;
+  dz.ca = (periodic || r > 0) ? sp->h_a[k0] : 0.0;
+  dz.cc = (periodic || r < P - 1) ? sp->h_c[k0 + n3l - 1] : 0.0;
+  const double* lam = sp->lam_int.as<double>();
+  // reference-order columns: the same list on every rank (the eigenvalues are identical everywhere)
+  std::vector<int> sel;
+  std::vector<double> hl((size_t)ncol);
+  CK(cudaMemcpyAsync(hl.data(), lam, (size_t)ncol * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if (g_ref_tol > 0.0 && ref_smem_per_warp(ng3) <= REF_MAX_SMEM) {
+    double amax = 0.0;
+    for (int k = 0; k < ng3; ++k) amax = std::max(amax, std::max(std::fabs(sp->h_a[k]), std::fabs(sp->h_c[k])));
+    const double thr = 4.0 * amax * g_ref_tol;
+    for (long q = 0; q < ncol; ++q) if (std::fabs(hl[q]) < thr) sel.push_back((int)q);
+    if ((int)sel.size() > REF_MAX_COLUMNS) {
+      std::nth_element(sel.begin(), sel.begin() + REF_MAX_COLUMNS, sel.end(),
+                       [&](int x, int y) { return std::fabs(hl[x]) < std::fabs(hl[y]); });
+      sel.resize(REF_MAX_COLUMNS);
+      std::sort(sel.begin(), sel.end());
+    }
+  }
+  dz.nsel = (int)sel.size();
+  if (8 * (size_t)ncol > nloc || (size_t)dz.nsel * (size_t)(ng3 + n3l) + 2 > nloc) return 0;     // exchange areas do not fit
+  const long ncol_own = ncol / P;
+  for (int q = 0; q <= P; ++q) dz.own.own0[q] = (int)(std::lower_bound(sel.begin(), sel.end(), (int)std::min<long>(q * ncol_own, ncol)) - sel.begin());
+  for (int q = P + 1; q <= FB_DZ_MAXG; ++q) dz.own.own0[q] = dz.nsel;
+  const int nown = dz.own.own0[r + 1] - dz.own.own0[r];
+  if (dz.nsel) {
+    if (int rc = dz.sel_dev.reserve(dz.nsel * sizeof(int))) return rc;
+    CK(cudaMemcpyAsync(dz.sel_dev.p, sel.data(), dz.nsel * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    std::vector<double> lo((size_t)std::max(nown, 1));
+    for (int q = 0; q < nown; ++q) lo[q] = hl[sel[dz.own.own0[r] + q]];
+    if (int rc = dz.sel_lam_own.reserve(lo.size() * sizeof(double))) return rc;
+    CK(cudaMemcpyAsync(dz.sel_lam_own.p, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (nown) {                                            // factor tables of the owned columns, global coefficients
+      if (int rc = ensure_ref(sp, nown, ng3, dz.sel_lam_own.as<double>(), periodic, singular)) return rc;
+      if (sp->ref.nsel != nown) return fail(FLUTAS_B200_ERR_ARG, "distributed z: reference-order selection mismatch (%d != %d)", sp->ref.nsel, nown);
+    }
+  }
+  // p = T_g^{-1}(a_first e_first), q = T_g^{-1}(c_last e_last) at the first / last level -> the column owners
+  const DzLayout L = dz_layout(ncol, P, dz.nsel, ng3);
+  double* S = sp->peer_recv[r];                            // scratch: the recv region is free outside a solve
+  const int nsm = g_nsm > 0 ? g_nsm : 148;
+  const int sing_loc = (singular && r == P - 1) ? 1 : 0;
+  const unsigned nb = (unsigned)((ncol + 255) / 256);
+  for (int pass = 0; pass < 2; ++pass) {
+    CK(cudaMemsetAsync(S, 0, nloc * sizeof(double), g_stream));
+    dz_fill_plane_kernel<<<nb, 256, 0, g_stream>>>(pass == 0 ? S : S + (size_t)ncol * (n3l - 1), ncol, pass == 0 ? dz.ca : dz.cc);
+    LAUNCHED();
+    bool done = false;
+    int rc = thomas_uni_local_run(ncol, n3l, lam, S, sing_loc, nsm, &dz.uni, nullptr, g_stream, &done);
+    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "distributed z set-up: local solve failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (!done) return 0;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    dz_send_planes_kernel<<<nb, 256, 0, g_stream>>>(ncol, ncol_own, r, S, S + (size_t)ncol * (n3l - 1),
+                                                     dz_peers(sp->peer_pencil, P, pass == 0 ? L.oPF : L.oQF),
+                                                     dz_peers(sp->peer_pencil, P, pass == 0 ? L.oPL : L.oQL));
+    LAUNCHED();
+  }
+  dz.ok = true;
+  return 0;
+}
+
+// the z stage of the slab solver without transposes; W1 = this rank's slab (n1, n2, n3l) after the forward y transform
+int dz_solve_z(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, double* W1, bool periodic, int singular) {
+  SolverPlan::DzState& dz = sp->dz;
+  const int ng3 = n3l * P, k0 = r * n3l;
+  const long ncol = (long)n1 * n2, ncol_own = ncol / P;
+  const DzLayout L = dz_layout(ncol, P, dz.nsel, ng3);
+  const double* lam = sp->lam_int.as<double>();
+  const int nsm = g_nsm > 0 ? g_nsm : 148;
+  const int sing_loc = (singular && r == P - 1) ? 1 : 0;
+  const unsigned nb = (unsigned)((ncol + 255) / 256);
+  double* mine = sp->peer_pencil[r];
+  double* mine_recv = sp->peer_recv[r];
+  const int nown = dz.own.own0[r + 1] - dz.own.own0[r];
+  bool done = false;
+  {
+    StageTimer t(ST_Z);
+    if (dz.nsel) {                                         // the reference-order columns, whole, to their owners (before y overwrites b)
+      const long cnt = (long)dz.nsel * n3l;
+      dz_gather_sel_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(dz.nsel, n3l, k0, ncol, ncol_own, dz.sel_dev.as<int>(), W1,
+                                                                                dz.own, dz_peers(sp->peer_recv, P, L.oGATH));
+      LAUNCHED();
+    }
+    int rc = thomas_uni_local_run(ncol, n3l, lam, W1, sing_loc, nsm, &dz.uni, nullptr, g_stream, &done);      // pass 1
+    if (rc || !done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: local solve failed (%s)", rc ? cudaGetErrorString((cudaError_t)rc) : "shape");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  {
+    StageTimer t(ST_ZI);
+    dz_send_planes_kernel<<<nb, 256, 0, g_stream>>>(ncol, ncol_own, r, W1, W1 + (size_t)ncol * (n3l - 1),
+                                                     dz_peers(sp->peer_pencil, P, L.oYF), dz_peers(sp->peer_pencil, P, L.oYL));
+    LAUNCHED();
+    if (int rc = p2p_barrier(sp)) return rc;
+    dz_interface_kernel<<<(unsigned)((ncol_own + 127) / 128), 128, 0, g_stream>>>(P, ncol_own, (long)r * ncol_own, mine + L.oPF, mine + L.oPL,
+                                                                                   mine + L.oQF, mine + L.oQL, mine + L.oYF, mine + L.oYL,
+                                                                                   dz_peers(sp->peer_pencil, P, L.oXP), dz_peers(sp->peer_pencil, P, L.oXN));
+    LAUNCHED();
+    if (nown) {
+      SolverPlan::RefFix& rf = sp->ref;
+      const size_t per = ref_smem_per_warp(ng3);
+      int warps = (int)(REF_MAX_SMEM / per);
+      warps = warps > 4 ? 4 : warps;
+      static size_t configured = 0;
+      if (per * warps > configured) {
+        CK(cudaFuncSetAttribute(ref_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per * warps)));
+        configured = per * warps;
+      }
+      ref_solve_kernel<<<(unsigned)((nown + warps - 1) / warps), 32 * warps, per * warps, g_stream>>>(rf.T, (long)nown, mine_recv + L.oGATH, rf.F.as<double>());
+      LAUNCHED();
+      const long cnt = (long)nown * ng3;
+      dz_push_sel_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(nown, dz.own.own0[r], ng3, n3l, rf.F.as<double>(),
+                                                                              dz_peers(sp->peer_recv, P, L.oOVR));
+      LAUNCHED();
+    }
+    if (int rc = p2p_barrier(sp)) return rc;
+  }
+  {
+    StageTimer t(ST_ZC);
+    const ThomasCorr corr{mine + L.oXP, mine + L.oXN, dz.ca, dz.cc};
+    int rc = thomas_uni_local_run(ncol, n3l, lam, W1, sing_loc, nsm, &dz.uni, &corr, g_stream, &done);          // pass 2
+    if (rc || !done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: correction solve failed (%s)", rc ? cudaGetErrorString((cudaError_t)rc) : "shape");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (dz.nsel) {
+      const long cnt = (long)dz.nsel * n3l;
+      dz_apply_sel_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(dz.nsel, n3l, ncol, dz.sel_dev.as<int>(), mine_recv + L.oOVR, W1);
+      LAUNCHED();
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
 
 int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normfft, const double* lambdaxy_global,
                             const double* a, const double* b, const double* c, const char bcz[2],
@@ -982,6 +1192,29 @@ int flutas_b200_solver_slab(const int n[3], void* const arrplan[4], double normf
   LineGeom gp{1 + s1 * (1 + s2), s1, s1 * s2, n2, (long)n2 * n3l};
   LineGeom gw{0, (long)n1, (long)n1 * n2, n2, (long)n2 * n3l};
 
+  // Distributed z solve (dz.cuh): every transform stays on the rank's own slab, the z stage is two local sweeps around a
+  // 2P x 2P interface system per column, and 32 bytes per COLUMN cross NVLink instead of 14 bytes per POINT.
+  if (dz_shape_ok(sp, n1, n2, n3l, P) && chunk == sp->p2p_chunk) {
+    if (int rc = dz_setup(sp, n1, n2, n3l, P, r, periodic, singular)) return rc;
+    sp->dz.last_used = sp->dz.ok ? 1 : 0;
+    if (sp->dz.ok) {
+      { StageTimer t(ST_XF); if (int rc = run_x<true>(sp->px, pd, gp, W1, gw, 1.0)) return rc; }
+      const SpecGeom sg = local_spec(W1, n1);
+      { StageTimer t(ST_YF); if (int rc = run_y<true>(sp->py, W1, n1, n3l, sg)) return rc; }
+      if (int rc = dz_solve_z(sp, n1, n2, n3l, P, r, W1, periodic, singular)) return rc;
+      { StageTimer t(ST_YB); if (int rc = run_y<false>(sp->py, W1, n1, n3l, sg)) return rc; }
+      { StageTimer t(ST_XB); if (int rc = run_x<false>(sp->px, W1, gw, pd, gp, normfft)) return rc; }
+      if (host_p) {
+        CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (sp->h_err && *sp->h_err)
+          return fail(FLUTAS_B200_ERR_CUDA, "solver_slab: cross-GPU barrier time-out (%d): a peer did not arrive; p is invalid", *sp->h_err);
+      }
+      return FLUTAS_B200_OK;
+    }
+  }
+
+  sp->dz.last_used = 0;
   // Forward half, pipelined over k-chunks (direct-store exchange only): the y transform + NVLink stores of chunk c run on
   // part of the SMs while the x transform of chunk c+1 runs on the rest (second stream), so the HBM-bound x stage hides
   // behind the NVLink-bound y stage.  FLUTAS_B200_PIPE = number of chunks (0/1 = off), FLUTAS_B200_PIPE_XSM = percentage

@@ -175,10 +175,21 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
-template <int L, int TI, int MINB>
+// Distributed z solve (capi.cu, solver_slab_dz): a rank holds n3l consecutive levels of EVERY column.  Pass 1 solves the
+// rank-local block T_g y = b (this kernel, CORR = false, coefficients truncated at the slab ends); after the 2G x 2G
+// interface system has delivered the neighbours' boundary unknowns x_prev, x_next per column, pass 2 (CORR = true) forms
+//     x = y + T_g^{-1} ( -a_first x_prev e_first - c_last x_next e_last )
+// in the same sweep: the tile is read as y, the right-hand side is synthesised in registers, and y + correction is stored.
+struct ThomasCorr {
+  const double* xprev;          // [ncol] last unknown of the rank below (unused where ca == 0)
+  const double* xnext;          // [ncol] first unknown of the rank above
+  double ca, cc;                // the true couplings a(first level), c(last level) that the local block leaves out
+};
+
+template <int L, int TI, int MINB, bool CORR = false>
 __global__ void __launch_bounds__(512 / MINB, MINB)
 thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const __grid_constant__ CUtensorMap tmap,
-                      int box_rows, ColGeom og) {
+                      int box_rows, ColGeom og, ThomasCorr corr) {
   using TU = ThomasUni<L, TI>;
   using TR = ThomasReg<L, TI>;
   extern __shared__ __align__(128) double smem[];
@@ -234,6 +245,15 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
 #pragma unroll
       for (int l = 0; l < L; ++l) v[l] = ts[l * TI];
     }
+    double yv[CORR ? L : 1];
+    if (CORR) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) { yv[l] = v[l]; v[l] = 0.0; }
+      if (live) {
+        if (s == 0) v[0] = -corr.ca * __ldg(corr.xprev + col);
+        if (s == S - 1) v[L - 1] = v[L - 1] - corr.cc * __ldg(corr.xnext + col);
+      }
+    }
     __syncthreads();                                        // tables ready; every thread has its levels: the tile buffer is free
     fetch(tile + gridDim.x);                                // next tile streams in during the rest of this iteration
     TU::phase1(v, tab, T, lane, s, ex);
@@ -253,6 +273,10 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
     TR::pcr_finish(src, X, T, lane, s);
     __syncthreads();
     TU::phase3(v, X, tab, T, lane, s);
+    if (CORR) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) v[l] += yv[l];
+    }
     if (live) {
       if (one_chunk) {
         double* dstp = obase + col;
@@ -400,11 +424,15 @@ inline cudaError_t thomas_uni_tensor_map(const double* W, long ncol, int nz, int
   return cudaSuccess;
 }
 
-template <int L, int TI, int MINB>
+inline int threads_of(const ThomasArgs& T, int ti) { return ti * T.S; }
+
+template <int L, int TI, int MINB, bool CORR = false>
 inline cudaError_t thomas_uni_tma_launch(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
-                                         int nsm, cudaStream_t st) {
+                                         int nsm, cudaStream_t st, const ThomasCorr* corr = nullptr) {
   using TU = ThomasUni<L, TI>;
-  auto kern = thomas_uni_tma_kernel<L, TI, MINB>;
+  auto kern = thomas_uni_tma_kernel<L, TI, MINB, CORR>;
+  if (threads_of(T, TI) > 512 / MINB) return cudaErrorInvalidValue;
+  const ThomasCorr cr = corr ? *corr : ThomasCorr{nullptr, nullptr, 0.0, 0.0};
   const int threads = TI * T.S;
   const int box_rows = T.nz < 256 ? T.nz : 256;
   if (T.nz % box_rows) return cudaErrorInvalidValue;
@@ -424,7 +452,7 @@ inline cudaError_t thomas_uni_tma_launch(long ncol, const ThomasArgs& T, const d
     per_sm = q; cfg_nz = T.nz;
   }
   const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
-  kern<<<(unsigned)grid, threads, smem, st>>>(ncol, ntiles, T, lam, map, box_rows, og);
+  kern<<<(unsigned)grid, threads, smem, st>>>(ncol, ntiles, T, lam, map, box_rows, og, cr);
   return cudaGetLastError();
 }
 
@@ -599,6 +627,31 @@ inline cudaError_t thomas_uni_launch(long ncol, const ThomasArgs& T, const doubl
   const long grid = ntiles < (long)nsm * per_sm ? ntiles : (long)nsm * per_sm;
   kern<<<(unsigned)grid, threads, smem, st>>>(ncol, ntiles, T, lam, W, og);
   return cudaGetLastError();
+}
+
+// Rank-local block of the distributed z solve: nz = n3l levels, never periodic (the wrap-around coupling lives in the
+// interface system), L = 16 levels per thread, S = nz/16 in 2..32 segments -> 32 S threads per tile, 4 / 2 / 1 blocks per SM.
+// corr = nullptr: pass 1 (y = T_g^{-1} b); else pass 2 (x = y + correction).  *done = false: shape not served.
+inline bool thomas_uni_local_ok(int nz, long ncol, const void* W, const void* lam) {
+  return nz % 16 == 0 && nz / 16 >= 2 && nz / 16 <= 32 && (ncol % 2) == 0 && (reinterpret_cast<uintptr_t>(W) % 16) == 0 &&
+         (reinterpret_cast<uintptr_t>(lam) % 16) == 0;
+}
+inline int thomas_uni_local_run(long ncol, int nz, const double* lam, double* W, int singular, int nsm, const ThomasArgs* uni,
+                                const ThomasCorr* corr, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!uni || !uni->uniform || !thomas_uni_local_ok(nz, ncol, W, lam)) return 0;
+  ThomasArgs T = *uni;
+  T.nz = nz; T.S = nz / 16; T.periodic = 0; T.singular = singular; T.az = T.bz = T.cz = nullptr; T.padded = 0;
+  ColGeom og;
+  for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = W;
+  og.n3l = nz; og.koff = 0;
+  cudaError_t e;
+  if (T.S <= 8) e = corr ? thomas_uni_tma_launch<16, 16, 4, true>(ncol, T, lam, W, og, nsm, st, corr) : thomas_uni_tma_launch<16, 16, 4, false>(ncol, T, lam, W, og, nsm, st);
+  else if (T.S <= 16) e = corr ? thomas_uni_tma_launch<16, 16, 2, true>(ncol, T, lam, W, og, nsm, st, corr) : thomas_uni_tma_launch<16, 16, 2, false>(ncol, T, lam, W, og, nsm, st);
+  else e = corr ? thomas_uni_tma_launch<16, 16, 1, true>(ncol, T, lam, W, og, nsm, st, corr) : thomas_uni_tma_launch<16, 16, 1, false>(ncol, T, lam, W, og, nsm, st);
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
+  return 0;
 }
 
 // *done = false if the grid is not exactly uniform or nz is not served (caller: thomas_reg_run).

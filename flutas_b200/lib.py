@@ -59,6 +59,8 @@ def load():
     L.flutas_b200_p2p_attach.argtypes = [C.POINTER(vp), vp]
     L.flutas_b200_p2p_errors.argtypes = [C.POINTER(vp)]
     L.flutas_b200_slab_config.argtypes = [ci, ci, ci]
+    L.flutas_b200_slab_distributed_z.argtypes = [ci]
+    L.flutas_b200_slab_last_distributed.argtypes = [C.POINTER(vp)]
     L.flutas_b200_solver_slab.argtypes = [ip, C.POINTER(vp), cd, vp, vp, vp, vp, cc, cc, vp]
     L.flutas_b200_profile_enable.argtypes = [ci]
     L.flutas_b200_profile_stage_name.restype = cc
@@ -81,6 +83,6 @@ EXPORTS = [
     "flutas_b200_launch_count", "flutas_b200_profile_enable", "flutas_b200_profile_stage_count",
     "flutas_b200_profile_stage_name", "flutas_b200_profile_read", "flutas_b200_set_alltoall",
     "flutas_b200_p2p_handle_bytes", "flutas_b200_p2p_export", "flutas_b200_p2p_attach", "flutas_b200_p2p_errors",
-    "flutas_b200_solver_slab", "flutas_b200_slab_config", "flutas_b200_boundp", "flutas_b200_set_halo_exchange",
+    "flutas_b200_solver_slab", "flutas_b200_slab_config", "flutas_b200_slab_distributed_z", "flutas_b200_slab_last_distributed", "flutas_b200_boundp", "flutas_b200_set_halo_exchange",
     "flutas_b200_bounduvw", "flutas_b200_chkdt", "flutas_b200_pres_sp_src", "flutas_b200_pres_tw_src", "flutas_b200_pold_update", "flutas_b200_load",
 ]

@@ -166,13 +166,19 @@ class SlabComm:
         """schedule knobs of the slab solver (flutas_b200_slab_config); the same values on every rank"""
         _lib.check(_lib.load().flutas_b200_slab_config(int(pipe_chunks), int(pipe_xsm_pct), int(zcopy)))
 
-    def autotune(self, solve, candidates=((0, 50), (2, 30), (4, 30), (4, 50)), reps=3):
-        """Plan-time measurement (the counterpart of FFTW_MEASURE): runs `solve()` under each (pipe_chunks, pipe_xsm_pct)
-        candidate, timed on the device, max over ranks, and keeps the fastest on ALL ranks.  Returns (choice, {cand: ms})."""
+    def distributed_z(self, on=True):
+        """z stage as a distributed tridiagonal solve (no transposes) where the plan allows it; the same value on every rank"""
+        _lib.check(_lib.load().flutas_b200_slab_distributed_z(1 if on else 0))
+
+    def autotune(self, solve, candidates=((1, 0, 50), (0, 0, 50), (0, 4, 50)), reps=3):
+        """Plan-time measurement (the counterpart of FFTW_MEASURE): runs `solve()` under each (distributed_z, pipe_chunks,
+        pipe_xsm_pct) candidate, timed on the device, max over ranks, and keeps the fastest on ALL ranks.
+        Returns (choice, {cand: ms})."""
         import torch
         times = {}
         for cand in candidates:
-            self.configure(cand[0], cand[1])
+            self.distributed_z(bool(cand[0]))
+            self.configure(cand[1], cand[2])
             solve()                                          # first call of a configuration: streams / events are created
             torch.cuda.synchronize()
             self.dist.barrier(group=self.group)
@@ -186,7 +192,8 @@ class SlabComm:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
             times[cand] = float(t.item())
         best = min(times, key=times.get)
-        self.configure(best[0], best[1])
+        self.distributed_z(bool(best[0]))
+        self.configure(best[1], best[2])
         return best, times
 
     def solver(self, n_local, arrplan, normfft, lam_window, a, b, c, bcz, c_or_f, p):

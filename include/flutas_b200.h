@@ -104,6 +104,13 @@ int flutas_b200_p2p_errors(void *const arrplan[4]);
  * A negative pipe_* value leaves that knob unchanged.  Defaults: FLUTAS_B200_PIPE / _PIPE_XSM / _ZCOPY or off/50/-1. */
 int flutas_b200_slab_config(int pipe_chunks, int pipe_xsm_pct, int zcopy);
 
+/* 1 (default): with the direct NVLink exchange attached and an exactly uniform z grid, the z stage of the slab solver
+ * runs as a DISTRIBUTED tridiagonal solve -- two rank-local sweeps around a 2P x 2P interface system per column -- and
+ * the two all-to-all transposes of the reference's slab path (src/solver_gpu.f90:150-153,179-182) disappear: 32 bytes
+ * per column cross NVLink instead of 14 bytes per point.  0: always transpose.  Same value on every rank. */
+int flutas_b200_slab_distributed_z(int on);
+int flutas_b200_slab_last_distributed(void *const arrplan[4]);   /* 1: the last solver_slab call ran the distributed z solve */
+
 /* solver on a z-slab: as flutas_b200_solver, with n = the LOCAL interior size (ng1, ng2, ng3/nranks) and
  * lambdaxy_global = lambdaxy(ng1, ng2) for the whole x-y plane (the shim all-gathers the (ng1, ng2/nranks)
  * windows initsolver produces on each rank, src/initsolver.f90:87-93; done once).  Collective. */

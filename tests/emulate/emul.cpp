@@ -507,3 +507,68 @@ extern "C" int emul_thomas_ref(int nz, long ncol, int periodic, int singular, co
   }
   return ns;
 }
+
+// ---------------------------------------------------------------------------------------------
+// distributed z solve (flutas_b200/csrc/dz.cuh): G ranks each own nz/G consecutive levels of every column.  Same steps
+// as capi.cu's dz_setup / dz_solve_z with the rank-local solves done by the shared-LU kernel's phase functions
+// (thomas_uni_emul<16,16>, exactly what thomas_uni_local_run launches) and the interface systems by dz_interface_solve.
+#include "../../flutas_b200/csrc/dz.cuh"
+
+static bool dz_local_solve(int n3l, long ncol, const ThomasArgs& uni, int singular, const double* lam, double* slab) {
+  ThomasArgs T = uni;
+  T.nz = n3l; T.S = n3l / 16; T.periodic = 0; T.singular = singular; T.az = T.bz = T.cz = nullptr; T.padded = 0;
+  if (n3l % 16 || T.S < 2 || T.S > 32) return false;
+  thomas_uni_emul<16, 16>(ncol, T, lam, slab);
+  return true;
+}
+
+extern "C" int emul_dz(int nz, int G, long ncol, int periodic, int singular, const double* a, const double* b, const double* c,
+                       const double* lam, double* W) {
+  if (G < 2 || G > FB_DZ_MAXG || nz % G) return 1;
+  const int n3l = nz / G;
+  std::vector<ThomasArgs> uni(G);
+  std::vector<double> ca(G), cc(G);
+  std::vector<double> PF((size_t)G * ncol), PL(PF), QF(PF), QL(PF), scratch((size_t)ncol * n3l);
+  for (int g = 0; g < G; ++g) {
+    const int k0 = g * n3l;
+    if (!thomas_detect_uniform(n3l, a + k0, b + k0, c + k0, false, uni[g])) return 2;
+    ca[g] = (periodic || g > 0) ? a[k0] : 0.0;
+    cc[g] = (periodic || g < G - 1) ? c[k0 + n3l - 1] : 0.0;
+    const int sing = (singular && g == G - 1) ? 1 : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      std::fill(scratch.begin(), scratch.end(), 0.0);
+      for (long q = 0; q < ncol; ++q) scratch[(pass == 0 ? 0 : (size_t)ncol * (n3l - 1)) + q] = pass == 0 ? ca[g] : cc[g];
+      if (!dz_local_solve(n3l, ncol, uni[g], sing, lam, scratch.data())) return 3;
+      for (long q = 0; q < ncol; ++q) {
+        (pass == 0 ? PF : QF)[(size_t)g * ncol + q] = scratch[q];
+        (pass == 0 ? PL : QL)[(size_t)g * ncol + q] = scratch[(size_t)ncol * (n3l - 1) + q];
+      }
+    }
+  }
+  // pass 1 on every rank
+  for (int g = 0; g < G; ++g)
+    if (!dz_local_solve(n3l, ncol, uni[g], (singular && g == G - 1) ? 1 : 0, lam, W + (size_t)ncol * g * n3l)) return 3;
+  // interface systems
+  std::vector<double> XP((size_t)G * ncol), XN((size_t)G * ncol);
+  for (long q = 0; q < ncol; ++q) {
+    double pF[FB_DZ_MAXG], pL[FB_DZ_MAXG], qF[FB_DZ_MAXG], qL[FB_DZ_MAXG], yF[FB_DZ_MAXG], yL[FB_DZ_MAXG], u[2 * FB_DZ_MAXG];
+    for (int g = 0; g < G; ++g) {
+      pF[g] = PF[(size_t)g * ncol + q]; pL[g] = PL[(size_t)g * ncol + q]; qF[g] = QF[(size_t)g * ncol + q]; qL[g] = QL[(size_t)g * ncol + q];
+      yF[g] = W[(size_t)ncol * g * n3l + q]; yL[g] = W[(size_t)ncol * (g * n3l + n3l - 1) + q];
+    }
+    dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
+    for (int g = 0; g < G; ++g) { XP[(size_t)g * ncol + q] = u[2 * ((g + G - 1) % G) + 1]; XN[(size_t)g * ncol + q] = u[2 * ((g + 1) % G)]; }
+  }
+  // pass 2: x = y + T_g^{-1}(-ca x_prev e_first - cc x_next e_last)   (the CORR variant of the kernel)
+  for (int g = 0; g < G; ++g) {
+    std::fill(scratch.begin(), scratch.end(), 0.0);
+    for (long q = 0; q < ncol; ++q) {
+      scratch[q] = -ca[g] * XP[(size_t)g * ncol + q];
+      scratch[(size_t)ncol * (n3l - 1) + q] += -cc[g] * XN[(size_t)g * ncol + q];
+    }
+    if (!dz_local_solve(n3l, ncol, uni[g], (singular && g == G - 1) ? 1 : 0, lam, scratch.data())) return 3;
+    double* y = W + (size_t)ncol * g * n3l;
+    for (size_t i = 0; i < (size_t)ncol * n3l; ++i) y[i] += scratch[i];
+  }
+  return 0;
+}

@@ -24,8 +24,20 @@ def main():
     api.init(lrank, rank, world)
     comm = slab.SlabComm()
     ok = True
-    for name, ng, cbc, gr in (("chan", (128, 64, 32), ("PP", "PP", "NN"), 1.0), ("hit", (64, 64, 64), ("PP", "PP", "PP"), 0.0),
-                              ("rb", (64, 48, 40), ("NN", "NN", "NN"), 0.0), ("dd72", (32, 40, 72), ("DD", "NN", "DD"), 0.0)):
+    from flutas_b200 import lib
+    transposes = mode.endswith("-transpose")                # p2p-transpose: the all-to-all path even where the distributed z solve applies
+    if mode.startswith("p2p"):
+        lib.check(lib.load().flutas_b200_slab_distributed_z(0 if transposes else 1))
+        mode = "p2p"
+    # the uni-* grids have exactly uniform z rows (lz = 1) and n3l a multiple of 16: with p2p they run the distributed z solve;
+    # uni-fix widens the reference-order selection so that many whole columns travel through the gather / override path
+    cases = (("chan", (128, 64, 32), ("PP", "PP", "NN"), 1.0, None), ("hit", (64, 64, 64), ("PP", "PP", "PP"), 0.0, None),
+             ("rb", (64, 48, 40), ("NN", "NN", "NN"), 0.0, None), ("dd72", (32, 40, 72), ("DD", "NN", "DD"), 0.0, None),
+             ("uni-chan", (64, 32, 128), ("PP", "PP", "NN"), 0.0, None), ("uni-per", (32, 32, 128), ("PP", "PP", "PP"), 0.0, None),
+             ("uni-rb", (64, 64, 64), ("NN", "NN", "NN"), 0.0, None), ("uni-dn", (32, 64, 256), ("ND", "PP", "DD"), 0.0, None),
+             ("uni-fix", (64, 32, 128), ("PP", "PP", "NN"), 0.0, 1.0e-2))
+    for name, ng, cbc, gr, ref_tol in cases:
+        lib.check(lib.load().flutas_b200_debug_ref_tol(1.0e-5 if ref_tol is None else ref_tol))
         if ng[0] % world or ng[2] % world or ng[1] % world:
             continue
         case = Case(ng, cbc, (2.0, 1.0, 1.0), gr=gr, seed=77)
@@ -66,7 +78,8 @@ def main():
         err = errs[0].item() / errs[1].item()
         nerr = comm.p2p_errors(plan) if mode == "p2p" else 0
         if rank == 0:
-            print("slab %s x%d %-5s %s %s: max|dp|/max|p| = %.2e barrier_timeouts=%d" % (mode, world, name, ng, "/".join(cbc), err, nerr),
+            zpath = "distributed" if lib.load().flutas_b200_slab_last_distributed(plan.h) else "transposed"
+            print("slab %s x%d %-8s %s %s: max|dp|/max|p| = %.2e barrier_timeouts=%d z=%s" % (mode, world, name, ng, "/".join(cbc), err, nerr, zpath),
                   flush=True)
         ok = ok and err <= 1e-12 and nerr == 0
         api.fftend(plan)

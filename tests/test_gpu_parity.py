@@ -198,7 +198,7 @@ def test_device_resident_step_and_linearity():
     api.fftend(pl)
 
 
-@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p-transpose"])
 def test_multi_gpu_slab_solver(mode):
     """N>1: z-slab decomposition, one process per GPU (torchrun), both exchange implementations."""
     import subprocess
@@ -215,6 +215,8 @@ def test_multi_gpu_slab_solver(mode):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0 and "SLAB_OK" in out.stdout
+    if mode == "p2p":                                        # the distributed z solve must actually have been exercised
+        assert "z=distributed" in out.stdout
 
 
 FULL_SIZE = [
