@@ -216,7 +216,7 @@ struct SolverPlan {
     int nsel = 0;
     DevBuf col, lam, pin, z, d, piv, p2, den, F;
     RefTables T{};
-  } ref;
+  } ref, dz_ref;                 // single-rank / transposed z stage; owned columns of the distributed z solve
   unsigned long long lam_win_gen = 0;
   int lam_win_rank = -1, lam_win_n1l = 0;
   // distributed z solve (dz.cuh)
@@ -426,8 +426,7 @@ size_t ref_smem_per_warp(int nz) { return (3 * (size_t)RefShape(nz).doubles() + 
 
 // (re)builds the tables of the selected columns for the z stage described by (lam, ncol, nz): selection on the host
 // from a copy of the eigenvalues, factors on the device in the reference's operation order (once per plan / layout)
-int ensure_ref(SolverPlan* sp, long ncol, int nz, const double* lam, bool periodic, int singular) {
-  SolverPlan::RefFix& rf = sp->ref;
+int ensure_ref(SolverPlan* sp, SolverPlan::RefFix& rf, long ncol, int nz, const double* lam, bool periodic, int singular) {
   if (rf.key_lam == lam && rf.key_ncol == ncol && rf.key_nz == nz && rf.key_periodic == periodic &&
       rf.key_singular == singular && rf.key_gen == sp->cache_gen && rf.key_tol == g_ref_tol) return 0;
   rf.key_lam = lam; rf.key_ncol = ncol; rf.key_nz = nz; rf.key_periodic = periodic; rf.key_singular = singular;
@@ -488,7 +487,7 @@ int run_z_main(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, 
 // z stage = [reference-order solve of the ill-conditioned columns into a side buffer] + main kernel (all columns, in
 // place or scattered to the peers) + [scatter of the side buffer over the main kernel's result]
 int run_z(SolverPlan* sp, long ncol, int nz, const double* lam, double* W, const ColGeom* out, bool periodic, int singular) {
-  if (int rc = ensure_ref(sp, ncol, nz, lam, periodic, singular)) return rc;
+  if (int rc = ensure_ref(sp, sp->ref, ncol, nz, lam, periodic, singular)) return rc;
   SolverPlan::RefFix& rf = sp->ref;
   if (rf.nsel) {
     const size_t per = ref_smem_per_warp(nz);
@@ -749,6 +748,7 @@ int flutas_b200_fftend(void* arrplan[4]) {
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
   for (DevBuf* b : {&sp->dz.sel_dev, &sp->dz.sel_lam_own}) b->release();
+  for (DevBuf* b : {&sp->dz_ref.col, &sp->dz_ref.lam, &sp->dz_ref.pin, &sp->dz_ref.z, &sp->dz_ref.d, &sp->dz_ref.piv, &sp->dz_ref.p2, &sp->dz_ref.den, &sp->dz_ref.F}) b->release();
   for (DevBuf* b : {&sp->ref.col, &sp->ref.lam, &sp->ref.pin, &sp->ref.z, &sp->ref.d, &sp->ref.piv, &sp->ref.p2, &sp->ref.den, &sp->ref.F}) b->release();
   for (int q = 0; q < FB_MAX_RANKS; ++q)
     if (sp->peer_base[q] && sp->peer_base[q] != sp->p2p_alloc) cudaIpcCloseMemHandle(sp->peer_base[q]);
@@ -1031,8 +1031,8 @@ int dz_setup(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, bool periodi
     CK(cudaMemcpyAsync(dz.sel_lam_own.p, lo.data(), lo.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     if (nown) {                                            // factor tables of the owned columns, global coefficients
-      if (int rc = ensure_ref(sp, nown, ng3, dz.sel_lam_own.as<double>(), periodic, singular)) return rc;
-      if (sp->ref.nsel != nown) return fail(FLUTAS_B200_ERR_ARG, "distributed z: reference-order selection mismatch (%d != %d)", sp->ref.nsel, nown);
+      if (int rc = ensure_ref(sp, sp->dz_ref, nown, ng3, dz.sel_lam_own.as<double>(), periodic, singular)) return rc;
+      if (sp->dz_ref.nsel != nown) return fail(FLUTAS_B200_ERR_ARG, "distributed z: reference-order selection mismatch (%d != %d)", sp->dz_ref.nsel, nown);
     }
   }
   // p = T_g^{-1}(a_first e_first), q = T_g^{-1}(c_last e_last) at the first / last level -> the column owners
@@ -1055,6 +1055,8 @@ int dz_setup(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, bool periodi
                                                      dz_peers(sp->peer_pencil, P, pass == 0 ? L.oPL : L.oQL));
     LAUNCHED();
   }
+  // every rank's p / q planes have landed and nobody's scratch (= the area peers gather into) is in use any more
+  if (int rc = p2p_barrier(sp)) return rc;
   dz.ok = true;
   return 0;
 }
@@ -1091,12 +1093,12 @@ int dz_solve_z(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, double* W1
                                                      dz_peers(sp->peer_pencil, P, L.oYF), dz_peers(sp->peer_pencil, P, L.oYL));
     LAUNCHED();
     if (int rc = p2p_barrier(sp)) return rc;
-    dz_interface_kernel<<<(unsigned)((ncol_own + 127) / 128), 128, 0, g_stream>>>(P, ncol_own, (long)r * ncol_own, mine + L.oPF, mine + L.oPL,
+    dz_interface_kernel<<<(unsigned)((ncol_own + 127) / 128), 128, 0, g_stream>>>(P, periodic ? 1 : 0, ncol_own, (long)r * ncol_own, mine + L.oPF, mine + L.oPL,
                                                                                    mine + L.oQF, mine + L.oQL, mine + L.oYF, mine + L.oYL,
                                                                                    dz_peers(sp->peer_pencil, P, L.oXP), dz_peers(sp->peer_pencil, P, L.oXN));
     LAUNCHED();
     if (nown) {
-      SolverPlan::RefFix& rf = sp->ref;
+      SolverPlan::RefFix& rf = sp->dz_ref;
       const size_t per = ref_smem_per_warp(ng3);
       int warps = (int)(REF_MAX_SMEM / per);
       warps = warps > 4 ? 4 : warps;

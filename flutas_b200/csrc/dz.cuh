@@ -61,6 +61,44 @@ FB_HD void dz_interface_solve(int G, const double* pF, const double* pL, const d
   }
 }
 
+// Non-periodic z: the same system, solved in O(G).  With w_j = (last_j, first_{j+1}), j = 0..G-2 (the two unknowns
+// either side of the cut between rank j and rank j+1) the equations become block tridiagonal with 2 x 2 blocks,
+//     [ 1        qL_j ] w_j  +  [ pL_j 0 ] w_{j-1}  +  [ 0 0        ] w_{j+1}  =  ( yL_j     )
+//     [ pF_{j+1} 1    ]         [ 0    0 ]             [ 0 qF_{j+1} ]             ( yF_{j+1} )
+// (pF_0 = pL_0 = 0: rank 0 has no neighbour below; qF_{G-1} = qL_{G-1} = 0).  Block Thomas: the only fill-in is one entry per
+// block, the determinants 1 - qL pF stay positive because |p|, |q| < 1 for the (negative definite) z operator.
+// Output: xprev[g] = last_{g-1}, xnext[g] = first_{g+1} (0 where the neighbour does not exist).
+FB_HD void dz_interface_solve_walls(int G, const double* pF, const double* pL, const double* qF, const double* qL, const double* yF,
+                                    const double* yL, double* xprev, double* xnext) {
+  double b01[FB_DZ_MAXG], b10[FB_DZ_MAXG], r0[FB_DZ_MAXG], r1[FB_DZ_MAXG], idet[FB_DZ_MAXG];
+  const int m = G - 1;                                     // number of cuts
+  // forward elimination: B'_j = B_j - A_j B'^{-1}_{j-1} C_{j-1} touches entry (0,1) only; r'_j = r_j - A_j B'^{-1}_{j-1} r'_{j-1} entry 0 only
+  for (int j = 0; j < m; ++j) {
+    double e01 = qL[j], f0 = yL[j];
+    const double e10 = pF[j + 1], f1 = yF[j + 1];
+    if (j > 0) {
+      // X = B'^{-1}_{j-1} = idet [[1, -b01],[-b10, 1]];  X[0][1] = -b01 idet;  (X r')[0] = idet (r0 - b01 r1)
+      const double x01 = -b01[j - 1] * idet[j - 1];
+      const double xr0 = idet[j - 1] * (r0[j - 1] - b01[j - 1] * r1[j - 1]);
+      e01 -= pL[j] * x01 * qF[j];
+      f0 -= pL[j] * xr0;
+    }
+    b01[j] = e01; b10[j] = e10; r0[j] = f0; r1[j] = f1;
+    idet[j] = 1.0 / (1.0 - e01 * e10);
+  }
+  // back substitution: w_j = B'^{-1}_j (r'_j - C_j w_{j+1}),  C_j w_{j+1} = (0, qF_{j+1} first_{j+2})
+  double wl = 0.0, wf = 0.0;
+  for (int g = 0; g < G; ++g) { xprev[g] = 0.0; xnext[g] = 0.0; }
+  for (int j = m - 1; j >= 0; --j) {
+    const double s0 = r0[j], s1 = r1[j] - ((j + 1 < m) ? qF[j + 1] * wf : 0.0);
+    const double nl = idet[j] * (s0 - b01[j] * s1);
+    const double nf = idet[j] * (s1 - b10[j] * s0);
+    wl = nl; wf = nf;
+    xprev[j + 1] = wl;                                     // last_j is what rank j+1 calls x_prev
+    xnext[j] = wf;                                         // first_{j+1} is what rank j calls x_next
+  }
+}
+
 }  // namespace fb
 
 #if defined(__CUDACC__)
@@ -82,7 +120,7 @@ __global__ void dz_send_planes_kernel(long ncol, long ncol_own, int rank, const 
 
 // one thread per owned column: 2G x 2G interface system; the neighbours' boundary unknowns go straight to every rank
 // (xprev[g][col], xnext[g][col] with col the global column index)
-__global__ void dz_interface_kernel(int G, long ncol_own, long col0, const double* __restrict__ PF, const double* __restrict__ PL,
+__global__ void dz_interface_kernel(int G, int periodic, long ncol_own, long col0, const double* __restrict__ PF, const double* __restrict__ PL,
                                     const double* __restrict__ QF, const double* __restrict__ QL, const double* __restrict__ YF,
                                     const double* __restrict__ YL, DzPeers xprev, DzPeers xnext) {
   const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,10 +130,16 @@ __global__ void dz_interface_kernel(int G, long ncol_own, long col0, const doubl
     const long o = (long)g * ncol_own + c;
     pF[g] = PF[o]; pL[g] = PL[o]; qF[g] = QF[o]; qL[g] = QL[o]; yF[g] = YF[o]; yL[g] = YL[o];
   }
-  dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
-  for (int g = 0; g < G; ++g) {
-    xprev.p[g][col0 + c] = u[2 * ((g + G - 1) % G) + 1];
-    xnext.p[g][col0 + c] = u[2 * ((g + 1) % G)];
+  if (periodic) {                                          // cyclic coupling rank 0 <-> rank G-1: dense elimination
+    dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
+    for (int g = 0; g < G; ++g) {
+      xprev.p[g][col0 + c] = u[2 * ((g + G - 1) % G) + 1];
+      xnext.p[g][col0 + c] = u[2 * ((g + 1) % G)];
+    }
+  } else {
+    double xp[FB_DZ_MAXG], xn[FB_DZ_MAXG];
+    dz_interface_solve_walls(G, pF, pL, qF, qL, yF, yL, xp, xn);
+    for (int g = 0; g < G; ++g) { xprev.p[g][col0 + c] = xp[g]; xnext.p[g][col0 + c] = xn[g]; }
   }
 }
 

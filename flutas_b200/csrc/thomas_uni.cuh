@@ -250,8 +250,8 @@ thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __rest
 #pragma unroll
       for (int l = 0; l < L; ++l) { yv[l] = v[l]; v[l] = 0.0; }
       if (live) {
-        if (s == 0) v[0] = -corr.ca * __ldg(corr.xprev + col);
-        if (s == S - 1) v[L - 1] = v[L - 1] - corr.cc * __ldg(corr.xnext + col);
+        if (s == 0 && corr.ca != 0.0) v[0] = -corr.ca * __ldg(corr.xprev + col);
+        if (s == S - 1 && corr.cc != 0.0) v[L - 1] = v[L - 1] - corr.cc * __ldg(corr.xnext + col);
       }
     }
     __syncthreads();                                        // tables ready; every thread has its levels: the tile buffer is free

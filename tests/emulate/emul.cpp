@@ -556,8 +556,20 @@ extern "C" int emul_dz(int nz, int G, long ncol, int periodic, int singular, con
       pF[g] = PF[(size_t)g * ncol + q]; pL[g] = PL[(size_t)g * ncol + q]; qF[g] = QF[(size_t)g * ncol + q]; qL[g] = QL[(size_t)g * ncol + q];
       yF[g] = W[(size_t)ncol * g * n3l + q]; yL[g] = W[(size_t)ncol * (g * n3l + n3l - 1) + q];
     }
-    dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
-    for (int g = 0; g < G; ++g) { XP[(size_t)g * ncol + q] = u[2 * ((g + G - 1) % G) + 1]; XN[(size_t)g * ncol + q] = u[2 * ((g + 1) % G)]; }
+    if (periodic) {
+      dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
+      for (int g = 0; g < G; ++g) { XP[(size_t)g * ncol + q] = u[2 * ((g + G - 1) % G) + 1]; XN[(size_t)g * ncol + q] = u[2 * ((g + 1) % G)]; }
+    } else {                                              // same branch as dz_interface_kernel; cross-checked against the dense solve
+      double xp[FB_DZ_MAXG], xn[FB_DZ_MAXG];
+      dz_interface_solve_walls(G, pF, pL, qF, qL, yF, yL, xp, xn);
+      dz_interface_solve(G, pF, pL, qF, qL, yF, yL, u);
+      for (int g = 0; g < G; ++g) {
+        XP[(size_t)g * ncol + q] = xp[g]; XN[(size_t)g * ncol + q] = xn[g];
+        const double dp = (g > 0) ? u[2 * (g - 1) + 1] : 0.0, dn = (g < G - 1) ? u[2 * (g + 1)] : 0.0;
+        const double sc = 1e-9 * (fabs(dp) + fabs(dn) + 1e-300);
+        if (fabs(xp[g] - dp) > sc + 1e-9 * fabs(dp) || fabs(xn[g] - dn) > sc + 1e-9 * fabs(dn)) return 9;
+      }
+    }
   }
   // pass 2: x = y + T_g^{-1}(-ca x_prev e_first - cc x_next e_last)   (the CORR variant of the kernel)
   for (int g = 0; g < G; ++g) {
