@@ -279,6 +279,7 @@ bool aligned16(const void* p, const LineGeom& g) {
 
 template <bool FWD>
 int run_x(const DevLinePlan& lp, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale) {
+  if (gs.nlines >= 0x7fffffffL) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "more than 2^31 x lines on one rank");
   if (lp.use_reg) {
     if (!(FWD ? aligned16(dst, gd) : aligned16(src, gs)))
       return fail(FLUTAS_B200_ERR_ARG, "register transform kernels need a 16-byte aligned spectral work array");
@@ -312,6 +313,7 @@ int launch_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& 
 }
 template <bool FWD>
 int run_y(const DevLinePlan& lp, double* W, int n1, long n3, const SpecGeom& sg) {
+  if ((long)n1 * n3 >= 0x7fffffffL) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "more than 2^31 y tiles on one rank");
   if (lp.use_reg) {
     const int nsm = g_nsm > 0 ? g_nsm : 148;
     cudaError_t e = FWD ? reg_run_y_fwd(lp.r, W, n1, n3, sg, nsm, g_stream) : reg_run_y_bwd(lp.r, W, n1, n3, sg, nsm, g_stream);

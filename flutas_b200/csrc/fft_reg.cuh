@@ -77,7 +77,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef FB_STREAM_X
 #define FB_STREAM_X 1
 #endif
+#ifndef FB_LDCS_Y
+#define FB_LDCS_Y 0
+#endif
 __device__ __forceinline__ void st_y(double* p, double v) { if (FB_STREAM_Y) __stcs(p, v); else *p = v; }
+__device__ __forceinline__ double ld_y(const double* p) { return FB_LDCS_Y ? __ldcs(p) : *p; }
 __device__ __forceinline__ void st_x2(double2* p, double2 v) { if (FB_STREAM_X) __stcs(p, v); else *p = v; }
 
 
@@ -299,10 +303,11 @@ template <int N, bool WIDE, bool MK, int RR = 16>
 struct YRegShape {
   using S = RegSched<N / 2, RR>;
   static constexpr int T = S::T;
-  static constexpr int NTMAX = (RR == 8) ? 512 : (WIDE && T >= 32) ? 512 : 256;
+  // RR = 8 && WIDE: 16 lanes x 64 threads per line = ONE 1024-thread block per SM, 128-byte row pieces (A/B variant)
+  static constexpr int NTMAX = (RR == 8) ? (WIDE ? 1024 : 512) : (WIDE && T >= 32) ? 512 : 256;
   static constexpr int TB = (NTMAX / T > 32) ? 32 : NTMAX / T;
   static constexpr int NT = TB * T;
-  static constexpr int MINB = (RR == 8) ? 2 : (NT > 256) ? 1 : 2;
+  static constexpr int MINB = (RR == 8) ? (WIDE ? 1 : 2) : (NT > 256) ? 1 : 2;
   static constexpr size_t smem = (size_t)RegTw<S, MK>::total * sizeof(cpx) + (size_t)(N / 2 + N / 32) * TB * sizeof(double2);
 };
 
@@ -338,9 +343,12 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
   const double sdd = (MK && P.kind == KIND_DD) ? -1.0 : 1.0;   // DST-II/III through the DCT: odd physical elements change sign
   const bool dn = IV && (P.kind == KIND_DN);
   const unsigned sstride = (unsigned)sg.n1l * 8u, pstride = (unsigned)n1 * 8u;      // row strides in bytes (< 4 GB)
+  // tile -> (i-tile, k) with 32-bit arithmetic (the tile count of one GPU is far below 2^31): the 64-bit divisions cost
+  // a ~100-instruction subroutine per tile and showed up with 3-4 % of the stall samples in the r02 source-level profile
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int ti = (int)(tile % ntile_i);
-    const long k = tile / ntile_i;
+    const unsigned ut = (unsigned)tile, uk = ut / (unsigned)ntile_i;
+    const int ti = (int)(ut - uk * (unsigned)ntile_i);
+    const long k = (long)uk;
     const int i0 = ti * TB;
     const bool live = (i0 + lane) < n1;
     const int il = i0 + (live ? lane : 0);
@@ -349,8 +357,9 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
     {                                                        // next tile -> L2 while this one is transformed
       const long tn = tile + gridDim.x;
       if (tn < ntiles) {
-        const int tin = (int)(tn % ntile_i);
-        const long kn = tn / ntile_i;
+        const unsigned utn = (unsigned)tn, ukn = utn / (unsigned)ntile_i;
+        const int tin = (int)(utn - ukn * (unsigned)ntile_i);
+        const long kn = (long)ukn;
         const int iln = min(tin * TB, n1 - 1);
         const double* pn = FWD ? (W + (long)n1 * N * kn + iln) : spec_base(sg, iln, N, kn);
         const unsigned sn = FWD ? pstride : sstride;
@@ -377,7 +386,7 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
       } else if (!MK) {
         const double* p0 = yrow(base, pstride, 2 * j);
 #pragma unroll
-        for (int u = 0; u < R; ++u) { re[u] = *yrow(p0, pstride, 2 * T * u); im[u] = *yrow(p0, pstride, 2 * T * u + 1); }
+        for (int u = 0; u < R; ++u) { re[u] = ld_y(yrow(p0, pstride, 2 * T * u)); im[u] = ld_y(yrow(p0, pstride, 2 * T * u + 1)); }
       } else {
         const double* plo = yrow(base, pstride, MR::base_lo(j));
         const double* phi = yrow(base, pstride, MR::base_hi(j));
@@ -408,7 +417,7 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
         const double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
         for (int u = 0; u < R; ++u) {
-          const double a = *yrow(ps, sstride, 2 * T * u), b = *yrow(ps, sstride, 2 * T * u + 1);
+          const double a = ld_y(yrow(ps, sstride, 2 * T * u)), b = ld_y(yrow(ps, sstride, 2 * T * u + 1));
           re[u] = dn ? b : a; im[u] = dn ? a : b;
         }
       }
@@ -509,6 +518,11 @@ inline cudaError_t reg_launch_y(const RegPlan& P, double* W, int n1, long n3, co
   const int kc = kind_is_iv(P.kind) ? 2 : (P.kind != KIND_PP) ? 1 : 0;
   if constexpr (N == 1024) {                            // 8 values per thread (see YRegShape); FLUTAS_B200_Y8=0/1 overrides
     static const int y8 = [] { const char* e = getenv("FLUTAS_B200_Y8"); return e ? atoi(e) : FB_Y8_DEFAULT; }();
+    static const int y8w = [] { const char* e = getenv("FLUTAS_B200_Y8WIDE"); return e ? atoi(e) : 0; }();
+    if (y8 && y8w && P.tw8[1])
+      return kc == 2 ? reg_launch_y1<N, FWD, true, 2, 8>(P, W, n1, n3, sg, nsm, st)
+           : kc == 1 ? reg_launch_y1<N, FWD, true, 1, 8>(P, W, n1, n3, sg, nsm, st)
+                     : reg_launch_y1<N, FWD, true, 0, 8>(P, W, n1, n3, sg, nsm, st);
     if (y8 && !wide && P.tw8[1])
       return kc == 2 ? reg_launch_y1<N, FWD, false, 2, 8>(P, W, n1, n3, sg, nsm, st)
            : kc == 1 ? reg_launch_y1<N, FWD, false, 1, 8>(P, W, n1, n3, sg, nsm, st)

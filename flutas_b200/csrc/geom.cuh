@@ -13,8 +13,11 @@ struct LineGeom {
   long nlines;
 };
 
+// (32-bit division: the number of lines of one rank is far below 2^31 -- checked by the launchers; a 64-bit division is a
+// ~100-instruction subroutine, executed per line and per thread)
 __device__ __forceinline__ long line_offset(const LineGeom& g, long line) {
-  const long k = line / g.n2, j = line - k * g.n2;
+  const unsigned ul = (unsigned)line, uk = ul / (unsigned)g.n2;
+  const long k = (long)uk, j = (long)(ul - uk * (unsigned)g.n2);
   return g.off0 + j * g.sj + k * g.sk;
 }
 
