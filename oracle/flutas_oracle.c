@@ -150,7 +150,24 @@ typedef struct {
   cfft_plan *cf;      /* length n (R2HC/HC2R) or 2n (DCT/DST kinds) */
   cplx *ph;           /* phase tables, see r2r_exec */
   cplx *ph2;
+  /* fast path (even n): half-length complex FFT + tables, see r2r_exec_fast */
+  cfft_plan *ch;      /* length n/2 */
+  cplx *wn;           /* wn[k] = exp(-2 pi i k / n),        k = 0..n/2 */
+  cplx *wq;           /* wq[k] = exp(-i pi k / (2n)),       k = 0..n/2 */
+  cplx *w4a;          /* w4a[m] = exp(-i pi (4m+1)/(4n)),   m = 0..n/2-1 */
+  cplx *w4b;          /* w4b[k] = exp(-i pi k / n),         k = 0..n/2-1 */
 } r2r_plan;
+
+/* 1: every transform goes through the definition-transcribing path (r2r_exec); 0 (default): even lengths use the fast path,
+ * which tests/test_oracle.py holds against the definition path, scipy/pocketfft and the long-double O(n^2) sums */
+static int g_force_definition_path = 0;
+void oracle_set_definition_path(int on) { g_force_definition_path = on; }
+
+static cplx unit_phase(long double num, long double den) {      /* exp(-i pi num/den) */
+  cplx w; long double ang = -PI_L * num / den;
+  w.re = (double)cosl(ang); w.im = (double)sinl(ang);
+  return w;
+}
 
 void *oracle_r2r_create(int n, int kind) {
   r2r_plan *pl = (r2r_plan *)calloc(1, sizeof(r2r_plan));
@@ -176,13 +193,24 @@ void *oracle_r2r_create(int n, int kind) {
     default:
       free(pl); return NULL;   /* face-centred kinds REDFT00/RODFT00: dead code in FluTAS */
   }
+  if (n % 2 == 0 && n >= 4) {
+    const int M = n / 2;
+    pl->ch = cfft_create(M);
+    pl->wn = (cplx *)malloc(sizeof(cplx) * (size_t)(M + 1));
+    pl->wq = (cplx *)malloc(sizeof(cplx) * (size_t)(M + 1));
+    pl->w4a = (cplx *)malloc(sizeof(cplx) * (size_t)M);
+    pl->w4b = (cplx *)malloc(sizeof(cplx) * (size_t)M);
+    for (int k = 0; k <= M; ++k) { pl->wn[k] = unit_phase(2.0L * k, (long double)n); pl->wq[k] = unit_phase((long double)k, 2.0L * n); }
+    for (int k = 0; k < M; ++k) { pl->w4a[k] = unit_phase(4.0L * k + 1.0L, 4.0L * n); pl->w4b[k] = unit_phase((long double)k, (long double)n); }
+  }
   return pl;
 }
 
 void oracle_r2r_destroy(void *h) {
   r2r_plan *pl = (r2r_plan *)h;
   if (!pl) return;
-  cfft_destroy(pl->cf); free(pl->ph); free(pl->ph2); free(pl);
+  cfft_destroy(pl->cf); free(pl->ph); free(pl->ph2);
+  cfft_destroy(pl->ch); free(pl->wn); free(pl->wq); free(pl->w4a); free(pl->w4b); free(pl);
 }
 
 /* transform one line x[0..n) (contiguous) in place; wa, wb: scratch of 2n cplx each */
@@ -257,6 +285,121 @@ static void r2r_exec(const r2r_plan *pl, double *x, cplx *wa, cplx *wb) {
   }
 }
 
+/* ---- fast path: the same eight kinds through ONE complex FFT of length n/2 (n even) ----------------------------------
+ * Textbook reductions, each checked against the definition path above:
+ *   R2HC / HC2R        pack z_m = x_{2m} + i x_{2m+1}; X_k = E_k + w^k O_k with E, O from Z_k and conj Z_{M-k}
+ *   REDFT10 / REDFT01  Makhoul: v_m = x_{2m}, v_{n-1-m} = x_{2m+1}; Y_k = 2 Re(e^{-i pi k/2n} V_k), Y_{n-k} = -2 Im(.)
+ *   RODFT10 / RODFT01  through the cosine transforms: sign flip of odd inputs + reversed output, and the converse
+ *   REDFT11 / RODFT11  z_m = x_{2m} + i x_{n-1-2m}, pre-twiddle e^{-i pi(4m+1)/4n}, post-twiddle e^{-i pi k/n}
+ * wa, wb: scratch of at least n/2 + 1 cplx; v: scratch of n doubles. */
+static void rfft_half(const r2r_plan *pl, const double *v, cplx *wa, cplx *wb) {
+  /* wb[0..M] <- DFT_n(v)_k, k = 0..M (v real, length n = 2M) */
+  const int M = pl->n / 2;
+  for (int m = 0; m < M; ++m) { wa[m].re = v[2 * m]; wa[m].im = v[2 * m + 1]; }
+  cfft_exec(pl->ch, wa, wb, -1);
+  wb[M] = wb[0];
+  /* in-place split needs both Z_k and Z_{M-k}: go pairwise */
+  for (int k = 0; k <= M / 2; ++k) {
+    const int j = M - k;
+    const cplx zk = wb[k], zj = wb[j];
+    /* E_k = (Z_k + conj Z_j)/2, O_k = -i (Z_k - conj Z_j)/2 ; X_k = E_k + w^k O_k ; X_j = conj(E_k) + w^j conj(O_k) */
+    const double er = 0.5 * (zk.re + zj.re), ei = 0.5 * (zk.im - zj.im);
+    const double orr = 0.5 * (zk.im + zj.im), oi = -0.5 * (zk.re - zj.re);
+    const cplx wk = pl->wn[k], wj = pl->wn[j];
+    cplx xk, xj;
+    xk.re = er + (orr * wk.re - oi * wk.im); xk.im = ei + (orr * wk.im + oi * wk.re);
+    xj.re = er + (orr * wj.re + oi * wj.im); xj.im = -ei + (orr * wj.im - oi * wj.re);
+    wb[k] = xk; wb[j] = xj;
+  }
+}
+static void irfft_half(const r2r_plan *pl, cplx *X, double *v, cplx *wa) {
+  /* v <- n * irfft(X): X[0..M] the half spectrum (destroyed), unnormalised like HC2R */
+  const int M = pl->n / 2;
+  for (int k = 0; k <= M / 2; ++k) {
+    const int j = M - k;
+    const cplx xk = X[k], xj = X[j];
+    /* Z'_k = (X_k + conj X_j) + i conj(w^k) (X_k - conj X_j) ; Z'_j likewise with k <-> j */
+    const double sr = xk.re + xj.re, si = xk.im - xj.im, dr = xk.re - xj.re, di = xk.im + xj.im;
+    const cplx wk = pl->wn[k], wj = pl->wn[j];
+    /* conj(w) * D */
+    const double ckr = dr * wk.re + di * wk.im, cki = di * wk.re - dr * wk.im;
+    const double cjr = -dr * wj.re + di * wj.im, cji = di * wj.re + dr * wj.im;     /* D_j = -conj(D_k): (-dr, di) */
+    cplx zk, zj;
+    zk.re = sr - cki; zk.im = si + ckr;
+    zj.re = sr - cji; zj.im = -si + cjr;
+    if (k < M) X[k] = zk;
+    if (j < M) X[j] = zj;
+    if (k == 0) X[0] = zk;
+  }
+  cfft_exec(pl->ch, X, wa, +1);
+  for (int m = 0; m < M; ++m) { v[2 * m] = wa[m].re; v[2 * m + 1] = wa[m].im; }
+}
+
+static void r2r_exec_fast(const r2r_plan *pl, double *x, cplx *wa, cplx *wb, double *v) {
+  const int n = pl->n, M = n / 2;
+  switch (pl->kind) {
+    case FFTW_R2HC: {
+      rfft_half(pl, x, wa, wb);
+      for (int k = 0; k <= M; ++k) x[k] = wb[k].re;
+      for (int k = 1; k < M; ++k) x[n - k] = wb[k].im;
+    } break;
+    case FFTW_HC2R: {
+      wb[0].re = x[0]; wb[0].im = 0.0;
+      for (int k = 1; k < M; ++k) { wb[k].re = x[k]; wb[k].im = x[n - k]; }
+      wb[M].re = x[M]; wb[M].im = 0.0;
+      irfft_half(pl, wb, x, wa);
+    } break;
+    case FFTW_REDFT10: case FFTW_RODFT10: {
+      const int dst = (pl->kind == FFTW_RODFT10);
+      for (int m = 0; m < M; ++m) {                       /* DST-II: odd inputs change sign (fft.f90:417-428) */
+        v[m] = x[2 * m];
+        v[n - 1 - m] = dst ? -x[2 * m + 1] : x[2 * m + 1];
+      }
+      rfft_half(pl, v, wa, wb);
+      /* Y_k = 2 Re(q_k V_k), Y_{n-k} = -2 Im(q_k V_k), q_k = e^{-i pi k/2n}; DST-II: output reversed (fft.f90:537-560) */
+      for (int k = 0; k <= M; ++k) {
+        const cplx q = pl->wq[k], V = wb[k];
+        const double tr = q.re * V.re - q.im * V.im, ti = q.re * V.im + q.im * V.re;
+        const int a = dst ? n - 1 - k : k;
+        x[a] = 2.0 * tr;
+        if (k > 0 && k < M) x[dst ? k - 1 : n - k] = -2.0 * ti;
+      }
+    } break;
+    case FFTW_REDFT01: case FFTW_RODFT01: {
+      const int dst = (pl->kind == FFTW_RODFT01);
+      /* DST-III: input reversed (fft.f90:859-875).  V'_k = conj(q_k) (Y_k - i Y_{n-k}), Y_n = 0 */
+      for (int k = 0; k <= M; ++k) {
+        const double yk = dst ? x[n - 1 - k] : x[k];
+        const double yn = (k == 0) ? 0.0 : (dst ? x[k - 1] : x[n - k]);
+        const cplx q = pl->wq[k];
+        const double c = q.re, sg = -q.im;                  /* conj(q) = c + i sg ; (c + i sg)(yk - i yn) */
+        wb[k].re = c * yk + sg * yn;
+        wb[k].im = sg * yk - c * yn;
+      }
+      irfft_half(pl, wb, v, wa);
+      for (int m = 0; m < M; ++m) {
+        x[2 * m] = v[m];
+        x[2 * m + 1] = dst ? -v[n - 1 - m] : v[n - 1 - m];
+      }
+    } break;
+    case FFTW_REDFT11: case FFTW_RODFT11: {
+      const int dst = (pl->kind == FFTW_RODFT11);
+      for (int m = 0; m < M; ++m) {                       /* RODFT11(x)_k = (-1)^k REDFT11(reversed x)_k */
+        const double a = dst ? x[n - 1 - 2 * m] : x[2 * m], b = dst ? x[2 * m] : x[n - 1 - 2 * m];
+        const cplx w = pl->w4a[m];
+        wa[m].re = a * w.re - b * w.im; wa[m].im = a * w.im + b * w.re;
+      }
+      cfft_exec(pl->ch, wa, wb, -1);
+      for (int k = 0; k < M; ++k) {
+        const cplx w = pl->w4b[k], V = wb[k];
+        const double tr = V.re * w.re - V.im * w.im, ti = V.re * w.im + V.im * w.re;
+        x[2 * k] = 2.0 * tr;
+        x[n - 1 - 2 * k] = dst ? 2.0 * ti : -2.0 * ti;
+      }
+    } break;
+  }
+}
+
 /* FFTW guru-style batched execute, in place:
  * n, stride of the transform; two howmany loops (h1n,h1s), (h2n,h2s)  (src/fft.f90:75-86,113-124) */
 void oracle_r2r_execute(void *h, double *data, long stride, long h1n, long h1s, long h2n, long h2s) {
@@ -265,21 +408,23 @@ void oracle_r2r_execute(void *h, double *data, long stride, long h1n, long h1s, 
 #pragma omp parallel
   {
     double *line = (double *)malloc(sizeof(double) * (size_t)n);
+    double *vv = (double *)malloc(sizeof(double) * (size_t)(n + 2));
     cplx *wa = (cplx *)malloc(sizeof(cplx) * (size_t)(2 * n + 2));
     cplx *wb = (cplx *)malloc(sizeof(cplx) * (size_t)(2 * n + 2));
+    const int fast = (pl->ch != NULL) && !g_force_definition_path;
 #pragma omp for collapse(2) schedule(static)
     for (long b = 0; b < h2n; ++b)
       for (long a = 0; a < h1n; ++a) {
         double *base = data + a * h1s + b * h2s;
         if (stride == 1) {
-          r2r_exec(pl, base, wa, wb);
+          if (fast) r2r_exec_fast(pl, base, wa, wb, vv); else r2r_exec(pl, base, wa, wb);
         } else {
           for (int j = 0; j < n; ++j) line[j] = base[(long)j * stride];
-          r2r_exec(pl, line, wa, wb);
+          if (fast) r2r_exec_fast(pl, line, wa, wb, vv); else r2r_exec(pl, line, wa, wb);
           for (int j = 0; j < n; ++j) base[(long)j * stride] = line[j];
         }
       }
-    free(line); free(wa); free(wb);
+    free(line); free(vv); free(wa); free(wb);
   }
 }
 

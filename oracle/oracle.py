@@ -51,6 +51,7 @@ def lib():
         L.oracle_updt_rhs_b.argtypes = [C.c_int] * 3 + [_dp] * 4
         L.oracle_correc.argtypes = [C.c_int] * 5 + [C.c_double] * 3 + [_dp, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
         L.oracle_chkdiv.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2 + [_dp] * 4 + [_dp, _dp]
+        L.oracle_set_definition_path.argtypes = [C.c_int]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _LIB = L
@@ -60,6 +61,13 @@ def lib():
 def _p(a):
     assert a.dtype == np.float64 and (a.flags.f_contiguous or a.ndim == 1), "need float64 Fortran-contiguous"
     return a.ctypes.data_as(_dp)
+
+
+def set_definition_path(on):
+    """True: every r2r transform goes through the path that transcribes FFTW's definitions (one zero-padded complex FFT);
+    False (default): even lengths use the half-length reductions (R2HC split, Makhoul, type-IV twiddles), 1.7x faster --
+    tests/test_oracle.py holds the two against each other, scipy/pocketfft and the long-double O(n^2) sums."""
+    lib().oracle_set_definition_path(1 if on else 0)
 
 
 def num_threads():

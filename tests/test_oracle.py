@@ -82,6 +82,23 @@ def test_r2r_matches_scipy_both_axes(kind, n):
         assert np.max(np.abs(got - ref)) <= 2e-14 * max(1.0, np.max(np.abs(ref)))
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [4, 6, 8, 10, 12, 30, 32, 64, 72, 100, 256, 1024, 2048])
+def test_fast_path_matches_definition_path(kind, n):
+    """The oracle's default transforms use half-length reductions; the path that transcribes FFTW's definitions through
+    one zero-padded complex FFT is kept and must agree with it to round-off (both are also pinned to scipy above)."""
+    rng = np.random.default_rng(n + len(kind))
+    for axis, shape in ((0, (n, 3, 2)), (1, (3, n, 2))):
+        x = np.asfortranarray(rng.uniform(-1, 1, shape))
+        try:
+            oracle.set_definition_path(True)
+            ref = oracle.r2r(kind, x.copy(order="F"), axis)
+        finally:
+            oracle.set_definition_path(False)
+        got = oracle.r2r(kind, x.copy(order="F"), axis)
+        assert np.max(np.abs(got - ref)) <= 5e-15 * max(1.0, np.max(np.abs(ref))) * np.log2(n)
+
+
 @pytest.mark.parametrize("kind", [k for k in KINDS if k != "HC2R"])
 @pytest.mark.parametrize("n", [2, 6, 8, 12, 30])
 def test_r2r_matches_longdouble_definition(kind, n):
