@@ -229,7 +229,8 @@ struct SolverPlan {
     double ca = 0.0, cc = 0.0;
     int nsel = 0;
     DzOwn own{};
-    DevBuf sel_dev, sel_lam_own;
+    DevBuf sel_dev, sel_lam_own, abc_loc;
+    bool general = false;        // local blocks through the general kernel (coefficient tables) instead of the shared-LU one
     int last_used = 0;           // 1: the last solver_slab call on this plan ran the distributed z solve
   } dz;
   // slab (multi-GPU) state
@@ -749,7 +750,7 @@ int flutas_b200_fftend(void* arrplan[4]) {
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
                     &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
-  for (DevBuf* b : {&sp->dz.sel_dev, &sp->dz.sel_lam_own}) b->release();
+  for (DevBuf* b : {&sp->dz.sel_dev, &sp->dz.sel_lam_own, &sp->dz.abc_loc}) b->release();
   for (DevBuf* b : {&sp->dz_ref.col, &sp->dz_ref.lam, &sp->dz_ref.pin, &sp->dz_ref.z, &sp->dz_ref.d, &sp->dz_ref.piv, &sp->dz_ref.p2, &sp->dz_ref.den, &sp->dz_ref.F}) b->release();
   for (DevBuf* b : {&sp->ref.col, &sp->ref.lam, &sp->ref.pin, &sp->ref.z, &sp->ref.d, &sp->ref.piv, &sp->ref.p2, &sp->ref.den, &sp->ref.F}) b->release();
   for (int q = 0; q < FB_MAX_RANKS; ++q)
@@ -963,7 +964,9 @@ static int p2p_barrier(SolverPlan* sp) {
 // true when the distributed z solve can serve this plan / decomposition (the same answer on every rank)
 bool dz_shape_ok(const SolverPlan* sp, int n1, int n2, int n3l, int P) {
   const long ncol = (long)n1 * n2;
-  return g_dz && sp->p2p && sp->thomas_mode == 0 && g_z_uniform_ok && sp->z_uniform.uniform && P >= 2 && P <= FB_DZ_MAXG &&
+  const bool uni = g_z_uniform_ok && sp->z_uniform.uniform;          // shared-LU kernel; else the general kernel (coefficient tables)
+  if (!uni && !thomas_reg_local_ok(n3l, ncol)) return false;
+  return g_dz && sp->p2p && sp->thomas_mode == 0 && P >= 2 && P <= FB_DZ_MAXG &&
          n3l % 16 == 0 && n3l / 16 >= 2 && n3l / 16 <= 32 && (ncol % 2) == 0 && (ncol % P) == 0 && ((ncol / P) % 2) == 0;
 }
 
@@ -986,18 +989,47 @@ DzPeers dz_peers(double* const* base, int P, size_t off) {
   return d;
 }
 
+// one sweep of the rank-local block over the slab W (ncol x n3l): shared-LU kernel on an exactly uniform grid, else the
+// general kernel with the local coefficient tables; corr = nullptr: pass 1, else pass 2
+int dz_local_run(SolverPlan* sp, long ncol, int n3l, double* W, int sing_loc, const ThomasCorr* corr, bool* done) {
+  SolverPlan::DzState& dz = sp->dz;
+  const int nsm = g_nsm > 0 ? g_nsm : 148;
+  const double* lam = sp->lam_int.as<double>();
+  int rc;
+  if (dz.general) {
+    const double* t = dz.abc_loc.as<double>();
+    rc = thomas_reg_local_run(ncol, n3l, t, t + n3l, t + 2 * n3l, lam, W, sing_loc, nsm, corr, g_stream, done);
+  } else {
+    rc = thomas_uni_local_run(ncol, n3l, lam, W, sing_loc, nsm, &dz.uni, corr, g_stream, done);
+  }
+  if (rc) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: local solve failed: %s", cudaGetErrorString((cudaError_t)rc));
+  if (*done) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 // once per plan / coefficient generation: local block description, the reference-order column list, and the
 // right-hand-side independent interface coefficients p, q (two local solves on unit right-hand sides)
 int dz_setup(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, bool periodic, int singular) {
   SolverPlan::DzState& dz = sp->dz;
-  if (dz.gen == sp->cache_gen && dz.n3l == n3l && dz.rank == r && dz.P == P && dz.tol == g_ref_tol) return 0;
+  const bool general = !(g_z_uniform_ok && sp->z_uniform.uniform);   // the same choice on every rank (global property)
+  if (dz.gen == sp->cache_gen && dz.n3l == n3l && dz.rank == r && dz.P == P && dz.tol == g_ref_tol && dz.general == general) return 0;
   dz.gen = sp->cache_gen; dz.n3l = n3l; dz.rank = r; dz.P = P; dz.tol = g_ref_tol;
   dz.ok = false;
   const int ng3 = n3l * P, k0 = r * n3l;
   const long ncol = (long)n1 * n2;
   const size_t nloc = (size_t)ncol * n3l;
   if ((int)sp->h_a.size() != ng3) return 0;
-  if (!thomas_detect_uniform(n3l, sp->h_a.data() + k0, sp->h_b.data() + k0, sp->h_c.data() + k0, false, dz.uni)) return 0;
+  dz.general = general;
+  if (!dz.general) {
+    if (!thomas_detect_uniform(n3l, sp->h_a.data() + k0, sp->h_b.data() + k0, sp->h_c.data() + k0, false, dz.uni)) return 0;
+  } else {                                                 // local rows of a, b, c with the couplings out of the block cut
+    std::vector<double> t(3 * (size_t)n3l);
+    for (int k = 0; k < n3l; ++k) { t[k] = sp->h_a[k0 + k]; t[n3l + k] = sp->h_b[k0 + k]; t[2 * n3l + k] = sp->h_c[k0 + k]; }
+    t[0] = 0.0; t[3 * (size_t)n3l - 1] = 0.0;
+    if (int rc = dz.abc_loc.reserve(t.size() * sizeof(double))) return rc;
+    CK(cudaMemcpyAsync(dz.abc_loc.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
   dz.ca = (periodic || r > 0) ? sp->h_a[k0] : 0.0;
   dz.cc = (periodic || r < P - 1) ? sp->h_c[k0 + n3l - 1] : 0.0;
   const double* lam = sp->lam_int.as<double>();
@@ -1048,10 +1080,8 @@ int dz_setup(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, bool periodi
     dz_fill_plane_kernel<<<nb, 256, 0, g_stream>>>(pass == 0 ? S : S + (size_t)ncol * (n3l - 1), ncol, pass == 0 ? dz.ca : dz.cc);
     LAUNCHED();
     bool done = false;
-    int rc = thomas_uni_local_run(ncol, n3l, lam, S, sing_loc, nsm, &dz.uni, nullptr, g_stream, &done);
-    if (rc) return fail(FLUTAS_B200_ERR_CUDA, "distributed z set-up: local solve failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (int rc = dz_local_run(sp, ncol, n3l, S, sing_loc, nullptr, &done)) return rc;
     if (!done) return 0;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
     dz_send_planes_kernel<<<nb, 256, 0, g_stream>>>(ncol, ncol_own, r, S, S + (size_t)ncol * (n3l - 1),
                                                      dz_peers(sp->peer_pencil, P, pass == 0 ? L.oPF : L.oQF),
                                                      dz_peers(sp->peer_pencil, P, pass == 0 ? L.oPL : L.oQL));
@@ -1085,9 +1115,8 @@ int dz_solve_z(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, double* W1
                                                                                 dz.own, dz_peers(sp->peer_recv, P, L.oGATH));
       LAUNCHED();
     }
-    int rc = thomas_uni_local_run(ncol, n3l, lam, W1, sing_loc, nsm, &dz.uni, nullptr, g_stream, &done);      // pass 1
-    if (rc || !done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: local solve failed (%s)", rc ? cudaGetErrorString((cudaError_t)rc) : "shape");
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (int rc = dz_local_run(sp, ncol, n3l, W1, sing_loc, nullptr, &done)) return rc;                        // pass 1
+    if (!done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: local solve not served for this shape");
   }
   {
     StageTimer t(ST_ZI);
@@ -1121,9 +1150,8 @@ int dz_solve_z(SolverPlan* sp, int n1, int n2, int n3l, int P, int r, double* W1
   {
     StageTimer t(ST_ZC);
     const ThomasCorr corr{mine + L.oXP, mine + L.oXN, dz.ca, dz.cc};
-    int rc = thomas_uni_local_run(ncol, n3l, lam, W1, sing_loc, nsm, &dz.uni, &corr, g_stream, &done);          // pass 2
-    if (rc || !done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: correction solve failed (%s)", rc ? cudaGetErrorString((cudaError_t)rc) : "shape");
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (int rc = dz_local_run(sp, ncol, n3l, W1, sing_loc, &corr, &done)) return rc;                           // pass 2
+    if (!done) return fail(FLUTAS_B200_ERR_CUDA, "distributed z: correction solve not served for this shape");
     if (dz.nsel) {
       const long cnt = (long)dz.nsel * n3l;
       dz_apply_sel_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, g_stream>>>(dz.nsel, n3l, ncol, dz.sel_dev.as<int>(), mine_recv + L.oOVR, W1);

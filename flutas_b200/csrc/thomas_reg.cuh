@@ -250,6 +250,17 @@ __device__ __forceinline__ void dsmem_store(double* local, unsigned peer, double
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
 }
 
+// Distributed z solve (capi.cu, solver_slab_dz): a rank holds n3l consecutive levels of EVERY column.  Pass 1 solves the
+// rank-local block T_g y = b (this kernel, CORR = false, coefficients truncated at the slab ends); after the 2G x 2G
+// interface system has delivered the neighbours' boundary unknowns x_prev, x_next per column, pass 2 (CORR = true) forms
+//     x = y + T_g^{-1} ( -a_first x_prev e_first - c_last x_next e_last )
+// in the same sweep: the tile is read as y, the right-hand side is synthesised in registers, and y + correction is stored.
+struct ThomasCorr {
+  const double* xprev;          // [ncol] last unknown of the rank below (unused where ca == 0)
+  const double* xnext;          // [ncol] first unknown of the rank above
+  double ca, cc;                // the true couplings a(first level), c(last level) that the local block leaves out
+};
+
 // shared memory (doubles) of the kernel below
 template <int L, int TI>
 inline size_t thomas_reg_smem_doubles(int nz, int maxt, int nbuf, int cl, bool uni) {
@@ -263,10 +274,12 @@ inline size_t thomas_reg_smem_doubles(int nz, int maxt, int nbuf, int cl, bool u
 // after next is requested as soon as the current one sits in registers.  Measured (B200, v7): NBUF = 2 is SLOWER
 // (512^3: 0.59 -> 0.76 ms, 1024^3: 6.36 -> 6.69 ms) -- more requests in flight do not help a kernel that sits at its
 // access-pattern ceiling; kept as a compile-time option, default 1.
-template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL>
+// CORR (distributed z solve, pass 2; CL = 1, NBUF = 1 only): the tile is NOT fetched -- the right-hand side is the two
+// boundary couplings, synthesised in registers -- and y is re-read (L2) and added at the store.
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL, bool CORR = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const double* W,
-                  ColGeom og) {
+                  ColGeom og, ThomasCorr corr) {
   using TR = ThomasReg<L, TI>;
   extern __shared__ double smem[];
   const int nz = T.nz, S = T.S;                           // S = segments of a whole column (all CTAs of the cluster)
@@ -298,7 +311,7 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
   const long tstride = gridDim.x / CL;                    // clusters in the grid
 
   auto fetch = [&](long tile, int buf) {                   // always commits a group (possibly empty): uniform counting
-    if (tile < ntiles) {
+    if (!CORR && tile < ntiles) {
       const long col = min(tile * TI + lane, ncol - 1);
       const double* src = W + col + (long)k0 * ncol;
       double* sl = slots + (size_t)buf * L * MAXT + tid;
@@ -330,7 +343,11 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
     {
       const double* sl = slots + (size_t)buf * L * MAXT + tid;
 #pragma unroll
-      for (int l = 0; l < L; ++l) v[l] = sl[l * MAXT];
+      for (int l = 0; l < L; ++l) v[l] = CORR ? 0.0 : sl[l * MAXT];
+    }
+    if (CORR && live) {
+      if (s == 0 && corr.ca != 0.0) v[0] = -corr.ca * __ldg(corr.xprev + col);
+      if (s == S - 1 && corr.cc != 0.0) v[L - 1] = v[L - 1] - corr.cc * __ldg(corr.xnext + col);
     }
     if (NBUF == 2) fetch(tile + 2 * tstride, buf);        // this slot set is free again (slots are private per thread)
 
@@ -379,6 +396,11 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
     for (int rr = 0; rr < CL; ++rr) TR::pcr_finish(src, X, T, lane, s_loc + rr * S_loc);
     __syncthreads();
     TR::phase3(v, X, T, lane, s, g);
+    if (CORR && live) {                                    // x = y + correction; y still sits where x goes (in place)
+      const double* yp = W + col + (long)k0 * ncol;
+#pragma unroll
+      for (int l = 0; l < L; ++l) v[l] += yp[(long)l * ncol];
+    }
     if (live) {
       if (one_chunk) {
         double* dstp = obase + col;
@@ -401,10 +423,11 @@ thomas_reg_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict
 
 struct ThomasCfgKey { int nz, uni, periodic; };
 
-template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL>
+template <int L, int TI, int MAXT, bool UNI, int MINB, int NBUF, int CL, bool CORR = false>
 inline cudaError_t thomas_reg_launch1(long ncol, const ThomasArgs& T, const double* lam, const double* W, const ColGeom& og,
-                                      int nsm, cudaStream_t st) {
-  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB, NBUF, CL>;
+                                      int nsm, cudaStream_t st, const ThomasCorr* corr = nullptr) {
+  auto kern = thomas_reg_kernel<L, TI, MAXT, UNI, MINB, NBUF, CL, CORR>;
+  const ThomasCorr cr = corr ? *corr : ThomasCorr{nullptr, nullptr, 0.0, 0.0};
   const size_t smem = thomas_reg_smem_doubles<L, TI>(T.nz, MAXT, NBUF, CL, UNI) * sizeof(double);
   const long ntiles = (ncol + TI - 1) / TI;
   const int threads = TI * T.S / CL;
@@ -432,7 +455,7 @@ inline cudaError_t thomas_reg_launch1(long ncol, const ThomasArgs& T, const doub
   }
   const long ncl = ntiles < (long)nclusters ? ntiles : (long)nclusters;
   cfg.gridDim = dim3((unsigned)(ncl * CL));
-  return cudaLaunchKernelEx(&cfg, kern, ncol, ntiles, T, lam, W, og);
+  return cudaLaunchKernelEx(&cfg, kern, ncol, ntiles, T, lam, W, og, cr);
 }
 
 // Tile shapes.  cfg 0: 8 columns, one CTA per tile (v4-v7).  cfg 1: 16 columns, one 512-thread CTA (nz <= 512 at L = 16).
@@ -499,6 +522,31 @@ inline int thomas_reg_run(long ncol, int nz, const double* az, const double* bz,
   }
   if (e != cudaSuccess) return (int)e;
   *done = served;
+  return 0;
+}
+
+// Rank-local block of the distributed z solve on a GENERAL z grid (coefficient tables az, bz, cz of the nz = n3l local rows,
+// couplings out of the block already zeroed): L = 16, 16-column tiles, S = nz/16 in 2..32; block size fitted to S so that
+// several CTAs share an SM.  corr = nullptr: pass 1; else pass 2.  *done = false: shape not served.
+inline bool thomas_reg_local_ok(int nz, long ncol) { return nz % 16 == 0 && nz / 16 >= 2 && nz / 16 <= 32 && (ncol % 16) == 0; }
+inline int thomas_reg_local_run(long ncol, int nz, const double* az, const double* bz, const double* cz, const double* lam, double* W,
+                                int singular, int nsm, const ThomasCorr* corr, cudaStream_t st, bool* done) {
+  *done = false;
+  if (!thomas_reg_local_ok(nz, ncol)) return 0;
+  ThomasArgs T;
+  T.nz = nz; T.S = nz / 16; T.periodic = 0; T.singular = singular; T.az = az; T.bz = bz; T.cz = cz; T.padded = 0; T.uniform = 0;
+  ColGeom og;
+  for (int q = 0; q < FB_MAX_RANKS; ++q) og.ptr[q] = W;
+  og.n3l = nz; og.koff = 0;
+  cudaError_t e;
+  if (T.S <= 8) e = corr ? thomas_reg_launch1<16, 16, 128, false, 4, 1, 1, true>(ncol, T, lam, W, og, nsm, st, corr)
+                         : thomas_reg_launch1<16, 16, 128, false, 4, 1, 1, false>(ncol, T, lam, W, og, nsm, st);
+  else if (T.S <= 16) e = corr ? thomas_reg_launch1<16, 16, 256, false, 2, 1, 1, true>(ncol, T, lam, W, og, nsm, st, corr)
+                               : thomas_reg_launch1<16, 16, 256, false, 2, 1, 1, false>(ncol, T, lam, W, og, nsm, st);
+  else e = corr ? thomas_reg_launch1<16, 16, 512, false, 1, 1, 1, true>(ncol, T, lam, W, og, nsm, st, corr)
+                : thomas_reg_launch1<16, 16, 512, false, 1, 1, 1, false>(ncol, T, lam, W, og, nsm, st);
+  if (e != cudaSuccess) return (int)e;
+  *done = true;
   return 0;
 }
 

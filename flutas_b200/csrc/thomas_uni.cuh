@@ -175,17 +175,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
-// Distributed z solve (capi.cu, solver_slab_dz): a rank holds n3l consecutive levels of EVERY column.  Pass 1 solves the
-// rank-local block T_g y = b (this kernel, CORR = false, coefficients truncated at the slab ends); after the 2G x 2G
-// interface system has delivered the neighbours' boundary unknowns x_prev, x_next per column, pass 2 (CORR = true) forms
-//     x = y + T_g^{-1} ( -a_first x_prev e_first - c_last x_next e_last )
-// in the same sweep: the tile is read as y, the right-hand side is synthesised in registers, and y + correction is stored.
-struct ThomasCorr {
-  const double* xprev;          // [ncol] last unknown of the rank below (unused where ca == 0)
-  const double* xnext;          // [ncol] first unknown of the rank above
-  double ca, cc;                // the true couplings a(first level), c(last level) that the local block leaves out
-};
-
 template <int L, int TI, int MINB, bool CORR = false>
 __global__ void __launch_bounds__(512 / MINB, MINB)
 thomas_uni_tma_kernel(long ncol, long ntiles, ThomasArgs T, const double* __restrict__ lam, const __grid_constant__ CUtensorMap tmap,

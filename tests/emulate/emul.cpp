@@ -514,7 +514,11 @@ extern "C" int emul_thomas_ref(int nz, long ncol, int periodic, int singular, co
 // (thomas_uni_emul<16,16>, exactly what thomas_uni_local_run launches) and the interface systems by dz_interface_solve.
 #include "../../flutas_b200/csrc/dz.cuh"
 
+// general == 1: the local block through the general kernel's phase functions (coefficient tables, thomas_reg_local_run)
+static int g_dz_general = 0;
+static const double *g_dz_a = nullptr, *g_dz_b = nullptr, *g_dz_c = nullptr;     // local rows of a, b, c for the general path
 static bool dz_local_solve(int n3l, long ncol, const ThomasArgs& uni, int singular, const double* lam, double* slab) {
+  if (g_dz_general) return emul_thomas_reg(16, n3l, ncol, 0, singular, g_dz_a, g_dz_b, g_dz_c, lam, slab, 0) == 0;
   ThomasArgs T = uni;
   T.nz = n3l; T.S = n3l / 16; T.periodic = 0; T.singular = singular; T.az = T.bz = T.cz = nullptr; T.padded = 0;
   if (n3l % 16 || T.S < 2 || T.S > 32) return false;
@@ -531,7 +535,8 @@ extern "C" int emul_dz(int nz, int G, long ncol, int periodic, int singular, con
   std::vector<double> PF((size_t)G * ncol), PL(PF), QF(PF), QL(PF), scratch((size_t)ncol * n3l);
   for (int g = 0; g < G; ++g) {
     const int k0 = g * n3l;
-    if (!thomas_detect_uniform(n3l, a + k0, b + k0, c + k0, false, uni[g])) return 2;
+    if (!g_dz_general && !thomas_detect_uniform(n3l, a + k0, b + k0, c + k0, false, uni[g])) return 2;
+    g_dz_a = a + k0; g_dz_b = b + k0; g_dz_c = c + k0;
     ca[g] = (periodic || g > 0) ? a[k0] : 0.0;
     cc[g] = (periodic || g < G - 1) ? c[k0 + n3l - 1] : 0.0;
     const int sing = (singular && g == G - 1) ? 1 : 0;
@@ -546,8 +551,10 @@ extern "C" int emul_dz(int nz, int G, long ncol, int periodic, int singular, con
     }
   }
   // pass 1 on every rank
-  for (int g = 0; g < G; ++g)
+  for (int g = 0; g < G; ++g) {
+    g_dz_a = a + g * n3l; g_dz_b = b + g * n3l; g_dz_c = c + g * n3l;
     if (!dz_local_solve(n3l, ncol, uni[g], (singular && g == G - 1) ? 1 : 0, lam, W + (size_t)ncol * g * n3l)) return 3;
+  }
   // interface systems
   std::vector<double> XP((size_t)G * ncol), XN((size_t)G * ncol);
   for (long q = 0; q < ncol; ++q) {
@@ -578,9 +585,18 @@ extern "C" int emul_dz(int nz, int G, long ncol, int periodic, int singular, con
       scratch[q] = -ca[g] * XP[(size_t)g * ncol + q];
       scratch[(size_t)ncol * (n3l - 1) + q] += -cc[g] * XN[(size_t)g * ncol + q];
     }
+    g_dz_a = a + g * n3l; g_dz_b = b + g * n3l; g_dz_c = c + g * n3l;
     if (!dz_local_solve(n3l, ncol, uni[g], (singular && g == G - 1) ? 1 : 0, lam, scratch.data())) return 3;
     double* y = W + (size_t)ncol * g * n3l;
     for (size_t i = 0; i < (size_t)ncol * n3l; ++i) y[i] += scratch[i];
   }
   return 0;
+}
+
+extern "C" int emul_dz_general(int nz, int G, long ncol, int periodic, int singular, const double* a, const double* b, const double* c,
+                               const double* lam, double* W) {
+  g_dz_general = 1;
+  const int rc = emul_dz(nz, G, ncol, periodic, singular, a, b, c, lam, W);
+  g_dz_general = 0;
+  return rc;
 }

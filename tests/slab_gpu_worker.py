@@ -35,7 +35,9 @@ def main():
              ("rb", (64, 48, 40), ("NN", "NN", "NN"), 0.0, None), ("dd72", (32, 40, 72), ("DD", "NN", "DD"), 0.0, None),
              ("uni-chan", (64, 32, 128), ("PP", "PP", "NN"), 0.0, None), ("uni-per", (32, 32, 128), ("PP", "PP", "PP"), 0.0, None),
              ("uni-rb", (64, 64, 64), ("NN", "NN", "NN"), 0.0, None), ("uni-dn", (32, 64, 256), ("ND", "PP", "DD"), 0.0, None),
-             ("uni-fix", (64, 32, 128), ("PP", "PP", "NN"), 0.0, 1.0e-2))
+             ("uni-fix", (64, 32, 128), ("PP", "PP", "NN"), 0.0, 1.0e-2),
+             # tanh-stretched z: the distributed z solve through the general kernel (coefficient tables)
+             ("str-chan", (64, 32, 128), ("PP", "PP", "NN"), 2.0, None), ("str-dd", (32, 32, 256), ("NN", "PP", "DD"), 1.0, 1.0e-3))
     for name, ng, cbc, gr, ref_tol in cases:
         lib.check(lib.load().flutas_b200_debug_ref_tol(1.0e-5 if ref_tol is None else ref_tol))
         if ng[0] % world or ng[2] % world or ng[1] % world:

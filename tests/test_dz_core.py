@@ -27,6 +27,7 @@ def emul():
         subprocess.check_call([cxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.emul_dz.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    L.emul_dz_general.argtypes = L.emul_dz.argtypes
     return L
 
 
@@ -85,3 +86,38 @@ def test_interface_couplings_vanish_at_walls(emul):
     for sol in sols:
         assert np.max(np.abs(sol - sols[0])) <= 1e-13 * np.max(np.abs(sols[0]))
         assert np.max(np.abs(sol - exact)) <= 2.0 / nz ** 2
+
+
+@pytest.mark.parametrize("bcz,gr", [("NN", 2.0), ("DD", 1.0), ("ND", 3.0), ("NN", 0.0), ("PP", 0.0)])
+@pytest.mark.parametrize("nz,G", [(64, 2), (128, 4), (256, 8), (512, 2)])
+def test_distributed_z_on_a_general_grid(emul, bcz, gr, nz, G):
+    """tanh-stretched (and round-off-non-uniform) z grids: the local blocks go through the general kernel's phase
+    functions with the local coefficient rows (thomas_reg_local_run)"""
+    periodic = 1 if bcz == "PP" else 0
+    rng = np.random.default_rng(nz + G + int(gr))
+    dzc, dzf = initsolver.initgrid(nz, gr, 2.0 * np.pi if gr == 0.0 else 1.0, 1)      # lz = 2 pi: rows differ in the last bits
+    a, b, c = initsolver.tridmatrix(bcz, nz, 1, 1.0 / dzc, 1.0 / dzf)
+    singular = 1 if bcz in ("NN", "PP") else 0
+    nx, ny = 4, 4
+    lam = -rng.uniform(0.01 * np.abs(a).max(), 4.0 * np.abs(a).max(), (nx, ny))
+    lam[0, 0] = 0.0
+    lam = np.asfortranarray(lam)
+    rhs = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, nz)))
+    if singular:
+        rhs[0, 0, :] -= (rhs[0, 0, :] * dzf[1:-1]).sum() / dzf[1:-1].sum()
+    ref = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bool(periodic))
+    got = rhs.copy(order="F")
+    assert emul.emul_dz_general(nz, G, nx * ny, periodic, singular, _p(a), _p(b), _p(c), _p(lam), _p(got)) == 0
+    for i in range(nx):
+        for j in range(ny):
+            g, r = got[i, j, :], ref[i, j, :]
+            if singular and i == 0 and j == 0:
+                assert g[-1] == 0.0
+                A = np.diag(b) + np.diag(a[1:], -1) + np.diag(c[:-1], 1)
+                if periodic:
+                    A[0, nz - 1] += a[0]
+                    A[nz - 1, 0] += c[nz - 1]
+                assert np.max(np.abs(A @ g - rhs[i, j, :])) <= 1e-11 * np.max(np.abs(a))
+                continue
+            tol = max(3e-13, 4.0 * np.abs(a).max() / max(abs(lam[i, j]), 1.0) * 2e-15)
+            assert np.max(np.abs(g - r)) <= tol * np.max(np.abs(r)), (i, j, lam[i, j])
