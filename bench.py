@@ -108,7 +108,7 @@ def run_reference(args, rank, world):
     from flutas_b200.cases import Case
     from oracle import oracle
     oracle.set_num_threads(host_threads())
-    case = Case.from_config(args.workload)
+    case = Case.from_config(args.workload, gr=args.gr)
     s, n = case.setup, case.ng
     n1, n2, n3 = n
     npts = n1 * n2 * n3
@@ -200,6 +200,7 @@ def workload_config(case, wid):
     from flutas_b200.cases import CONFIGS
     n1, n2, n3 = case.ng
     return {"workload": "%s: %s" % (wid, CONFIGS[wid]["desc"]), "grid": [n1, n2, n3], "pressure_bc": "/".join(case.cbc),
+            "z_grid": "uniform" if case.setup.gr == 0.0 else "tanh-stretched, gr = %g" % case.setup.gr,
             "l2_policy": "inputs larger than L2: one FP64 field is %.2f GB vs 126 MB of L2" % (8e-9 * n1 * n2 * n3),
             "step": "one solver call (5 kernels), in place, device resident"}
 
@@ -212,6 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="NS")
+    ap.add_argument("--gr", type=float, default=0.0, help="tanh stretching of the z grid (initgrid.f90:17-97); 0 = uniform, as in every BASELINE config")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the oracle run (parity + cpu_baseline keys become null): kernel A/B timing only")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -242,7 +244,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     api.init(local_rank, rank, world)
 
-    case = Case.from_config(args.workload)
+    case = Case.from_config(args.workload, gr=args.gr)
     s = case.setup
     ng = case.ng
     n1, n2, n3g = ng

@@ -100,6 +100,7 @@ class SolverSetup:
         self.cbc = tuple(cbc)                     # ("PP","PP","NN")
         self.bc = bc if bc is not None else ((0.0, 0.0),) * 3
         self.nh_d = nh_d
+        self.gr = float(gr)
         n1, n2, n3 = self.ng
         self.dl = (lengths[0] / n1, lengths[1] / n2, lengths[2] / n3)
         self.dli = tuple(1.0 / d for d in self.dl)
