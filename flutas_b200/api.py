@@ -90,6 +90,51 @@ def fftend(arrplan):
     _lib.check(_lib.load().flutas_b200_fftend(arrplan.h))
 
 
+def fft(plan, arr, n=None):
+    """fft(plan,arr), src/fft.f90:181-193: unnormalised in-place r2r transform of a dense pencil array in FFTW's element
+    order.  plan = `arrplan.h[q]` (q = 0 fwd-x, 1 bwd-x, 2 fwd-y, 3 bwd-y) or an `R2RPlan`; arr = Fortran-ordered numpy
+    array, or a device tensor together with its extents n."""
+    _use_torch_stream()
+    if isinstance(plan, R2RPlan):
+        plan = plan.h
+    if n is None:
+        n = arr.shape
+    nn = (C.c_int * 3)(*n)
+    _lib.check(_lib.load().flutas_b200_fft(C.c_void_p(plan) if isinstance(plan, int) else plan, nn, _ptr(arr)))
+    return arr
+
+
+FFTW_KINDS = {"R2HC": 0, "HC2R": 1, "REDFT01": 4, "REDFT10": 5, "REDFT11": 6, "RODFT01": 8, "RODFT10": 9, "RODFT11": 10}
+
+
+class R2RPlan:
+    """Stand-alone plan with the arguments of the reference's fftw_plan_guru_r2r calls (src/fft.f90:75-86,113-124)."""
+
+    def __init__(self, n, stride, howmany_n, howmany_stride, kind):
+        self.h = C.c_void_p()
+        hn = (C.c_int * 2)(*howmany_n)
+        hs = (C.c_int * 2)(*howmany_stride)
+        code = FFTW_KINDS[kind] if isinstance(kind, str) else int(kind)
+        _lib.check(_lib.load().flutas_b200_plan_r2r(n, stride, hn, hs, code, C.byref(self.h)))
+
+    @property
+    def dims(self):
+        nn = (C.c_int * 3)()
+        _lib.check(_lib.load().flutas_b200_plan_dims(self.h, nn))
+        return tuple(nn)
+
+    def destroy(self):
+        if self.h:
+            _lib.check(_lib.load().flutas_b200_destroy_plan(self.h))
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 def solver(n, arrplan, normfft, lambdaxy, a, b, c, bcz, c_or_f, p):
     _use_torch_stream()
     nn = (C.c_int * 3)(*n)

@@ -5,6 +5,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SO = os.path.join(CSRC, "libflutas_b200.so")
+SEAM_SO = os.path.join(CSRC, "libflutas_b200_fftw.so")     # FFTW-named entry points over the C ABI (csrc/fftw_seam.cpp)
 SOURCES = ["capi.cu", "fft_p2_x.cu", "fft_p2_y.cu", "fft_reg_x_fwd.cu", "fft_reg_x_bwd.cu", "fft_reg_y_fwd.cu",
            "fft_reg_y_bwd.cu"]
 HEADERS = ["kernels.cuh", "tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "thomas_uni.cuh", "thomas_ref.cuh", "geom.cuh", "fft_p2.cuh", "fft_p2.h", "reg_fft.cuh", "fft_reg.cuh", "fft_reg.h"]
@@ -20,10 +21,10 @@ def _nvcc():
 
 
 def is_stale():
-    if not os.path.exists(SO):
+    if not os.path.exists(SO) or not os.path.exists(SEAM_SO):
         return True
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    t = min(os.path.getmtime(SO), os.path.getmtime(SEAM_SO))
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["fftw_seam.cpp"]]
     deps.append(os.path.join(CSRC, "..", "..", "include", "flutas_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -49,6 +50,10 @@ def build(force=False, verbose=False, defines=(), tag=None):
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     subprocess.check_call(nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs, cwd=CSRC)
+    if tag is None:
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SEAM_SO, "fftw_seam.cpp", "-L.", "-lflutas_b200",
+                               "-Wl,-rpath,$ORIGIN"], cwd=CSRC)
     return so
 
 

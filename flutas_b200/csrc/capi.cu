@@ -195,6 +195,7 @@ struct SolverPlan {
   DevBuf work, scratchD, scratchP2, pstage;
   // cached coefficients
   DevBuf lam_int, abc, maps, lam_raw;
+  DevBuf fft_maps;               // spectral slot -> FFTW index of both directions (flutas_b200_fft)
   int cached_nz = 0;
   bool cached_periodic = false;
   const double* key_lam = nullptr;
@@ -252,6 +253,8 @@ struct PlanHandle {
   unsigned long long magic;
   SolverPlan* plan;
   int which;                     // 0 fwd-x, 1 bwd-x, 2 fwd-y, 3 bwd-y
+  bool owned = false;            // stand-alone plan of flutas_b200_plan_r2r: the handle owns `plan`
+  int dims[3] = {0, 0, 0};       // ... and knows the array it was planned for
 };
 
 SolverPlan* plan_of(void* const arrplan[4]) {
@@ -704,6 +707,18 @@ int flutas_b200_synchronize(void) {
   return FLUTAS_B200_OK;
 }
 
+}  // extern "C"
+// tables of one transform direction (shared-memory tile kernels always, register kernels where the length allows)
+static int build_line(DevLinePlan& lp, int N, int kind) {
+  lp.h = make_line_plan(N, kind);
+  if (!lp.h.ok) return fail(FLUTAS_B200_ERR_UNSUPPORTED, "transform length %d: need an even length whose half factors into 2,3,5", N);
+  if (int rc = lp.upload()) return rc;
+  if (g_fft_level != 0 || !reg_fft_supported(lp.h.N)) return 0;
+  lp.hr = make_reg_plan(lp.h.N, lp.h.kind);
+  lp.use_reg = lp.hr.ok;
+  return lp.use_reg ? lp.upload_reg() : 0;
+}
+extern "C" {
 int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], const char c_or_f[2],
                        void* arrplan[4], double* normfft) {
   if (!n_x || !n_y || !bcxy || !c_or_f || !arrplan || !normfft) return fail(FLUTAS_B200_ERR_ARG, "null argument");
@@ -718,37 +733,22 @@ int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], c
   SolverPlan* sp = new SolverPlan();
   sp->n1 = n_x[0]; sp->n2 = n_y[1];
   memcpy(sp->bcxy, bcxy, 4);
-  sp->px.h = make_line_plan(sp->n1, kx);
-  sp->py.h = make_line_plan(sp->n2, ky);
-  if (!sp->px.h.ok || !sp->py.h.ok) {
-    const int bad = sp->px.h.ok ? sp->n2 : sp->n1;
-    delete sp;
-    return fail(FLUTAS_B200_ERR_UNSUPPORTED, "transform length %d: need an even length whose half factors into 2,3,5", bad);
-  }
-  int rc = sp->px.upload();
-  if (!rc) rc = sp->py.upload();
-  for (DevLinePlan* lp : {&sp->px, &sp->py}) {
-    if (rc || g_fft_level != 0 || !reg_fft_supported(lp->h.N)) continue;
-    lp->hr = make_reg_plan(lp->h.N, lp->h.kind);
-    lp->use_reg = lp->hr.ok;
-    if (lp->use_reg) rc = lp->upload_reg();
-  }
+  int rc = build_line(sp->px, sp->n1, kx);
+  if (!rc) rc = build_line(sp->py, sp->n2, ky);
   if (rc) { delete sp; return rc; }
   // normfft exactly as src/fft.f90:71,87,125,150 (norm = (1,0) for PP, (2,0) for NN/DD; ix = iy = 0)
   double nf = 1.0;
   nf = nf * (kx == KIND_PP ? 1.0 : 2.0) * (sp->n1 + 0.0 - 0);
   nf = nf * (ky == KIND_PP ? 1.0 : 2.0) * (sp->n2 + 0.0 - 0);
   *normfft = 1.0 / nf;
-  for (int q = 0; q < 4; ++q) arrplan[q] = new PlanHandle{PLAN_MAGIC, sp, q};
+  for (int q = 0; q < 4; ++q) { PlanHandle* h = new PlanHandle(); h->magic = PLAN_MAGIC; h->plan = sp; h->which = q; arrplan[q] = h; }
   return FLUTAS_B200_OK;
 }
 
-int flutas_b200_fftend(void* arrplan[4]) {
-  SolverPlan* sp = plan_of(arrplan);
-  if (!sp) return fail(FLUTAS_B200_ERR_ARG, "fftend: not a flutas_b200 plan");
+static void destroy_solver_plan(SolverPlan* sp) {
   for (DevBuf* b : {&sp->px.rtables, &sp->py.rtables}) b->release();
   for (DevBuf* b : {&sp->px.tables, &sp->py.tables, &sp->work, &sp->scratchD, &sp->scratchP2, &sp->pstage,
-                    &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw}) b->release();
+                    &sp->lam_int, &sp->abc, &sp->maps, &sp->lam_raw, &sp->fft_maps}) b->release();
   for (DevBuf* b : {&sp->sendrecv, &sp->pencil, &sp->lam_win}) b->release();
   for (DevBuf* b : {&sp->dz.sel_dev, &sp->dz.sel_lam_own, &sp->dz.abc_loc}) b->release();
   for (DevBuf* b : {&sp->dz_ref.col, &sp->dz_ref.lam, &sp->dz_ref.pin, &sp->dz_ref.z, &sp->dz_ref.d, &sp->dz_ref.piv, &sp->dz_ref.p2, &sp->dz_ref.den, &sp->dz_ref.F}) b->release();
@@ -761,6 +761,13 @@ int flutas_b200_fftend(void* arrplan[4]) {
   if (sp->h_err) cudaFreeHost(sp->h_err);
   sp->magic = 0;
   delete sp;
+}
+
+int flutas_b200_fftend(void* arrplan[4]) {
+  SolverPlan* sp = plan_of(arrplan);
+  if (!sp) return fail(FLUTAS_B200_ERR_ARG, "fftend: not a flutas_b200 plan");
+  if (((PlanHandle*)arrplan[0])->owned) return fail(FLUTAS_B200_ERR_ARG, "fftend: stand-alone plans end with flutas_b200_destroy_plan");
+  destroy_solver_plan(sp);
   for (int q = 0; q < 4; ++q) { delete (PlanHandle*)arrplan[q]; arrplan[q] = nullptr; }
   return FLUTAS_B200_OK;
 }
@@ -843,6 +850,119 @@ int flutas_b200_solver(const int n[3], void* const arrplan[4], double normfft, c
     CK(cudaMemcpyAsync(p, pd, pcount * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
   }
+  return FLUTAS_B200_OK;
+}
+
+// fft(plan,arr), src/fft.f90:181-193: one batched, unnormalised, in-place r2r transform of a dense pencil array in FFTW's
+// element order.  The solver never calls this (its stages hand the spectrum over in slot order); it exists for hosts that
+// keep the reference's solver_cpu.f90 and for the per-kind parity tests.  n = extents of arr.
+int flutas_b200_fft(void* plan, const int n[3], double* arr) {
+  PlanHandle* h = (PlanHandle*)plan;
+  if (!h || h->magic != PLAN_MAGIC || !h->plan || h->plan->magic != PLAN_MAGIC) return fail(FLUTAS_B200_ERR_ARG, "fft: not a flutas_b200 plan");
+  if (!n || !arr) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  SolverPlan* sp = h->plan;
+  const bool xdir = h->which < 2, fwd = (h->which % 2) == 0;
+  DevLinePlan& lp = xdir ? sp->px : sp->py;
+  const int n1 = n[0], n2 = n[1];
+  const long n3 = n[2];
+  if (n1 < 1 || n2 < 1 || n3 < 1 || lp.h.N != (xdir ? n1 : n2))
+    return fail(FLUTAS_B200_ERR_ARG, "fft: array (%d,%d,%ld) does not match the plan (length %d along %c)", n1, n2, n3, lp.h.N, xdir ? 'x' : 'y');
+  const size_t npts = (size_t)n1 * n2 * n3;
+  if (int rc = sp->work.reserve(npts * sizeof(double))) return rc;
+  double* W = sp->work.as<double>();
+  double* A = arr;
+  const bool host = !on_device(arr);
+  if (host) {
+    if (int rc = sp->pstage.reserve(npts * sizeof(double))) return rc;
+    A = sp->pstage.as<double>();
+    CK(cudaMemcpyAsync(A, arr, npts * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  }
+  const size_t nmx = sp->px.mode().size(), nmy = sp->py.mode().size();
+  if (!sp->fft_maps.p) {
+    if (int rc = sp->fft_maps.reserve((nmx + nmy + 1) * sizeof(int))) return rc;
+    if (nmx) CK(cudaMemcpyAsync(sp->fft_maps.p, sp->px.mode().data(), nmx * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    if (nmy) CK(cudaMemcpyAsync(sp->fft_maps.as<int>() + nmx, sp->py.mode().data(), nmy * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  }
+  const int* map = sp->fft_maps.as<int>() + (xdir ? 0 : nmx);
+  const unsigned nblk = (unsigned)((npts + 255) / 256);
+  const LineGeom gw{0, (long)n1, (long)n1 * n2, n2, (long)n2 * n3};
+  int rc = 0;
+  if (xdir) {
+    if (fwd) {
+      rc = run_x<true>(lp, A, gw, W, gw, 1.0);
+      if (!rc) { fft_permute_kernel<<<nblk, 256, 0, g_stream>>>(n1, n2, n3, 0, 1, map, W, A); LAUNCHED(); }
+    } else {
+      fft_permute_kernel<<<nblk, 256, 0, g_stream>>>(n1, n2, n3, 0, 0, map, A, W); LAUNCHED();
+      rc = run_x<false>(lp, W, gw, A, gw, 1.0);
+    }
+  } else {
+    const SpecGeom sg = local_spec(W, n1);
+    if (fwd) {
+      CK(cudaMemcpyAsync(W, A, npts * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+      rc = run_y<true>(lp, W, n1, n3, sg);
+      if (!rc) { fft_permute_kernel<<<nblk, 256, 0, g_stream>>>(n1, n2, n3, 1, 1, map, W, A); LAUNCHED(); }
+    } else {
+      fft_permute_kernel<<<nblk, 256, 0, g_stream>>>(n1, n2, n3, 1, 0, map, A, W); LAUNCHED();
+      rc = run_y<false>(lp, W, n1, n3, sg);
+      if (!rc) CK(cudaMemcpyAsync(A, W, npts * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    }
+  }
+  if (rc) return rc;
+  if (host) {
+    CK(cudaMemcpyAsync(arr, A, npts * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+  }
+  return FLUTAS_B200_OK;
+}
+
+// Stand-alone plan with the arguments of fftw_plan_guru_r2r as src/fft.f90:75-86,113-124 passes them: rank 1,
+// (n, is) of the transform, two howmany dimensions (n, is), in place (os = is).  Served: the x layout (is = 1, dense lines)
+// and the y layout (is = howmany(1).n, howmany(1).is = 1).  kind = FFTW's integer code (src/fftw.f90:41-61).
+int flutas_b200_plan_r2r(int n, int is, const int hm_n[2], const int hm_is[2], int kind, void** plan) {
+  if (!hm_n || !hm_is || !plan) return fail(FLUTAS_B200_ERR_ARG, "null argument");
+  *plan = nullptr;
+  int k = -1, bwd = 0;
+  switch (kind) {
+    case 0: k = KIND_PP; break;             // R2HC
+    case 1: k = KIND_PP; bwd = 1; break;    // HC2R
+    case 5: k = KIND_NN; break;             // REDFT10
+    case 4: k = KIND_NN; bwd = 1; break;    // REDFT01
+    case 9: k = KIND_DD; break;             // RODFT10
+    case 8: k = KIND_DD; bwd = 1; break;    // RODFT01
+    case 6: k = KIND_ND; break;             // REDFT11 (its own inverse up to 2n)
+    case 10: k = KIND_DN; break;            // RODFT11
+    default: return fail(FLUTAS_B200_ERR_UNSUPPORTED, "r2r kind %d: the cell-centred table of src/fft.f90:233-291 uses R2HC, HC2R, "
+                         "REDFT10/01, RODFT10/01, REDFT11, RODFT11", kind);
+  }
+  int xdir = -1, dims[3] = {0, 0, hm_n[1]};
+  if (is == 1 && hm_is[0] == n && (long)hm_is[1] == (long)n * hm_n[0]) { xdir = 1; dims[0] = n; dims[1] = hm_n[0]; }
+  else if (hm_is[0] == 1 && is == hm_n[0] && (long)hm_is[1] == (long)hm_n[0] * n) { xdir = 0; dims[0] = hm_n[0]; dims[1] = n; }
+  if (xdir < 0 || n < 2 || hm_n[0] < 1 || hm_n[1] < 1)
+    return fail(FLUTAS_B200_ERR_UNSUPPORTED, "plan_r2r: only the dense x (is = 1) and y (is = n1) pencil layouts of src/fft.f90:75-86,113-124");
+  if (int rc = ensure_device()) return rc;
+  SolverPlan* sp = new SolverPlan();
+  if (xdir) sp->n1 = n; else sp->n2 = n;
+  if (int rc = build_line(xdir ? sp->px : sp->py, n, k)) { delete sp; return rc; }
+  PlanHandle* h = new PlanHandle();
+  h->magic = PLAN_MAGIC; h->plan = sp; h->which = (xdir ? 0 : 2) + bwd; h->owned = true;
+  for (int q = 0; q < 3; ++q) h->dims[q] = dims[q];
+  *plan = h;
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_plan_dims(void* plan, int n[3]) {
+  PlanHandle* h = (PlanHandle*)plan;
+  if (!h || h->magic != PLAN_MAGIC || !h->owned || !n) return fail(FLUTAS_B200_ERR_ARG, "plan_dims: not a stand-alone flutas_b200 plan");
+  for (int q = 0; q < 3; ++q) n[q] = h->dims[q];
+  return FLUTAS_B200_OK;
+}
+
+int flutas_b200_destroy_plan(void* plan) {
+  PlanHandle* h = (PlanHandle*)plan;
+  if (!h || h->magic != PLAN_MAGIC || !h->owned || !h->plan) return fail(FLUTAS_B200_ERR_ARG, "destroy_plan: not a stand-alone flutas_b200 plan");
+  destroy_solver_plan(h->plan);
+  h->magic = 0;
+  delete h;
   return FLUTAS_B200_OK;
 }
 

@@ -254,6 +254,20 @@ __global__ void permute_lambda_kernel(int n1, int n2, const double* __restrict__
   out[idx] = lam[mx[rx] + (long)n1 * my[ry]];
 }
 
+// One axis of a dense (n1, n2, n3) array between the kernels' spectral slot order and FFTW's order (map[slot] = FFTW index):
+// to_fftw: dst(.., map[s], ..) = src(.., s, ..); else dst(.., s, ..) = src(.., map[s], ..).  flutas_b200_fft only.
+__global__ void fft_permute_kernel(int n1, int n2, long n3, int axis, int to_fftw, const int* __restrict__ map,
+                                   const double* __restrict__ src, double* __restrict__ dst) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)n1 * n2 * n3) return;
+  const long jk = idx / n1;
+  const int i = (int)(idx - jk * n1);
+  const long k = jk / n2;
+  const int j = (int)(jk - k * n2);
+  const long other = axis == 0 ? idx - i + map[i] : ((long)k * n2 + map[j]) * n1 + i;
+  if (to_fftw) dst[other] = src[idx]; else dst[idx] = src[other];
+}
+
 // ------------------------------------------------------------------------------------------------
 // stencils.  u,v,w have halo nh_u (lower bound 1-nh_u), p has halo 1 (lower bound 0).
 struct StencilGeom {

@@ -68,6 +68,9 @@ module mod_flutas_b200
     integer(c_int) function flutas_b200_fftend(arrplan) bind(C,name='flutas_b200_fftend')
       import; type(c_ptr), intent(inout) :: arrplan(4)
     end function
+    integer(c_int) function flutas_b200_fft(plan,n,arr) bind(C,name='flutas_b200_fft')
+      import; type(c_ptr), value :: plan,arr; integer(c_int), intent(in) :: n(3)
+    end function
     integer(c_int) function flutas_b200_solver(n,arrplan,normfft,lambdaxy,a,b,c,bcz,c_or_f,p) bind(C,name='flutas_b200_solver')
       import; integer(c_int), intent(in) :: n(3); type(c_ptr), intent(in) :: arrplan(4)
       real(c_double), value :: normfft; type(c_ptr), value :: lambdaxy,a,b,c,p
@@ -226,8 +229,13 @@ module mod_fft                                ! same public names as src/fft.f90
   use mod_types
   implicit none
   private
-  public :: fftini,fftend
+  public :: fftini,fftend,fft
 contains
+  subroutine fft(plan,arr)                    ! src/fft.f90:181-193: one unnormalised in-place transform, FFTW element order
+    type(C_PTR), intent(in   )                           :: plan
+    real(rp)   , intent(inout), dimension(:,:,:), target :: arr
+    call b200_check(flutas_b200_fft(plan,int(shape(arr),c_int),c_loc(arr)),'fft')
+  end subroutine fft
   subroutine fftini(n_x,n_y,bcxy,c_or_f,arrplan,normfft)
     integer         , intent(in ), dimension(3)     :: n_x,n_y
     character(len=1), intent(in ), dimension(0:1,2) :: bcxy

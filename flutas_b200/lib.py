@@ -37,6 +37,10 @@ def load():
     L.flutas_b200_fftini.argtypes = [ip, ip, cc, cc, C.POINTER(vp), _dp]
     L.flutas_b200_fftend.argtypes = [C.POINTER(vp)]
     L.flutas_b200_solver.argtypes = [ip, C.POINTER(vp), cd, vp, vp, vp, vp, cc, cc, vp]
+    L.flutas_b200_fft.argtypes = [vp, ip, vp]
+    L.flutas_b200_plan_r2r.argtypes = [ci, ci, ip, ip, ci, C.POINTER(vp)]
+    L.flutas_b200_plan_dims.argtypes = [vp, ip]
+    L.flutas_b200_destroy_plan.argtypes = [vp]
     L.flutas_b200_solver_invalidate.argtypes = [C.POINTER(vp)]
     L.flutas_b200_debug_thomas_mode.argtypes = [C.POINTER(vp), ci]
     L.flutas_b200_debug_generic_fft.argtypes = [ci]
@@ -79,6 +83,7 @@ EXPORTS = [
     "flutas_b200_version", "flutas_b200_last_error", "flutas_b200_init", "flutas_b200_set_stream",
     "flutas_b200_alloc", "flutas_b200_alloc_managed", "flutas_b200_free", "flutas_b200_memcpy", "flutas_b200_synchronize",
     "flutas_b200_fftini", "flutas_b200_fftend", "flutas_b200_solver", "flutas_b200_solver_invalidate",
+    "flutas_b200_fft", "flutas_b200_plan_r2r", "flutas_b200_plan_dims", "flutas_b200_destroy_plan",
     "flutas_b200_fillps", "flutas_b200_updt_rhs_b", "flutas_b200_correc", "flutas_b200_chkdiv",
     "flutas_b200_launch_count", "flutas_b200_profile_enable", "flutas_b200_profile_stage_count",
     "flutas_b200_profile_stage_name", "flutas_b200_profile_read", "flutas_b200_set_alltoall",

@@ -62,6 +62,27 @@ int flutas_b200_fftini(const int n_x[3], const int n_y[3], const char bcxy[4], c
 /* fftend, src/fft.f90:159-179. */
 int flutas_b200_fftend(void *arrplan[4]);
 
+/* fft(plan,arr), src/fft.f90:181-193 (dfftw_execute_r2r(plan,arr,arr), :188-190): one batched, unnormalised,
+ * in-place r2r transform of a dense pencil array, input and output in FFTW's element order (half-complex
+ * r0..r_{n/2}, i_{n/2-1}..i_1 for R2HC; k = 0..n-1 for the DCT/DST kinds).  plan = one of the four arrplan
+ * handles (its direction and axis are the handle's) or a stand-alone plan; n = extents of arr (the x pencil
+ * for x plans, the y pencil for y plans).  flutas_b200_solver does NOT go through this call -- its stages
+ * hand the spectrum over in the kernels' own slot order -- it serves hosts that keep the reference's
+ * solver_cpu.f90 (its transposes and Thomas loops) and the per-kind parity tests. */
+int flutas_b200_fft(void *plan, const int n[3], double *arr);
+
+/* Stand-alone plan with the arguments fftini hands to fftw_plan_guru_r2r (src/fft.f90:75-86,113-124,
+ * interface src/fftw.f90:15-36): rank-1 transform (n, is), two howmany dimensions (hm_n, hm_is), in
+ * place (os = is).  Served layouts: x (is = 1, hm_is = (n, n*hm_n[0])) and y (is = hm_n[0], hm_is =
+ * (1, hm_n[0]*n)).  kind = FFTW's integer code (src/fftw.f90:41-61): R2HC 0, HC2R 1, REDFT01 4, REDFT10 5,
+ * REDFT11 6, RODFT01 8, RODFT10 9, RODFT11 10.  flutas_b200_plan_dims returns the array extents the plan
+ * was made for; flutas_b200_destroy_plan is dfftw_destroy_plan (src/fft.f90:165-175).
+ * libflutas_b200_fftw.so (csrc/fftw_seam.cpp) exports the reference's own FFTW symbols on top of these
+ * three calls, so that fft.f90 / fftw.f90 link unchanged without FFTW. */
+int flutas_b200_plan_r2r(int n, int is, const int hm_n[2], const int hm_is[2], int kind, void **plan);
+int flutas_b200_plan_dims(void *plan, int n[3]);
+int flutas_b200_destroy_plan(void *plan);
+
 /* solver_cpu / solver_gpu, src/solver_cpu.f90:20-115, src/solver_gpu.f90:31-472.
  * n = local x-pencil interior size; lambdaxy, a, b, c as returned by initsolver (CPU, i.e. FFTW
  * half-complex eigenvalue order, src/initsolver.f90:87-93,136-139); bcz(0:1); c_or_f(3) (must be 'c').

@@ -74,3 +74,23 @@ def test_header_is_plain_c_and_the_shim_binds_every_compute_entry_point():
         assert "subroutine " + proc in shim, proc                            # the reference's argument lists
     assert needed <= bound, needed - bound
     assert bound <= set(_declared_symbols()), bound - set(_declared_symbols())
+
+
+def test_fftw_seam_library_exports_the_references_fftw_symbols():
+    """src/fftw.f90:15-36 binds fftw_plan_guru_r2r; src/fft.f90:53-57,165-175,188-190 call the legacy dfftw_* entry points
+    (compiler-mangled with a trailing underscore).  The seam library must load without a GPU and carry all of them."""
+    import ctypes as C
+    from flutas_b200 import build as b
+    lib.load()
+    assert os.path.exists(b.SEAM_SO)
+    S = C.CDLL(b.SEAM_SO)
+    for name in ("fftw_plan_guru_r2r", "dfftw_execute_r2r_", "dfftw_destroy_plan_", "dfftw_init_threads_",
+                 "dfftw_plan_with_nthreads_", "dfftw_cleanup_threads_", "dfftw_execute_r2r", "dfftw_destroy_plan"):
+        assert hasattr(S, name), name
+    ierr = C.c_int(0)
+    S.dfftw_init_threads_(C.byref(ierr))
+    assert ierr.value != 0                       # FFTW: non-zero = success
+    # the main library must NOT carry FFTW's names (it would shadow a real FFTW in the host program)
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", b.SO], capture_output=True, text=True).stdout
+    assert "fftw" not in syms
