@@ -71,6 +71,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef FB_Y8_DEFAULT
 #define FB_Y8_DEFAULT 1
 #endif
+#ifndef FB_X8_DEFAULT
+#define FB_X8_DEFAULT 0
+#endif
 #ifndef FB_STREAM_Y
 #define FB_STREAM_Y 1
 #endif
@@ -107,19 +110,21 @@ __device__ __forceinline__ void reg_stage_tw(cpx* sm, const RegPlan& P, int tid,
   const cpx* s_wQ = RegTw<S, MK>::QSM ? (s_wN + RegTw<S, MK>::nN) : P.wQ;                      \
   const cpx* tw[RF_MAXPASS] = {nullptr, s_tw1, s_tw2};
 
-template <int N, bool MK>
+template <int N, bool MK, int RR = 16>
 constexpr size_t xfft_reg_smem() {
   constexpr int M = N / 2;
-  return (size_t)RegTw<RegSched<M>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M>::T) * (M + M / 16) * sizeof(double2);
+  return (size_t)RegTw<RegSched<M, RR>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M, RR>::T) * (M + M / 16) * sizeof(double2);
 }
 
 // KC: 0 = periodic (R2HC / HC2R), 1 = Makhoul (NN / DD), 2 = types IV (ND / DN)
-template <int N, bool FWD, int KC>
-__global__ void __launch_bounds__(256, 2)
+// RR = 8 (N = 1024 only, A/B variant FLUTAS_B200_X8): 64 threads = two warps per line at 8 values each, <= 64 registers,
+// four 256-thread blocks = 32 warps per SM instead of 16.
+template <int N, bool FWD, int KC, int RR = 16>
+__global__ void __launch_bounds__(256, RR == 8 ? 4 : 2)
 xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* __restrict__ dst, LineGeom gd, double scale) {
   constexpr bool MK = (KC == 1), IV = (KC == 2);
   constexpr int M = N / 2;
-  using S = RegSched<M>;
+  using S = RegSched<M, RR>;
   constexpr int T = S::T, R = S::R;
   constexpr bool WARP = (T <= 32);
   constexpr int GT = WARP ? 32 : 256;                 // threads that synchronise with each other
@@ -460,13 +465,13 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
 }
 
 
-template <int N, bool FWD, int KC>
+template <int N, bool FWD, int KC, int RR = 16>
 inline cudaError_t reg_launch_x1(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                                  int nsm, cudaStream_t st) {
-  constexpr int M = N / 2, T = RegSched<M>::T;
+  constexpr int M = N / 2, T = RegSched<M, RR>::T;
   constexpr int LPB = 256 / T;                         // lines per block per iteration
-  const size_t smem = xfft_reg_smem<N, KC == 1>();
-  auto kern = xfft_reg_kernel<N, FWD, KC>;
+  const size_t smem = xfft_reg_smem<N, KC == 1, RR>();
+  auto kern = xfft_reg_kernel<N, FWD, KC, RR>;
   static int per_sm = 0;                               // configured once per process (one device per process)
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -486,6 +491,14 @@ inline cudaError_t reg_launch_x1(const RegPlan& P, const double* src, LineGeom g
 template <int N, bool FWD>
 inline cudaError_t reg_launch_x(const RegPlan& P, const double* src, LineGeom gs, double* dst, LineGeom gd, double scale,
                                 int nsm, cudaStream_t st) {
+  if constexpr (N == 1024) {                            // 8 values per thread, 32 warps per SM: FLUTAS_B200_X8=1
+    static const int x8 = [] { const char* e = getenv("FLUTAS_B200_X8"); return e ? atoi(e) : FB_X8_DEFAULT; }();
+    if (x8 && P.tw8[1]) {
+      if (kind_is_iv(P.kind)) return reg_launch_x1<N, FWD, 2, 8>(P, src, gs, dst, gd, scale, nsm, st);
+      return (P.kind == KIND_PP) ? reg_launch_x1<N, FWD, 0, 8>(P, src, gs, dst, gd, scale, nsm, st)
+                                 : reg_launch_x1<N, FWD, 1, 8>(P, src, gs, dst, gd, scale, nsm, st);
+    }
+  }
   if (kind_is_iv(P.kind)) return reg_launch_x1<N, FWD, 2>(P, src, gs, dst, gd, scale, nsm, st);
   return (P.kind == KIND_PP) ? reg_launch_x1<N, FWD, 0>(P, src, gs, dst, gd, scale, nsm, st)
                              : reg_launch_x1<N, FWD, 1>(P, src, gs, dst, gd, scale, nsm, st);

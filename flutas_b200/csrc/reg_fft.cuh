@@ -38,9 +38,12 @@ struct RegPlan {
 };
 
 // compile-time schedule for a complex length M (power of two, 16 <= M <= 2048): RR complex values per thread,
-// T = M / RR threads per line, one first pass of radix R0 <= RR followed by radix-RR passes.
-//   RR = 16 (default): M = 16: {16}; M <= 256: {M/16, 16}; else {M/256, 16, 16}
+// T = M / RR threads per line, radix-RR passes and one pass of radix R0 <= RR.
+//   RR = 16 (default): M = 16: {16}; M <= 256: {16, M/16}; else {16, 16, M/256}   (FB_SCHED_SMALL_FIRST: small radix first)
 //   RR = 8  (twice the threads at half the registers; used where it has the same number of passes: M = 512 = 8 x 8 x 8)
+#ifndef FB_SCHED_SMALL_FIRST
+#define FB_SCHED_SMALL_FIRST 0
+#endif
 template <int M_, int RR = 16>
 struct RegSched {
   static constexpr int M = M_;
@@ -49,8 +52,16 @@ struct RegSched {
   static constexpr int NP = (M == RR) ? 1 : (M <= RR * RR) ? 2 : 3;
   static constexpr int R0 = (NP == 1) ? RR : (NP == 2) ? M / RR : M / (RR * RR);
   static_assert(R0 >= 1 && R0 <= RR && T * R == M, "schedule not representable");
+#if FB_SCHED_SMALL_FIRST
   static FB_CX int radix(int q) { return q == 0 ? R0 : RR; }
   static FB_CX int ns(int q) { return q == 0 ? 1 : (q == 1 ? R0 : R0 * RR); }
+#else
+  // the small radix goes LAST: its results stay in registers, so every exchange store has the radix-RR stride the
+  // buffer padding is made for (a radix-2 first pass stores at a stride of two slots: two-way bank conflicts), and the
+  // last pass has fewer twiddle products than a radix-RR one ((R0-1)/R0 instead of (RR-1)/RR per element)
+  static FB_CX int radix(int q) { return q == NP - 1 ? R0 : RR; }
+  static FB_CX int ns(int q) { return q == 0 ? 1 : (q == 1 ? RR : RR * RR); }
+#endif
 };
 
 FB_CX bool reg_fft_supported(int N) {

@@ -29,7 +29,7 @@ def _rel(a, b):
 
 # register kernels: powers of two 32..2048; shared-memory radix-2/3/5 kernels: the rest
 @pytest.mark.parametrize("bcx,bcy", [("PP", "NN"), ("NN", "PP"), ("DD", "ND"), ("ND", "DN"), ("DN", "DD")])
-@pytest.mark.parametrize("n1,n2,n3", [(64, 32, 5), (12, 72, 3), (256, 1024, 2), (2048, 20, 2), (30, 512, 3)])
+@pytest.mark.parametrize("n1,n2,n3", [(64, 32, 5), (12, 72, 3), (256, 1024, 2), (2048, 20, 2), (30, 512, 3), (1024, 16, 3)])
 def test_arrplan_handles_match_fftw_definitions(api, bcx, bcy, n1, n2, n3):
     rng = np.random.default_rng(n1 * 7 + n2)
     pl, _ = api.fftini((n1, n2, n3), (n1, n2, n3), (bcx, bcy))

@@ -16,6 +16,9 @@ VARIANTS = {
     "z-double-buffer": {"FLUTAS_B200_THOMAS_UNI": "0", "FLUTAS_B200_THOMAS_NBUF": "2"},
     "y-16-values": {"FLUTAS_B200_Y8": "0"},
     "y-wide": {"FLUTAS_B200_YWIDE": "1"},
+    "y-8-values-wide": {"FLUTAS_B200_Y8WIDE": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
+    "x-8-values": {"FLUTAS_B200_X8": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
+    "x-16-values": {"FLUTAS_B200_X8": "0", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "correc-scalar": {"FLUTAS_B200_CORREC_VEC": "0", "_subset": "stencils"},
 }
 
@@ -26,8 +29,9 @@ def test_variant_passes_parity_subset(name):
     env = dict(os.environ)
     var = dict(VARIANTS[name])
     subset = var.pop("_subset", SUBSET)
+    target = var.pop("_file", "test_gpu_parity.py")
     env.update(var)
-    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, target), "-m", "gpu", "-x", "-q",
                           "-k", subset], env=env, capture_output=True, text=True, timeout=900)
     tail = out.stdout[-1500:] + out.stderr[-500:]
     assert out.returncode == 0 and " passed" in out.stdout, tail
