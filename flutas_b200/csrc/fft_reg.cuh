@@ -35,21 +35,41 @@ struct RegTw {
   static constexpr int total = n1 + n2 + nN + nQ + ((n1 + n2 + nQ) & 1);     // cpx entries (16 bytes each)
 };
 
-// exchange buffer of one x line: M slots of (re,im), one pad slot per 16 (scattered 16-slot strides -> all banks)
-struct XLineBuf {
+// exchange buffer of one x line: M slots of (re,im); XOR-swizzled (reg_fft.cuh: rf_swz) or one pad slot per 16.
+// Measured on B200 (profiles/r02_swz_ab.log): the swizzle wins where a line spans two warps (N = 2048: x fwd 2.41 -> 2.31,
+// x inv 3.10 -> 2.87 ms) and loses in the warp-per-line kernels (N = 1024: 3.28 -> 3.38 ms; their 128-register budget has
+// no room for the extra address registers, and keeping the compiler from hoisting them out of the line loop only gets back
+// to parity) -> chosen per length.  FB_XBUF_PAD=1 / FB_XBUF_SWZ=1 force one (A/B builds).
+#ifndef FB_XBUF_PAD
+#define FB_XBUF_PAD 0
+#endif
+#ifndef FB_XBUF_SWZ
+#define FB_XBUF_SWZ 0
+#endif
+template <bool XOR_>
+struct XLineBufT {
+  static constexpr bool XOR = XOR_;
   double2* b;
-  __device__ __forceinline__ int base(int pos) const { return rf_pad(pos); }
-  __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[bs + coff] = make_double2(r, i); }
+  static FB_CX int off(int c) { return XOR ? rf_swzoff(c) : rf_padoff(c); }
+  static FB_CX int slot(int m) { return XOR ? rf_swz(m) : rf_pad(m); }
+  static FB_CX int length(int M) { return XOR ? M : M + M / 16; }
+  static FB_CX int at(int bs, int coff) { return XOR ? (bs ^ coff) : (bs + coff); }
+  __device__ __forceinline__ int base(int pos) const { return slot(pos); }
+  __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[at(bs, coff)] = make_double2(r, i); }
   __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
-    const double2 v = b[bs + coff];
+    const double2 v = b[at(bs, coff)];
     r = v.x; i = v.y;
   }
 };
+template <int N>
+using XLineBuf = XLineBufT<(FB_XBUF_SWZ || N >= 2048) && !FB_XBUF_PAD>;
 
 // exchange buffer of a y tile: [slot][lane]
 template <int TB>
 struct YTileBuf {
+  static constexpr bool XOR = false;
   double2* b;   // already offset by the lane
+  static FB_CX int off(int c) { return rf_padoff(c); }
   __device__ __forceinline__ int base(int pos) const { return rf_pad(pos) * TB; }
   __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[bs + coff * TB] = make_double2(r, i); }
   __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
@@ -113,7 +133,7 @@ __device__ __forceinline__ void reg_stage_tw(cpx* sm, const RegPlan& P, int tid,
 template <int N, bool MK, int RR = 16>
 constexpr size_t xfft_reg_smem() {
   constexpr int M = N / 2;
-  return (size_t)RegTw<RegSched<M, RR>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M, RR>::T) * (M + M / 16) * sizeof(double2);
+  return (size_t)RegTw<RegSched<M, RR>, MK>::total * sizeof(cpx) + (size_t)(256 / RegSched<M, RR>::T) * XLineBuf<N>::length(M) * sizeof(double2);
 }
 
 // KC: 0 = periodic (R2HC / HC2R), 1 = Makhoul (NN / DD), 2 = types IV (ND / DN)
@@ -129,7 +149,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   constexpr bool WARP = (T <= 32);
   constexpr int GT = WARP ? 32 : 256;                 // threads that synchronise with each other
   constexpr int LG = GT / T;                          // lines per group
-  constexpr int BUFL = M + M / 16;
+  constexpr int BUFL = XLineBuf<N>::length(M);
   extern __shared__ double2 smem2[];
   double2* bufs = smem2 + RegTw<S, MK>::total;
   const int tid = threadIdx.x;
@@ -138,7 +158,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   FB_REG_TABLES(S, MK, smem2, P)
   const int gi = WARP ? (tid >> 5) : 0, tg = tid % GT;
   const int lw = tg / T, j = tg % T;
-  const XLineBuf xb{bufs + (size_t)(gi * LG + lw) * BUFL};
+  const XLineBuf<N> xb{bufs + (size_t)(gi * LG + lw) * BUFL};
   // a line of N = 2048 needs T = 64 threads = two whole warps: they meet at their own named barrier, so the four lines of
   // a block never wait for each other (B200, 2048 x 2048 x 128: x fwd 2.92 -> 2.48 ms, x inv 3.35 -> 3.13 ms against __syncthreads)
   auto sync = [lw] {
@@ -172,7 +192,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   auto slot_sign = [&](int e, double& sgn) {                   // slot (doubles) of physical element e in the buffer
     int m, part;
     elem_to_slot(kind, N, e, m, part, sgn);
-    return 2 * (m + (m >> 4)) + part;
+    return 2 * XLineBuf<N>::slot(m) + part;
   };
   double* lbuf = reinterpret_cast<double*>(xb.b);
   for (long g = WARP ? (long)blockIdx.x * 8 + gi : (long)blockIdx.x; g < ngroups; g += gstride) {

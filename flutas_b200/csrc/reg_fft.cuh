@@ -142,6 +142,15 @@ template <int R, int SIGN> FB_HD void rbfly(double* re, double* im) {
 //   void ld(base, coff, re, im)
 FB_CX int rf_pad(int pos) { return pos + (pos >> 4); }
 FB_CX int rf_padoff(int c) { return c >= 0 ? c + (c >> 4) : -((-c) + ((-c) >> 4)); }
+// The same contract with an XOR swizzle instead of pad slots: slot pos lives at pos ^ ((pos >> 4) & 7).  A warp's 32
+// consecutive 16-byte slots then stay inside one aligned 512-byte window (four shared-memory wavefronts; with a pad slot
+// in the middle they straddle five), and the 16-slot strides still spread over all eight 16-byte bank groups.  In every
+// access of the passes base and offset occupy disjoint bits up to the swizzle field (the no-carry cases above), so
+// swz(base + c) = swz(base) ^ swz(|c|): one LOP3 with an immediate per access.  An exchange buffer XB provides
+//   static int off(c)            : the offset code of a compile-time c (rf_padoff(c) or rf_swz(|c|))
+// and combines base and offset itself (+ or ^).
+FB_CX int rf_swz(int pos) { return pos ^ ((pos >> 4) & 7); }
+FB_CX int rf_swzoff(int c) { return rf_swz(c >= 0 ? c : -c); }
 
 // One Stockham pass of the T threads owning a line.  Thread j holds element j + T*u in (re[u], im[u]).
 // Not the last pass: results go to the exchange buffer (scattered), the caller synchronises and gathers.
@@ -184,11 +193,12 @@ FB_HD void reg_pass(double* re, double* im, int j, const cpx* tw, const XB& xb) 
       for (int t = 0; t < r; ++t) { re[b + t * NB] = vr[t]; im[b + t * NB] = vi[t]; }
     } else {
       const int base = BCONST ? xb.base(j * r) : xb.base((jb - k) * r + k);     // (jb / Ns) * Ns * r + k
-      const int boff = BCONST ? rf_padoff(T * r * b) : 0;
+      static_assert(NB == 1 || last || !XB::XOR, "swizzled buffers: non-final passes have one butterfly per thread");
+      const int boff = BCONST ? XB::off(T * r * b) : 0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 0; t < r; ++t) xb.st(base, boff + rf_padoff(t * Ns), vr[t], vi[t]);
+      for (int t = 0; t < r; ++t) xb.st(base, boff + XB::off(t * Ns), vr[t], vi[t]);
     }
   }
 }
@@ -200,7 +210,7 @@ FB_HD void reg_gather(double* re, double* im, int j, const XB& xb) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int u = 0; u < S::R; ++u) xb.ld(base, rf_padoff(S::T * u), re[u], im[u]);
+  for (int u = 0; u < S::R; ++u) xb.ld(base, XB::off(S::T * u), re[u], im[u]);
 }
 
 template <class S, class XB>
@@ -209,7 +219,7 @@ FB_HD void reg_scatter_modes(const double* re, const double* im, int j, const XB
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int u = 0; u < S::R; ++u) xb.st(base, rf_padoff(S::T * u), re[u], im[u]);
+  for (int u = 0; u < S::R; ++u) xb.st(base, XB::off(S::T * u), re[u], im[u]);
 }
 
 // partner mode of k = j + T u in the exchange buffer: M - k (k > 0), 0 (k = 0).  T >= 16: M - j - T u is a base
@@ -221,9 +231,14 @@ struct RegPartner {
   int bm, b0;
   FB_HD RegPartner(int j, const XB& xb) : bm(CONSTOFF ? xb.base(M - j) : 0), b0(CONSTOFF ? (j == 0 ? xb.base(0) : xb.base(M - j)) : 0) {}
   FB_HD void ld(const XB& xb, int j, int u, double& r, double& i) const {
-    if (CONSTOFF) {
+    if (CONSTOFF && XB::XOR) {
+      // j > 0: M - j - T u = (T (R-1) + T - j) ^ (T u) (the u field of the base is all ones: subtracting is XOR);
+      // j = 0: T ((R - u) mod R) is not an XOR of T u -> its own compile-time address, selected per lane
+      const int a0 = XB::off(S::T * ((S::R - u) % S::R)), a1 = bm ^ XB::off(S::T * u);
+      xb.ld(j == 0 ? a0 : a1, 0, r, i);
+    } else if (CONSTOFF) {
       if (u == 0) xb.ld(b0, 0, r, i);
-      else xb.ld(bm, rf_padoff(-S::T * u), r, i);
+      else xb.ld(bm, XB::off(-S::T * u), r, i);
     } else {
       const int k = j + S::T * u;
       xb.ld(xb.base((M - k) & (M - 1)), 0, r, i);

@@ -1,3 +1,4 @@
+#include <cstdio>
 // CPU emulation of the tile-FFT core (flutas_b200/csrc/tile_fft.cuh) for the "not gpu" tests.
 // TEST INFRASTRUCTURE: runs the kernels' per-thread phase functions in a serial loop over
 // (lane, worker) with the phase boundaries where the CUDA kernels have __syncthreads().  It lets
@@ -339,20 +340,24 @@ extern "C" int emul_thomas_reg_pick(int nz, int periodic) {
 // ---------------------------------------------------------------------------------------------
 // register-resident transforms (flutas_b200/csrc/reg_fft.cuh): the per-thread functions the kernels call, run
 // serially over the T threads of one line with the phase boundaries where the kernels synchronise.
-struct EmulXB {                          // exchange buffer of one line, padded like the kernels' (they add lanes)
+template <bool SWZ>
+struct EmulXB {                          // exchange buffer of one line: padded like the y tiles' (they add lanes) or
+  static constexpr bool XOR = SWZ;       // XOR-swizzled like the x lines'
   double* re; double* im;
-  int base(int pos) const { return rf_pad(pos); }
-  void st(int b, int coff, double r, double i) const { re[b + coff] = r; im[b + coff] = i; }
-  void ld(int b, int coff, double& r, double& i) const { r = re[b + coff]; i = im[b + coff]; }
+  static constexpr int off(int c) { return SWZ ? rf_swzoff(c) : rf_padoff(c); }
+  int base(int pos) const { return SWZ ? rf_swz(pos) : rf_pad(pos); }
+  static int at(int b, int coff) { return SWZ ? (b ^ coff) : (b + coff); }
+  void st(int b, int coff, double r, double i) const { re[at(b, coff)] = r; im[at(b, coff)] = i; }
+  void ld(int b, int coff, double& r, double& i) const { r = re[at(b, coff)]; i = im[at(b, coff)]; }
 };
 
-template <int M, int RR = 16>
-static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
+template <int M, int RR = 16, bool SWZ = false>
+static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
   using S = RegSched<M, RR>;
   constexpr int T = S::T, R = S::R, N = 2 * M;
   // poisoned padded buffer: a wrong padded address reads NaN (or clobbers a slot that is read later)
   std::vector<double> bre(M + M / 16 + 2, std::nan("")), bim(M + M / 16 + 2, std::nan(""));
-  EmulXB xb{bre.data(), bim.data()};
+  EmulXB<SWZ> xb{bre.data(), bim.data()};
   std::vector<double> re((size_t)T * R), im((size_t)T * R);
   auto RE = [&](int j) { return re.data() + (size_t)j * R; };
   auto IM = [&](int j) { return im.data() + (size_t)j * R; };
@@ -422,6 +427,18 @@ static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, doub
         reg_phys_slots(hp.kind, N, j + T * u, e0, e1, s0, s1);
         out[e0] = s0 * scale * RE(j)[u]; out[e1] = s1 * scale * IM(j)[u];
       }
+  }
+}
+
+// both exchange-buffer addressings (padded: y tiles; XOR-swizzled: x lines) must give the same bits
+template <int M, int RR = 16>
+static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
+  reg_line_emul1<M, RR, true>(hp, fwd, in, out, scale);
+  std::vector<double> alt((size_t)2 * M);
+  reg_line_emul1<M, RR, false>(hp, fwd, in, alt.data(), scale);
+  if (std::memcmp(alt.data(), out, sizeof(double) * 2 * M) != 0) {
+    std::fprintf(stderr, "exchange-buffer addressings disagree: M=%d RR=%d kind=%d fwd=%d\n", M, RR, hp.kind, fwd);
+    std::abort();
   }
 }
 
