@@ -40,6 +40,9 @@ struct RegTw {
 // x inv 3.10 -> 2.87 ms) and loses in the warp-per-line kernels (N = 1024: 3.28 -> 3.38 ms; their 128-register budget has
 // no room for the extra address registers, and keeping the compiler from hoisting them out of the line loop only gets back
 // to parity) -> chosen per length.  FB_XBUF_PAD=1 / FB_XBUF_SWZ=1 force one (A/B builds).
+#ifndef FB_PAIR_SPLIT
+#define FB_PAIR_SPLIT 1
+#endif
 #ifndef FB_XBUF_PAD
 #define FB_XBUF_PAD 0
 #endif
@@ -54,6 +57,8 @@ struct XLineBufT {
   static FB_CX int slot(int m) { return XOR ? rf_swz(m) : rf_pad(m); }
   static FB_CX int length(int M) { return XOR ? M : M + M / 16; }
   static FB_CX int at(int bs, int coff) { return XOR ? (bs ^ coff) : (bs + coff); }
+  static FB_CX int offsub(int a, int b) { return XOR ? (rf_swz(a) ^ rf_swz(b)) : (rf_padoff(a) - rf_padoff(b)); }   // offset code of +a - b
+  __device__ __forceinline__ int addr(int bs, int coff) const { return at(bs, coff); }                               // ld/st(addr, 0)
   __device__ __forceinline__ int base(int pos) const { return slot(pos); }
   __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[at(bs, coff)] = make_double2(r, i); }
   __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
@@ -70,6 +75,8 @@ struct YTileBuf {
   static constexpr bool XOR = false;
   double2* b;   // already offset by the lane
   static FB_CX int off(int c) { return rf_padoff(c); }
+  static FB_CX int offsub(int a, int b) { return rf_padoff(a) - rf_padoff(b); }
+  __device__ __forceinline__ int addr(int bs, int coff) const { return bs + coff * TB; }
   __device__ __forceinline__ int base(int pos) const { return rf_pad(pos) * TB; }
   __device__ __forceinline__ void st(int bs, int coff, double r, double i) const { b[bs + coff * TB] = make_double2(r, i); }
   __device__ __forceinline__ void ld(int bs, int coff, double& r, double& i) const {
@@ -147,6 +154,7 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   using S = RegSched<M, RR>;
   constexpr int T = S::T, R = S::R;
   constexpr bool WARP = (T <= 32);
+  constexpr bool PAIR = FWD && !IV && FB_PAIR_SPLIT && reg_has_pair_pass<S>();
   constexpr int GT = WARP ? 32 : 256;                 // threads that synchronise with each other
   constexpr int LG = GT / T;                          // lines per group
   constexpr int BUFL = XLineBuf<N>::length(M);
@@ -246,18 +254,27 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
         }
       }
       if (IV) reg_iv_pre<S, false>(re, im, j, P.wQ);
-      reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
-      if (IV) {
-        reg_iv_post<S, true>(re, im, j, s_wN, dn);
-      } else {
-        reg_scatter_modes<S>(re, im, j, xb);
+      if constexpr (PAIR) {                             // last pass on symmetric butterfly pairs: split in registers, stored from there
+        reg_fft_passes_head<S, -1>(re, im, j, tw, xb, sync);
         sync();
-        reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
-      }
-      if (live) {
-        double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
+        double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, lc));
+        reg_pair_pass_split<S, MK>(j, tw[S::NP - 1], s_wN, s_wQ, xb, [&](int k, double xr, double xi) {
+          if (live) st_x2(pd + k, make_double2(scale * xr, scale * xi));
+        });
+      } else {
+        reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
+        if (IV) {
+          reg_iv_post<S, true>(re, im, j, s_wN, dn);
+        } else {
+          reg_scatter_modes<S>(re, im, j, xb);
+          sync();
+          reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+        }
+        if (live) {
+          double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, line));
 #pragma unroll
-        for (int u = 0; u < R; ++u) st_x2(pd + (j + T * u), make_double2(scale * re[u], scale * im[u]));
+          for (int u = 0; u < R; ++u) st_x2(pd + (j + T * u), make_double2(scale * re[u], scale * im[u]));
+        }
       }
     } else {
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));

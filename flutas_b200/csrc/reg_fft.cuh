@@ -246,43 +246,111 @@ struct RegPartner {
   }
 };
 
+// one mode of the forward split: (Z_k, Z_{M-k}) -> the two spectral rows of mode k.  w = wN[k]; MK: q = wQ[k] (Makhoul
+// post-twiddle, NN/DD lines), wQM = wQ[M].x; k0: mode 0, whose rows are (X_0, X_M).  Same arithmetic as split_core (tile_fft.cuh).
+template <bool MK>
+FB_HD void reg_split_one(double zkr, double zki, double zjr, double zji, const cpx& w, const cpx& q, bool k0, double wQM,
+                         double& xr, double& xi) {
+  const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
+  const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
+  const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
+  xr = er + wor; xi = ei + woi;
+  if (k0) xi = zkr - zki;                              // row 1 holds X_M = Re Z_0 - Im Z_0
+  if (MK) {
+    if (k0) { xr = 2.0 * xr; xi = 2.0 * wQM * xi; }
+    else {
+      const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
+      xr = 2.0 * tr; xi = -2.0 * ti;
+    }
+  }
+}
+
 // forward split for this thread's modes k = j + T*u: (re,im)[u] <- the two spectral rows of mode k.
-// The exchange buffer holds Z (all modes of the line).  Same arithmetic as split_core (tile_fft.cuh).
-// MK: Makhoul post-twiddle (NN/DD lines); wN / wQ may point to shared memory (indexed j + T u: immediates).
+// The exchange buffer holds Z (all modes of the line).  wN / wQ may point to shared memory (indexed j + T u: immediates).
 template <class S, bool MK, class XB>
 FB_HD void reg_split(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
   constexpr int M = S::M;
   const RegPartner<S, XB> pt(j, xb);
   const cpx* wNj = wN + j;
   const cpx* wQj = wQ + j;
+  const double wQM = MK ? wQ[M].x : 0.0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int u = 0; u < S::R; ++u) {
-    const double zkr = re[u], zki = im[u];
-    double zjr, zji;
+    double zjr, zji, xr, xi;
     pt.ld(xb, j, u, zjr, zji);
-    const double er = 0.5 * (zkr + zjr), ei = 0.5 * (zki - zji);
-    const double orr = 0.5 * (zki + zji), oi = -0.5 * (zkr - zjr);
-    const cpx w = wNj[S::T * u];
-    const double wor = orr * w.x - oi * w.y, woi = orr * w.y + oi * w.x;
-    double xr = er + wor, xi = ei + woi;
     const bool k0 = (u == 0) && (j == 0);
-    if (k0) xi = zkr - zki;                            // row 1 holds X_M = Re Z_0 - Im Z_0
-    if (MK) {
-      if (k0) { xr = 2.0 * xr; xi = 2.0 * wQ[M].x * xi; }
-      else {
-        const cpx q = wQj[S::T * u];
-        const double tr = xr * q.x - xi * q.y, ti = xr * q.y + xi * q.x;
-        xr = 2.0 * tr; xi = -2.0 * ti;
-      }
-    }
+    reg_split_one<MK>(re[u], im[u], zjr, zji, wNj[S::T * u], MK ? wQj[S::T * u] : wNj[S::T * u], k0, wQM, xr, xi);
     re[u] = xr; im[u] = xi;
   }
 }
 
-// backward merge: (re,im)[u] holds this thread's spectral rows of mode k = j + T*u, the exchange buffer
-// holds all modes of the line; result: Z'_k (input of the inverse complex FFT).  Same arithmetic as merge_core.
+// ---- forward: last (small-radix) pass on SYMMETRIC butterfly pairs, split in registers -------------------------------
+// The last pass has radix r = R0 < RR and NB = RR / r butterflies per thread.  Butterfly jb (0 <= jb < Ns = M / r) turns
+// buffer positions jb + t Ns into modes jb + t Ns, and the split pairs mode k with M - k, i.e. (jb, t) with (Ns - jb, r-1-t).
+// A thread that runs butterflies jbA = j + T b and jbB = Ns - jbA (b < NB / 2) holds every pair itself: no exchange (and
+// no barrier) between the last pass and the split -- two exchanges per line instead of three.  The one self-paired slot
+// (j = 0, b = 0) runs butterflies 0 (modes t Ns pair as t <-> r - t; mode 0 is the (X_0, X_M) row) and Ns / 2 (t <-> r-1-t).
+// Modes leave through out(k, xr, xi): the spectral layout (slot k = mode k) is the one of reg_split.
+template <class S>
+FB_CX bool reg_has_pair_pass() {
+  return S::NP >= 2 && S::R0 < S::R && ((S::R / S::R0) % 2 == 0) && (S::T % 16 == 0) && !FB_SCHED_SMALL_FIRST;
+}
+
+template <class S, bool MK, class XB, class OUT>
+FB_HD void reg_pair_pass_split(int j, const cpx* tw, const cpx* wN, const cpx* wQ, const XB& xb, const OUT& out) {
+  constexpr int M = S::M, Q = S::NP - 1, r = S::radix(Q), Ns = S::ns(Q), NB = S::R / r, T = S::T;
+  static_assert(Ns * r == M && NB % 2 == 0, "pair pass needs an even number of small-radix butterflies per thread");
+  const int bA = xb.base(j), bB = xb.base(Ns - j);
+  const cpx* twA = tw + j;
+  const double wQM = MK ? wQ[M].x : 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int b = 0; b < NB / 2; ++b) {
+    const bool self = (b == 0) && (j == 0);
+    // butterfly B of lane 0 sits at compile-time positions (Ns - T b is not an XOR / no-carry offset of base(Ns))
+    const int jbB = (j == 0) ? (b == 0 ? Ns / 2 : Ns - T * b) : Ns - j - T * b;
+    double ar[r], ai[r], br[r], bi[r];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) {
+      xb.ld(bA, XB::off(T * b + t * Ns), ar[t], ai[t]);
+      const int a0 = xb.base((b == 0 ? Ns / 2 : Ns - T * b) + t * Ns), a1 = xb.addr(bB, XB::offsub(t * Ns, T * b));
+      xb.ld(j == 0 ? a0 : a1, 0, br[t], bi[t]);
+    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 1; t < r; ++t) {                      // forward twiddles w^(t k), k = jb
+      const cpx wa = twA[(t - 1) * Ns + T * b], wb = tw[(t - 1) * Ns + jbB];
+      const double xr = ar[t] * wa.x - ai[t] * wa.y, xi = ar[t] * wa.y + ai[t] * wa.x;
+      ar[t] = xr; ai[t] = xi;
+      const double yr = br[t] * wb.x - bi[t] * wb.y, yi = br[t] * wb.y + bi[t] * wb.x;
+      br[t] = yr; bi[t] = yi;
+    }
+    rbfly<r, -1>(ar, ai);
+    rbfly<r, -1>(br, bi);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) {
+      // mode kA = jbA + t Ns pairs with B's output r-1-t (self: A's output (r - t) mod r);
+      // mode kB = jbB + t Ns pairs with A's output r-1-t (self: B's output r-1-t)
+      const double pAr = self ? ar[(r - t) % r] : br[r - 1 - t], pAi = self ? ai[(r - t) % r] : bi[r - 1 - t];
+      const double pBr = self ? br[r - 1 - t] : ar[r - 1 - t], pBi = self ? bi[r - 1 - t] : ai[r - 1 - t];
+      const int kA = j + T * b + t * Ns, kB = jbB + t * Ns;
+      double xr, xi;
+      reg_split_one<MK>(ar[t], ai[t], pAr, pAi, wN[kA], MK ? wQ[kA] : wN[kA], self && t == 0, wQM, xr, xi);
+      out(kA, xr, xi);
+      reg_split_one<MK>(br[t], bi[t], pBr, pBi, wN[kB], MK ? wQ[kB] : wN[kB], false, wQM, xr, xi);
+      out(kB, xr, xi);
+    }
+  }
+}
+
 template <class S, bool MK, class XB>
 FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
   constexpr int M = S::M;
@@ -369,6 +437,18 @@ FB_HD void reg_phys_slots(int kind, int N, int m, int& e0, int& e1, double& s0, 
 }
 
 // complete forward / backward passes between gather points; SYNC is the caller's barrier functor
+// all passes but the last one; the last of them leaves its results in the exchange buffer (reg_pair_pass_split follows
+// after the caller's barrier)
+template <class S, int SIGN, class XB, class SYNC>
+FB_HD void reg_fft_passes_head(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
+  static_assert(S::NP >= 2, "no head pass");
+  reg_pass<S, 0, SIGN>(re, im, j, tw[0], xb);
+  if constexpr (S::NP > 2) {
+    sync(); reg_gather<S>(re, im, j, xb); sync();
+    reg_pass<S, 1, SIGN>(re, im, j, tw[1], xb);
+  }
+}
+
 template <class S, int SIGN, class XB, class SYNC>
 FB_HD void reg_fft_passes(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
   reg_pass<S, 0, SIGN>(re, im, j, tw[0], xb);

@@ -347,12 +347,14 @@ struct EmulXB {                          // exchange buffer of one line: padded 
   static constexpr int off(int c) { return SWZ ? rf_swzoff(c) : rf_padoff(c); }
   int base(int pos) const { return SWZ ? rf_swz(pos) : rf_pad(pos); }
   static int at(int b, int coff) { return SWZ ? (b ^ coff) : (b + coff); }
+  static constexpr int offsub(int a, int b) { return SWZ ? (rf_swz(a) ^ rf_swz(b)) : (rf_padoff(a) - rf_padoff(b)); }
+  int addr(int b, int coff) const { return at(b, coff); }
   void st(int b, int coff, double r, double i) const { re[at(b, coff)] = r; im[at(b, coff)] = i; }
   void ld(int b, int coff, double& r, double& i) const { r = re[at(b, coff)]; i = im[at(b, coff)]; }
 };
 
 template <int M, int RR = 16, bool SWZ = false>
-static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
+static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale, bool pair = false) {
   using S = RegSched<M, RR>;
   constexpr int T = S::T, R = S::R, N = 2 * M;
   // poisoned padded buffer: a wrong padded address reads NaN (or clobbers a slot that is read later)
@@ -390,6 +392,23 @@ static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, dou
       }
     const bool iv = kind_is_iv(hp.kind), dn = (hp.kind == KIND_DN);
     if (iv) for (int j = 0; j < T; ++j) reg_iv_pre<S, false>(RE(j), IM(j), j, hp.wQ.data());
+    if (!iv && pair && reg_has_pair_pass<S>()) {          // small-radix last pass on symmetric butterfly pairs + split in registers
+      if constexpr (reg_has_pair_pass<S>()) {
+        for (int j = 0; j < T; ++j) reg_pass<S, 0, -1>(RE(j), IM(j), j, tw[0], xb);
+        if constexpr (S::NP > 2) {
+          for (int j = 0; j < T; ++j) reg_gather<S>(RE(j), IM(j), j, xb);
+          for (int j = 0; j < T; ++j) reg_pass<S, 1, -1>(RE(j), IM(j), j, tw[1], xb);
+        }
+        std::vector<int> seen(M, 0);
+        auto put = [&](int k, double xr, double xi) { out[2 * k] = scale * xr; out[2 * k + 1] = scale * xi; seen[k]++; };
+        for (int j = 0; j < T; ++j) {
+          if (hp.kind == KIND_PP) reg_pair_pass_split<S, false>(j, tw[S::NP - 1], hp.wN.data(), hp.wQ.data(), xb, put);
+          else reg_pair_pass_split<S, true>(j, tw[S::NP - 1], hp.wN.data(), hp.wQ.data(), xb, put);
+        }
+        for (int k = 0; k < M; ++k) if (seen[k] != 1) std::abort();      // every mode exactly once
+      }
+      return;
+    }
     passes(std::integral_constant<int, -1>{});
     if (iv) {
       for (int j = 0; j < T; ++j) reg_iv_post<S, true>(RE(j), IM(j), j, hp.wN.data(), dn);
@@ -430,12 +449,14 @@ static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, dou
   }
 }
 
+static bool g_pair = false;           // emul_reg_pair_mode: forward lines through reg_pair_pass_split where the schedule has it
+extern "C" int emul_reg_pair_mode(int on) { g_pair = on != 0; return 0; }
 // both exchange-buffer addressings (padded: y tiles; XOR-swizzled: x lines) must give the same bits
 template <int M, int RR = 16>
 static void reg_line_emul(const HostRegPlan& hp, int fwd, const double* in, double* out, double scale) {
-  reg_line_emul1<M, RR, true>(hp, fwd, in, out, scale);
+  reg_line_emul1<M, RR, true>(hp, fwd, in, out, scale, g_pair);
   std::vector<double> alt((size_t)2 * M);
-  reg_line_emul1<M, RR, false>(hp, fwd, in, alt.data(), scale);
+  reg_line_emul1<M, RR, false>(hp, fwd, in, alt.data(), scale, g_pair);
   if (std::memcmp(alt.data(), out, sizeof(double) * 2 * M) != 0) {
     std::fprintf(stderr, "exchange-buffer addressings disagree: M=%d RR=%d kind=%d fwd=%d\n", M, RR, hp.kind, fwd);
     std::abort();

@@ -75,9 +75,13 @@ def test_tile_forward_matches_fftw_definition(emul, bc, n, tb, rot):
 
 # ---- register-resident transforms (reg_fft.cuh) --------------------------------------------------
 @pytest.mark.parametrize("bc", ["PP", "NN", "DD", "ND", "DN"])
-@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, (1024, 8)], ids=str)
+@pytest.mark.parametrize("n", [32, 64, 128, 256, 512, 1024, 2048, (1024, 8), (1024, "pair"), (2048, "pair")], ids=str)
 def test_reg_fft_matches_fftw_definition(emul, bc, n):
     transform = emul.emul_reg_line_transform
+    pair = isinstance(n, tuple) and n[1] == "pair"      # small-radix last pass on symmetric pairs, split in registers
+    emul.emul_reg_pair_mode(1 if pair else 0)
+    if pair:
+        n = n[0]
     if isinstance(n, tuple):                               # the 8-values-per-thread schedule of the N = 1024 y kernels
         n = n[0]
         emul.emul_reg_line_transform8.argtypes = emul.emul_reg_line_transform.argtypes
