@@ -43,6 +43,15 @@ struct RegTw {
 #ifndef FB_PAIR_SPLIT
 #define FB_PAIR_SPLIT 1
 #endif
+#ifndef FB_PAIR_Y
+#define FB_PAIR_Y 1
+#endif
+#ifndef FB_PAIR_YB
+#define FB_PAIR_YB 1
+#endif
+#ifndef FB_PAIR_MERGE
+#define FB_PAIR_MERGE 1
+#endif
 #ifndef FB_XBUF_PAD
 #define FB_XBUF_PAD 0
 #endif
@@ -91,12 +100,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // puts the ceiling of plain stores above st.cs for 64-byte pieces (halves of a 128-byte line merge in L2 instead of
 // leaving it evict-first), but the transform kernels are not at that ceiling: measured on B200, 512^3 and 1024^3,
 // st.cs is 0-2 % faster than plain stores on every stage -> st.cs stays the default.
-// y lines of N = 1024 with 8 values per thread (YRegShape, RR = 8): 64 registers, 28 resident warps per SM instead of 16.
-// Measured on B200 (1024^3): y fwd 4.57 -> 4.35 ms, y inv 4.55 -> 4.52 ms; 1024x1024x512 NN: 2.36 -> 2.25, 2.51 -> 2.42 ms.
-// The ncu capture of this shape (profiles/r01_ncu_full_v10_y8_keys.txt) still shows mio_throttle (5.6 per issue) and
-// barrier (4.0) on top: the block-synchronous exchange phases arrive at the shared-memory pipe in bursts.
+// y lines of N = 1024 with 8 values per thread (YRegShape, RR = 8: 64 registers, 32 warps per SM, schedule 8 x 8 x 8) were the
+// default until the 16-value schedule {16,16,2} got the pair passes (two exchanges and four barriers per tile instead of
+// three and seven): measured on B200 at 1024^3 (profiles/r02_ypair_ab.log) y fwd 4.34 -> 4.00 ms, y inv 4.48 -> 3.98 ms.
+// FLUTAS_B200_Y8=1 selects the 8-value kernels.
 #ifndef FB_Y8_DEFAULT
-#define FB_Y8_DEFAULT 1
+#define FB_Y8_DEFAULT 0
 #endif
 #ifndef FB_X8_DEFAULT
 #define FB_X8_DEFAULT 0
@@ -155,6 +164,9 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
   constexpr int T = S::T, R = S::R;
   constexpr bool WARP = (T <= 32);
   constexpr bool PAIR = FWD && !IV && FB_PAIR_SPLIT && reg_has_pair_pass<S>();
+  // backward: measured on B200 (profiles/r02_pairb_ab.log) the transposed schedule wins on DCT/DST lines (N = 1024: 2.27 -> 1.96 ms,
+  // N = 2048: 2.86 -> 2.40 ms) and loses on periodic ones (N = 1024: 3.21 -> 3.48 ms) -> Makhoul kinds only
+  constexpr bool PAIRB = !FWD && !IV && (MK || FB_PAIR_MERGE > 1) && FB_PAIR_MERGE && reg_has_pair_pass<S>();
   constexpr int GT = WARP ? 32 : 256;                 // threads that synchronise with each other
   constexpr int LG = GT / T;                          // lines per group
   constexpr int BUFL = XLineBuf<N>::length(M);
@@ -278,18 +290,27 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
       }
     } else {
       const double2* ps = reinterpret_cast<const double2*>(src + line_offset(gs, lc));
-#pragma unroll
-      for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = dn ? v.y : v.x; im[u] = dn ? v.x : v.y; }
-      if (IV) {
-        reg_iv_pre<S, true>(re, im, j, P.wQ);
+      if constexpr (PAIRB) {                            // rows of (k, M - k) merged in registers, transposed schedule
+        reg_pair_merge_pass<S, MK>(j, tw[S::NP - 1], s_wN, s_wQ, xb, [&](int k, double& xr, double& xi) {
+          const double2 v = ps[k];
+          xr = v.x; xi = v.y;
+        });
+        reg_fft_passes_T_tail<S, +1>(re, im, j, tw, xb, sync);
+        if (viabuf) sync();                            // the last pass read the buffer the permutation below rewrites
       } else {
-        reg_scatter_modes<S>(re, im, j, xb);
-        sync();
-        reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
-        sync();
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const double2 v = ps[j + T * u]; re[u] = dn ? v.y : v.x; im[u] = dn ? v.x : v.y; }
+        if (IV) {
+          reg_iv_pre<S, true>(re, im, j, P.wQ);
+        } else {
+          reg_scatter_modes<S>(re, im, j, xb);
+          sync();
+          reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
+          sync();
+        }
+        reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
+        if (IV) reg_iv_post<S, false>(re, im, j, s_wN, dn);
       }
-      reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
-      if (IV) reg_iv_post<S, false>(re, im, j, s_wN, dn);
       if (viabuf) {                                    // packed element m = slot m, then read back in natural order
         reg_scatter_modes<S>(re, im, j, xb);
         sync();
@@ -373,6 +394,7 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
   using Y = YRegShape<N, WIDE, MK, RR>;
   using MR = MkRows<N, RR>;
   constexpr int T = S::T, R = S::R, TB = Y::TB, NT = Y::NT;
+  constexpr bool PAIR = !IV && (FWD ? FB_PAIR_Y : FB_PAIR_YB) && reg_has_pair_pass<S>();
   extern __shared__ double2 smem2[];
   double2* buf = smem2 + RegTw<S, MK>::total;
   const int tid = threadIdx.x;
@@ -438,40 +460,60 @@ yfft_reg_kernel(RegPlan P, double* W, int n1, int ntile_i, long ntiles, SpecGeom
           else { re[u] = sdd * *yrow(phi, pstride, MR::off0(u)); im[u] = sdd * *yrow(phi, pstride, MR::off1(u)); }
         }
       }
-      reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
-      if (IV) {
-        reg_iv_post<S, true>(re, im, j, s_wN, dn);
-      } else {
-        reg_scatter_modes<S>(re, im, j, xb);
+      if constexpr (PAIR) {                               // last pass on symmetric butterfly pairs, split in registers
+        reg_fft_passes_head<S, -1>(re, im, j, tw, xb, sync);
         sync();
-        reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
-      }
-      if (live) {
-        double* ps = yrow(sbase, sstride, 2 * j);
+        reg_pair_pass_split<S, MK>(j, tw[S::NP - 1], s_wN, s_wQ, xb, [&](int k, double xr, double xi) {
+          if (live) {
+            double* pr = yrow(sbase, sstride, 2 * k);
+            st_y(pr, xr);
+            st_y(yrow(pr, sstride, 1), xi);
+          }
+        });
+      } else {
+        reg_fft_passes<S, -1>(re, im, j, tw, xb, sync);
+        if (IV) {
+          reg_iv_post<S, true>(re, im, j, s_wN, dn);
+        } else {
+          reg_scatter_modes<S>(re, im, j, xb);
+          sync();
+          reg_split<S, MK>(re, im, j, s_wN, s_wQ, xb);
+        }
+        if (live) {
+          double* ps = yrow(sbase, sstride, 2 * j);
 #pragma unroll
-        for (int u = 0; u < R; ++u) {
-          st_y(yrow(ps, sstride, 2 * T * u), re[u]);
-          st_y(yrow(ps, sstride, 2 * T * u + 1), im[u]);
+          for (int u = 0; u < R; ++u) {
+            st_y(yrow(ps, sstride, 2 * T * u), re[u]);
+            st_y(yrow(ps, sstride, 2 * T * u + 1), im[u]);
+          }
         }
       }
     } else {
-      {
-        const double* ps = yrow(sbase, sstride, 2 * j);
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          const double a = ld_y(yrow(ps, sstride, 2 * T * u)), b = ld_y(yrow(ps, sstride, 2 * T * u + 1));
-          re[u] = dn ? b : a; im[u] = dn ? a : b;
-        }
-      }
-      if (IV) {
-        reg_iv_pre<S, true>(re, im, j, P.wQ);
+      if constexpr (PAIR) {                               // rows of (k, M - k) merged in registers, transposed schedule
+        reg_pair_merge_pass<S, MK>(j, tw[S::NP - 1], s_wN, s_wQ, xb, [&](int k, double& xr, double& xi) {
+          const double* pr = yrow(sbase, sstride, 2 * k);
+          xr = ld_y(pr); xi = ld_y(yrow(pr, sstride, 1));
+        });
+        reg_fft_passes_T_tail<S, +1>(re, im, j, tw, xb, sync);
       } else {
-        reg_scatter_modes<S>(re, im, j, xb);
-        sync();
-        reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
-        sync();
+        {
+          const double* ps = yrow(sbase, sstride, 2 * j);
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const double a = ld_y(yrow(ps, sstride, 2 * T * u)), b = ld_y(yrow(ps, sstride, 2 * T * u + 1));
+            re[u] = dn ? b : a; im[u] = dn ? a : b;
+          }
+        }
+        if (IV) {
+          reg_iv_pre<S, true>(re, im, j, P.wQ);
+        } else {
+          reg_scatter_modes<S>(re, im, j, xb);
+          sync();
+          reg_merge<S, MK>(re, im, j, s_wN, s_wQ, xb);
+          sync();
+        }
+        reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
       }
-      reg_fft_passes<S, +1>(re, im, j, tw, xb, sync);
       if (IV) reg_iv_post<S, false>(re, im, j, s_wN, dn);
       if (live) {
         if (IV) {                                            // packed element k -> (x_{2k}, x_{N-1-2k}); DN: (x_{N-1-2k}, x_{2k})

@@ -351,6 +351,27 @@ FB_HD void reg_pair_pass_split(int j, const cpx* tw, const cpx* wN, const cpx* w
   }
 }
 
+// one mode of the backward merge: the spectral rows of modes k and M - k -> Z_k.  w = wN[k]; MK: qk = wQ[k], qj = wQ[M-k];
+// k0: mode 0 from its (X_0, X_M) rows.
+template <bool MK>
+FB_HD void reg_merge_one(double xkr, double xki, double xjr, double xji, const cpx& w, const cpx& qk, const cpx& qj, bool k0,
+                         double wQM, double& zr, double& zi) {
+  if (k0) {
+    double xm = xki;
+    if (MK) xm = 2.0 * wQM * xm;
+    zr = xkr + xm; zi = xkr - xm;
+    return;
+  }
+  if (MK) {
+    const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
+    const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
+    xkr = vkr; xki = vki; xjr = vjr; xji = vji;
+  }
+  const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
+  const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
+  zr = sr - ci; zi = si + cr;                                           // S + i conj(w) D
+}
+
 template <class S, bool MK, class XB>
 FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ, const XB& xb) {
   constexpr int M = S::M;
@@ -358,29 +379,143 @@ FB_HD void reg_merge(double* re, double* im, int j, const cpx* wN, const cpx* wQ
   const cpx* wNj = wN + j;
   const cpx* wQj = wQ + j;
   const cpx* wQm = wQ + (M - j);
+  const double wQM = MK ? wQ[M].x : 0.0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int u = 0; u < S::R; ++u) {
-    double xkr = re[u], xki = im[u], xjr, xji;
+    double xjr, xji, zr, zi;
     pt.ld(xb, j, u, xjr, xji);
-    if ((u == 0) && (j == 0)) {
-      double xm = xki;
-      if (MK) xm = 2.0 * wQ[M].x * xm;
-      re[u] = xkr + xm; im[u] = xkr - xm;
-      continue;
-    }
-    if (MK) {
-      const cpx qk = wQj[S::T * u], qj = wQm[-S::T * u];
-      const double vkr = xkr * qk.x - xki * qk.y, vki = -xki * qk.x - xkr * qk.y;
-      const double vjr = xjr * qj.x - xji * qj.y, vji = -xji * qj.x - xjr * qj.y;
-      xkr = vkr; xki = vki; xjr = vjr; xji = vji;
-    }
-    const double sr = xkr + xjr, si = xki - xji, dr = xkr - xjr, di = xki + xji;
+    const bool k0 = (u == 0) && (j == 0);
     const cpx w = wNj[S::T * u];
-    const double cr = dr * w.x + di * w.y, ci = di * w.x - dr * w.y;     // conj(w) D
-    re[u] = sr - ci; im[u] = si + cr;                                     // S + i conj(w) D
+    reg_merge_one<MK>(re[u], im[u], xjr, xji, w, MK ? wQj[S::T * u] : w, MK ? wQm[-S::T * u] : w, k0, wQM, zr, zi);
+    re[u] = zr; im[u] = zi;
   }
+}
+
+// ---- backward: the transposed schedule ------------------------------------------------------------------------------------
+// The DFT matrix is symmetric, so the forward factorisation P_last ... P_1 P_0 read backwards with every pass transposed
+// (gather <-> scatter swapped, twiddles after the butterfly) is the same transform; with conjugated twiddles, the inverse.
+// Run that way the backward line STARTS with the small-radix pass on symmetric butterfly pairs, whose inputs are exactly the
+// (k, M - k) pairs of the merge: rows come in through in(k, xr, xi), are merged in registers, and every exchange of the
+// remaining radix-RR passes has the forward one's (conflict-free) access patterns -- two exchanges per line instead of three.
+template <class S, bool MK, class XB, class IN>
+FB_HD void reg_pair_merge_pass(int j, const cpx* tw, const cpx* wN, const cpx* wQ, const XB& xb, const IN& in) {
+  constexpr int M = S::M, Q = S::NP - 1, r = S::radix(Q), Ns = S::ns(Q), NB = S::R / r, T = S::T;
+  static_assert(Ns * r == M && NB % 2 == 0, "pair pass needs an even number of small-radix butterflies per thread");
+  const int bA = xb.base(j), bB = xb.base(Ns - j);
+  const cpx* twA = tw + j;
+  const double wQM = MK ? wQ[M].x : 0.0;
+  // every row of the line first (one round of independent loads, as the exchange-based path has), then slot by slot
+  double xr_[S::R], xi_[S::R];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int b = 0; b < NB / 2; ++b) {
+    const int jbB = (j == 0) ? (b == 0 ? Ns / 2 : Ns - T * b) : Ns - j - T * b;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) {
+      in(j + T * b + t * Ns, xr_[2 * r * b + t], xi_[2 * r * b + t]);
+      in(jbB + t * Ns, xr_[2 * r * b + r + t], xi_[2 * r * b + r + t]);
+    }
+  }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int b = 0; b < NB / 2; ++b) {
+    const bool self = (b == 0) && (j == 0);
+    const int jbB = (j == 0) ? (b == 0 ? Ns / 2 : Ns - T * b) : Ns - j - T * b;
+    const double* xar = xr_ + 2 * r * b; const double* xai = xi_ + 2 * r * b;
+    const double* xbr = xar + r; const double* xbi = xai + r;
+    double ar[r], ai[r], br[r], bi[r];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) {                      // partner rows: see reg_pair_pass_split
+      const double pAr = self ? xar[(r - t) % r] : xbr[r - 1 - t], pAi = self ? xai[(r - t) % r] : xbi[r - 1 - t];
+      const double pBr = self ? xbr[r - 1 - t] : xar[r - 1 - t], pBi = self ? xbi[r - 1 - t] : xai[r - 1 - t];
+      const int kA = j + T * b + t * Ns, kB = jbB + t * Ns;
+      const cpx wa = wN[kA], wb = wN[kB];
+      reg_merge_one<MK>(xar[t], xai[t], pAr, pAi, wa, MK ? wQ[kA] : wa, MK ? wQ[M - kA] : wa, self && t == 0, wQM, ar[t], ai[t]);
+      reg_merge_one<MK>(xbr[t], xbi[t], pBr, pBi, wb, MK ? wQ[kB] : wb, MK ? wQ[M - kB] : wb, false, wQM, br[t], bi[t]);
+    }
+    rbfly<r, +1>(ar, ai);
+    rbfly<r, +1>(br, bi);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 1; t < r; ++t) {                      // conjugate twiddles w^(t k), k = jb, AFTER the butterfly
+      const cpx wa = twA[(t - 1) * Ns + T * b], wb = tw[(t - 1) * Ns + jbB];
+      const double xr = ar[t] * wa.x + ai[t] * wa.y, xi = ai[t] * wa.x - ar[t] * wa.y;
+      ar[t] = xr; ai[t] = xi;
+      const double yr = br[t] * wb.x + bi[t] * wb.y, yi = bi[t] * wb.x - br[t] * wb.y;
+      br[t] = yr; bi[t] = yi;
+    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) {
+      xb.st(bA, XB::off(T * b + t * Ns), ar[t], ai[t]);
+      const int a0 = xb.base((b == 0 ? Ns / 2 : Ns - T * b) + t * Ns), a1 = xb.addr(bB, XB::offsub(t * Ns, T * b));
+      xb.st(j == 0 ? a0 : a1, 0, br[t], bi[t]);
+    }
+  }
+}
+
+// transposed radix-RR pass Q (one butterfly per thread), first half: read where the forward pass stores
+template <class S, int Q, class XB>
+FB_HD void reg_pass_T_load(double* re, double* im, int j, const XB& xb) {
+  constexpr int r = S::radix(Q), Ns = S::ns(Q), T = S::T;
+  static_assert(S::R / r == 1, "transposed passes: radix RR only");
+  constexpr bool BCONST = (Ns == 1) && ((T * r) % 16 == 0);
+  const int k = j & (Ns - 1);
+  const int base = BCONST ? xb.base(j * r) : xb.base((j - k) * r + k);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < r; ++t) xb.ld(base, XB::off(t * Ns), re[t], im[t]);
+}
+// second half (after the caller's barrier): butterfly, twiddles, and -- unless it is pass 0, whose results are the line's
+// elements j + T t and stay in registers -- store where the forward pass gathers
+template <class S, int Q, int SIGN, class XB>
+FB_HD void reg_pass_T_finish(double* re, double* im, int j, const cpx* tw, const XB& xb) {
+  constexpr int r = S::radix(Q), Ns = S::ns(Q), T = S::T;
+  const int k = j & (Ns - 1);
+  rbfly<r, SIGN>(re, im);
+  if (Ns > 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 1; t < r; ++t) {
+      const cpx w = tw[(t - 1) * Ns + k];
+      const double wy = (SIGN < 0) ? w.y : -w.y;
+      const double xr = re[t] * w.x - im[t] * wy, xi = re[t] * wy + im[t] * w.x;
+      re[t] = xr; im[t] = xi;
+    }
+  }
+  if (Q > 0) {
+    const int bs = xb.base(j);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < r; ++t) xb.st(bs, XB::off(T * t), re[t], im[t]);
+  }
+}
+// the transposed passes after reg_pair_merge_pass; on return (re, im)[u] = element j + T u of the inverse transform
+template <class S, int SIGN, class XB, class SYNC>
+FB_HD void reg_fft_passes_T_tail(double* re, double* im, int j, const cpx* const* tw, const XB& xb, const SYNC& sync) {
+  static_assert(S::NP >= 2, "no tail pass");
+  sync();
+  if constexpr (S::NP > 2) {
+    reg_pass_T_load<S, 1>(re, im, j, xb);
+    sync();
+    reg_pass_T_finish<S, 1, SIGN>(re, im, j, tw[1], xb);
+    sync();
+  }
+  reg_pass_T_load<S, 0>(re, im, j, xb);
+  reg_pass_T_finish<S, 0, SIGN>(re, im, j, tw[0], xb);
 }
 
 // ---- types IV (ND / DN: REDFT11 / RODFT11, the same transform in both directions; tile_fft.cuh has the algebra) ----

@@ -429,7 +429,27 @@ static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, dou
         RE(j)[u] = dn ? in[2 * k + 1] : in[2 * k]; IM(j)[u] = dn ? in[2 * k] : in[2 * k + 1];
       }
     const bool iv = kind_is_iv(hp.kind);
-    if (iv) {
+    bool transposed = false;
+    if constexpr (reg_has_pair_pass<S>()) {
+      if (!iv && pair) {                                   // merge in registers + transposed schedule
+        transposed = true;
+        std::vector<int> seen(M, 0);
+        auto get = [&](int k, double& xr, double& xi) { xr = in[2 * k]; xi = in[2 * k + 1]; seen[k]++; };
+        for (int j = 0; j < T; ++j) {
+          if (hp.kind == KIND_PP) reg_pair_merge_pass<S, false>(j, tw[S::NP - 1], hp.wN.data(), hp.wQ.data(), xb, get);
+          else reg_pair_merge_pass<S, true>(j, tw[S::NP - 1], hp.wN.data(), hp.wQ.data(), xb, get);
+        }
+        for (int k = 0; k < M; ++k) if (seen[k] != 1) std::abort();
+        if constexpr (S::NP > 2) {
+          for (int j = 0; j < T; ++j) reg_pass_T_load<S, 1>(RE(j), IM(j), j, xb);
+          for (int j = 0; j < T; ++j) reg_pass_T_finish<S, 1, +1>(RE(j), IM(j), j, tw[1], xb);
+        }
+        for (int j = 0; j < T; ++j) reg_pass_T_load<S, 0>(RE(j), IM(j), j, xb);
+        for (int j = 0; j < T; ++j) reg_pass_T_finish<S, 0, +1>(RE(j), IM(j), j, tw[0], xb);
+      }
+    }
+    if (transposed) {
+    } else if (iv) {
       for (int j = 0; j < T; ++j) reg_iv_pre<S, true>(RE(j), IM(j), j, hp.wQ.data());
     } else {
       for (int j = 0; j < T; ++j) reg_scatter_modes<S>(RE(j), IM(j), j, xb);
@@ -438,7 +458,7 @@ static void reg_line_emul1(const HostRegPlan& hp, int fwd, const double* in, dou
         else reg_merge<S, true>(RE(j), IM(j), j, hp.wN.data(), hp.wQ.data(), xb);
       }
     }
-    passes(std::integral_constant<int, +1>{});
+    if (!transposed) passes(std::integral_constant<int, +1>{});
     if (iv) for (int j = 0; j < T; ++j) reg_iv_post<S, false>(RE(j), IM(j), j, hp.wN.data(), hp.kind == KIND_DN);
     for (int j = 0; j < T; ++j)
       for (int u = 0; u < R; ++u) {

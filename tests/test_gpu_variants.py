@@ -14,9 +14,9 @@ VARIANTS = {
     "z-general-tma": {"FLUTAS_B200_THOMAS_UNI": "0", "FLUTAS_B200_THOMAS_TMA_GEN": "1"},
     "z-uniform-cpasync": {"FLUTAS_B200_THOMAS_TMA": "0"},
     "z-double-buffer": {"FLUTAS_B200_THOMAS_UNI": "0", "FLUTAS_B200_THOMAS_NBUF": "2"},
-    "y-16-values": {"FLUTAS_B200_Y8": "0"},
+    "y-8-values": {"FLUTAS_B200_Y8": "1"},
     "y-wide": {"FLUTAS_B200_YWIDE": "1"},
-    "y-8-values-wide": {"FLUTAS_B200_Y8WIDE": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
+    "y-8-values-wide": {"FLUTAS_B200_Y8": "1", "FLUTAS_B200_Y8WIDE": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "x-8-values": {"FLUTAS_B200_X8": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "x-16-values": {"FLUTAS_B200_X8": "0", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "correc-scalar": {"FLUTAS_B200_CORREC_VEC": "0", "_subset": "stencils"},
