@@ -40,6 +40,11 @@ struct RegTw {
 // x inv 3.10 -> 2.87 ms) and loses in the warp-per-line kernels (N = 1024: 3.28 -> 3.38 ms; their 128-register budget has
 // no room for the extra address registers, and keeping the compiler from hoisting them out of the line loop only gets back
 // to parity) -> chosen per length.  FB_XBUF_PAD=1 / FB_XBUF_SWZ=1 force one (A/B builds).
+// FB_XFETCH_AHEAD=1 (A/B builds): the forward x kernel issues the next line's loads into the registers the head passes have
+// freed, under the pair pass of the current line.  Costs 200-330 bytes of spills per thread at the 128-register budget.
+#ifndef FB_XFETCH_AHEAD
+#define FB_XFETCH_AHEAD 0
+#endif
 #ifndef FB_PAIR_SPLIT
 #define FB_PAIR_SPLIT 1
 #endif
@@ -215,60 +220,84 @@ xfft_reg_kernel(RegPlan P, const double* __restrict__ src, LineGeom gs, double* 
     return 2 * XLineBuf<N>::slot(m) + part;
   };
   double* lbuf = reinterpret_cast<double*>(xb.b);
+  // forward: the raw loads of a line (fetch) are separate from their arrangement (signs / Makhoul permutation), so that the
+  // pair-pass kernels can issue the NEXT line's loads as soon as the registers are free (after the head passes have stored to
+  // the exchange buffer) and let them fly under the pair pass, the split and the stores of the current line
+  auto fetch = [&](long lcn, double (&re)[R], double (&im)[R]) {
+    const double* ps = src + line_offset(gs, lcn);
+    if (shift) {
+      const double2* pa = reinterpret_cast<const double2*>(ps + 1);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int m = j + T * u;
+        if (u == R - 1 && j == T - 1) { re[u] = ps[N - 1]; im[u] = ps[0]; }
+        else { const double2 v = pa[m]; re[u] = v.x; im[u] = v.y; }
+      }
+    } else if (!MK && !IV) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
+    } else if (viabuf) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        int ea, eb; bool vec;
+        pair_elems(j + T * u, ea, eb, vec);
+        if (vec) { const double2 v = *reinterpret_cast<const double2*>(ps + ea); re[u] = v.x; im[u] = v.y; }
+        else { re[u] = ps[ea]; im[u] = ps[eb]; }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        int e0, e1; double s0, s1;
+        reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+        re[u] = ps[e0]; im[u] = ps[e1];
+      }
+    }
+  };
+  auto arrange = [&](double (&re)[R], double (&im)[R]) {
+    if (!MK && !IV) return;
+    if (viabuf) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        int ea, eb; bool vec; double sa, sb;
+        pair_elems(j + T * u, ea, eb, vec);
+        const int pa = slot_sign(ea, sa), pb = slot_sign(eb, sb);
+        lbuf[pa] = sa * re[u]; lbuf[pb] = sb * im[u];
+      }
+      sync();
+      reg_gather<S>(re, im, j, xb);
+      sync();
+    } else {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        int e0, e1; double s0, s1;
+        reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
+        re[u] = s0 * re[u]; im[u] = s1 * im[u];
+      }
+    }
+  };
+  double re[R], im[R];
+  bool fetched = false;                                // (re, im) already hold this iteration's raw line
   for (long g = WARP ? (long)blockIdx.x * 8 + gi : (long)blockIdx.x; g < ngroups; g += gstride) {
     const long line = g * LG + lw;
     const bool live = line < nlines;
     const long lc = live ? line : nlines - 1;
-    {                                                  // next group's line -> L2 while this one is transformed
-      const long ln = min(line + gstride * LG, nlines - 1);
+    {                                                  // a later group's line -> L2 while this one is transformed
+      const long ln = min(line + (PAIR && FB_XFETCH_AHEAD ? 2 : 1) * gstride * LG, nlines - 1);
       const double* pn = src + line_offset(gs, ln) + (N / T) * j;
 #pragma unroll
       for (int q = 0; q < (N / T) / 16; ++q) prefetch_l2(pn + 16 * q);
     }
-    double re[R], im[R];
     if (FWD) {
-      const double* ps = src + line_offset(gs, lc);
-      if (shift) {
-        const double2* pa = reinterpret_cast<const double2*>(ps + 1);
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          const int m = j + T * u;
-          if (u == R - 1 && j == T - 1) { re[u] = ps[N - 1]; im[u] = ps[0]; }
-          else { const double2 v = pa[m]; re[u] = v.x; im[u] = v.y; }
-        }
-      } else if (!MK && !IV) {
-#pragma unroll
-        for (int u = 0; u < R; ++u) { const int m = j + T * u; re[u] = ps[2 * m]; im[u] = ps[2 * m + 1]; }
-      } else if (viabuf) {
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          int ea, eb; bool vec;
-          pair_elems(j + T * u, ea, eb, vec);
-          if (vec) { const double2 v = *reinterpret_cast<const double2*>(ps + ea); re[u] = v.x; im[u] = v.y; }
-          else { re[u] = ps[ea]; im[u] = ps[eb]; }
-        }
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          int ea, eb; bool vec; double sa, sb;
-          pair_elems(j + T * u, ea, eb, vec);
-          const int pa = slot_sign(ea, sa), pb = slot_sign(eb, sb);
-          lbuf[pa] = sa * re[u]; lbuf[pb] = sb * im[u];
-        }
-        sync();
-        reg_gather<S>(re, im, j, xb);
-        sync();
-      } else {
-#pragma unroll
-        for (int u = 0; u < R; ++u) {
-          int e0, e1; double s0, s1;
-          reg_phys_slots(kind, N, j + T * u, e0, e1, s0, s1);
-          re[u] = s0 * ps[e0]; im[u] = s1 * ps[e1];
-        }
-      }
+      if (!fetched) fetch(lc, re, im);
+      arrange(re, im);
       if (IV) reg_iv_pre<S, false>(re, im, j, P.wQ);
       if constexpr (PAIR) {                             // last pass on symmetric butterfly pairs: split in registers, stored from there
         reg_fft_passes_head<S, -1>(re, im, j, tw, xb, sync);
         sync();
+        if (FB_XFETCH_AHEAD) {
+          fetched = g + gstride < ngroups;
+          if (fetched) fetch(min((g + gstride) * LG + lw, nlines - 1), re, im);
+        }
         double2* pd = reinterpret_cast<double2*>(dst + line_offset(gd, lc));
         reg_pair_pass_split<S, MK>(j, tw[S::NP - 1], s_wN, s_wQ, xb, [&](int k, double xr, double xi) {
           if (live) st_x2(pd + k, make_double2(scale * xr, scale * xi));

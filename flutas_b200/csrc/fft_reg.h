@@ -9,10 +9,12 @@
 
 namespace fb {
 // y tiles at N >= 1024 (a line needs >= 32 threads): "wide" = 16 lanes (128-byte row pieces) in 512-thread blocks, one
-// block per SM; otherwise 8 lanes in 256-thread blocks, two blocks per SM.  Measured on one B200 at 1024^3: narrow
-// 4.86 / 5.36 ms (fwd / bwd), wide 5.42 / 5.64 ms -> narrow is the default; the slab solver asks for wide tiles when the
-// spectral side is written straight into peer memory (NVLink stores: 128-byte pieces move ~1.5x faster than 64-byte ones).
-// FLUTAS_B200_YWIDE=0/1 overrides both.
+// block per SM; otherwise 8 lanes in 256-thread blocks, two blocks per SM.  Measured on one B200 at 1024^3 with the pair-pass
+// kernels (profiles/r02_v_ab.log): forward narrow 4.21 / wide 3.76 ms, backward narrow 4.18 / wide 5.13 ms (1024 x 1024 x 512
+// DCT lines: 2.09 / 1.85 and 2.15 / 2.57 ms) -> the forward kernel runs wide tiles from N = 1024 up, the backward one only at
+// N = 2048 (where narrow tiles would be 32-byte pieces) or when the slab solver asks for them because the spectral side
+// is written straight into peer memory (NVLink stores: 128-byte pieces move ~1.5x faster than 64-byte ones).
+// FLUTAS_B200_YWIDE=0/1 overrides all of it.
 inline int& y_wide_request() { static int v = 0; return v; }
 inline bool y_wide_enabled() {
   static int env = -2;
