@@ -210,72 +210,6 @@ extern "C" int emul_thomas_reg(int L, int nz, long ncol, int periodic, int singu
   return 0;
 }
 
-// hierarchical reduced-system solve (flutas_b200/csrc/thomas_hier.cuh): thomas_reg phases with the flat PCR replaced by
-// G local three-right-hand-side PCRs + the 2G x 2G interface system -- what G cluster CTAs would each do for their rows
-#include "../../flutas_b200/csrc/thomas_hier.cuh"
-
-template <int L, int TI>
-static void thomas_hier_emul(long ncol, ThomasArgs T, const double* lam, double* W, int G) {
-  using TR = ThomasReg<L, TI>;
-  using TH = ThomasHier<TI>;
-  using CF = CoefTable<L>;
-  const int nz = T.nz, S = T.S, st = S * TI, m = S / G;
-  const long ntiles = (ncol + TI - 1) / TI;
-  const int tr = TR::tile_rows(nz);
-  std::vector<double> coef(3 * (size_t)tr, 0.0);
-  for (int k = 0; k < nz; ++k) { const int r = TR::prow(k); coef[r] = T.az[k]; coef[tr + r] = T.bz[k]; coef[2 * tr + r] = T.cz[k]; }
-  T.az = coef.data(); T.bz = coef.data() + tr; T.cz = coef.data() + 2 * tr; T.padded = 1;
-  std::vector<double> ex(6 * (size_t)st), pa(3 * (size_t)st), wa(5 * (size_t)st), wb(5 * (size_t)st), X(st);
-  std::vector<SegRegs<L>> regs(st);
-  std::vector<double> v((size_t)st * L);
-  for (long tile = 0; tile < ntiles; ++tile) {
-    auto colof = [&](int lane) { return tile * TI + lane; };
-    auto live = [&](int lane) { return colof(lane) < ncol; };
-    auto lamof = [&](int lane) { return live(lane) ? lam[colof(lane)] : -1.0; };
-    auto vof = [&](int lane, int s) { return v.data() + ((size_t)s * TI + lane) * L; };
-#define ALLT for (int s = 0; s < S; ++s) for (int lane = 0; lane < TI; ++lane)
-    ALLT { const long col = live(lane) ? colof(lane) : ncol - 1; for (int l = 0; l < L; ++l) vof(lane, s)[l] = W[col + (long)(s * L + l) * ncol]; }
-    ALLT TR::phase1(vof(lane, s), T, CF(T, s), lamof(lane), lane, s, regs[s * TI + lane], ex.data());
-    ALLT { const bool pin = T.singular && live(lane) && lamof(lane) == 0.0;
-           TR::reduced_row(vof(lane, s)[L - 1], ex.data(), pa.data(), T, CF(T, s), lamof(lane), lane, s, pin); }
-    ALLT TH::init_row(pa.data(), wa.data(), S, m, lane, s);
-    double* src = wa.data(); double* dst = wb.data();
-    for (int h = 1; h < m; h *= 2) {
-      bool any = false;
-      ALLT any = TH::pcr3_step(src, dst, S, m, lane, s, h) || any;
-      double* t = src; src = dst; dst = t;
-      if (!any) break;
-    }
-    for (int lane = 0; lane < TI; ++lane) {
-      double u[2 * FB_HIER_MAXG];
-      TH::interface_solve(src, S, G, lane, u);
-      for (int s = 0; s < S; ++s) TH::substitute(src, u, X.data(), S, G, lane, s);
-    }
-    ALLT TR::phase3(vof(lane, s), X.data(), T, lane, s, regs[s * TI + lane]);
-    ALLT if (live(lane)) for (int l = 0; l < L; ++l) W[colof(lane) + (long)(s * L + l) * ncol] = vof(lane, s)[l];
-#undef ALLT
-  }
-}
-
-extern "C" int emul_thomas_hier(int L, int G, int nz, long ncol, int periodic, int singular, const double* a, const double* b,
-                                const double* c, const double* lam, double* W) {
-  if (nz % L || G < 2 || G > FB_HIER_MAXG) return 1;
-  std::vector<double> az(a, a + nz), cz(c, c + nz);
-  if (!periodic) { az[0] = 0.0; cz[nz - 1] = 0.0; }
-  ThomasArgs T;
-  T.nz = nz; T.S = nz / L; T.periodic = periodic; T.singular = singular; T.az = az.data(); T.bz = b; T.cz = cz.data();
-  T.padded = 0; T.uniform = 0;
-  if (T.S % G || T.S / G < 1) return 2;
-  switch (L) {
-    case 2: thomas_hier_emul<2, 16>(ncol, T, lam, W, G); break;
-    case 4: thomas_hier_emul<4, 16>(ncol, T, lam, W, G); break;
-    case 8: thomas_hier_emul<8, 16>(ncol, T, lam, W, G); break;
-    case 16: thomas_hier_emul<16, 16>(ncol, T, lam, W, G); break;
-    default: return 3;
-  }
-  return 0;
-}
-
 // shared-LU kernel for exactly uniform grids (flutas_b200/csrc/thomas_uni.cuh): same phases as thomas_uni_kernel
 #include "../../flutas_b200/csrc/thomas_uni.cuh"
 

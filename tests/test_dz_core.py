@@ -21,7 +21,7 @@ def emul():
     so = os.path.join(HERE, "emulate", "libemul.so")
     deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f)
                     for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "reg_fft.cuh", "thomas_uni.cuh",
-                              "thomas_hier.cuh", "thomas_ref.cuh", "dz.cuh")]
+                              "thomas_ref.cuh", "dz.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])

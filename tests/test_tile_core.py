@@ -21,7 +21,7 @@ def emul():
     so = os.path.join(HERE, "emulate", "libemul.so")
     deps = [src] + [os.path.join(HERE, "..", "flutas_b200", "csrc", f)
                     for f in ("tile_fft.cuh", "line_plan.h", "thomas_tile.cuh", "thomas_reg.cuh", "reg_fft.cuh", "thomas_uni.cuh",
-                              "thomas_hier.cuh", "thomas_ref.cuh")]
+                              "thomas_ref.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
@@ -123,7 +123,6 @@ def emul_t(emul):
     emul.emul_thomas_tile.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     emul.emul_thomas_reg.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]
     emul.emul_thomas_uni.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
-    emul.emul_thomas_hier.argtypes = [C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     return emul
 
 
@@ -131,14 +130,12 @@ def emul_t(emul):
 @pytest.mark.parametrize("nz,L", [(8, 2), (16, 4), (32, 8), (64, 8), (72, 8), (40, 8), (64, 16), (128, 16), (512, 16),
                                   (256, 32), (1024, 32), (12, 2), (24, 4), (1024, 16), (48, 16), (4, 2)])
 @pytest.mark.parametrize("stretched", [False, True])
-@pytest.mark.parametrize("variant", ["tile", "reg", "reg-uniform", "uni", "hier2", "hier4"])
+@pytest.mark.parametrize("variant", ["tile", "reg", "reg-uniform", "uni"])
 def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched, variant):
     if variant in ("reg-uniform", "uni") and (stretched or nz < 4):
         pytest.skip("scalar-coefficient path: uniform grids only")
-    if variant in ("reg", "reg-uniform", "hier2", "hier4") and L > 16:
+    if variant in ("reg", "reg-uniform") and L > 16:
         pytest.skip("the register kernel keeps at most 16 levels per thread")
-    if variant.startswith("hier") and (nz // L) % int(variant[4:]):
-        pytest.skip("separators not divisible by the number of groups")
     if variant == "uni":                                 # the shared-LU kernel picks its own segment length
         L = next((q for q in (4, 8, 16, 32) if nz % q == 0 and 2 <= nz // q <= 32
                   and not (periodic and (nz // q) & (nz // q - 1))), None)
@@ -178,8 +175,6 @@ def test_thomas_tile_matches_reference_thomas(emul_t, periodic, nz, L, stretched
         rc = emul_t.emul_thomas_tile(*args)
     elif variant == "uni":
         rc = 0 if emul_t.emul_thomas_uni(*args[1:]) == L else 5
-    elif variant.startswith("hier"):                     # G groups of separators, as G cluster CTAs would solve them
-        rc = emul_t.emul_thomas_hier(L, int(variant[4:]), *args[1:])
     else:
         rc = emul_t.emul_thomas_reg(*args, 2 if variant == "reg-uniform" else 0)
     assert rc == 0
