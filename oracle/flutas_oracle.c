@@ -13,7 +13,9 @@
  *   oracle_find_fft      src/fft.f90:233-291
  *   oracle_normfft       src/fft.f90:71,87,125,150
  *   oracle_solver_cpu    src/solver_cpu.f90:20-115 (one rank: the 2DECOMP transposes are identities)
- *   gaussel / gaussel_periodic / dgtsv_homebrewed  src/solver_cpu.f90:117-223 (exact operation order)
+ *   gaussel / gaussel_periodic / dgtsv_homebrewed  src/solver_cpu.f90:117-223 (exact operation order; by default swept over eight
+ *                        adjacent columns at a time -- bit-identical to the column-at-a-time transcription, which
+ *                        oracle_set_definition_path(1) selects and tests/test_oracle.py compares bit for bit)
  *   oracle_correc        src/correc.f90:16-81      (_CONSTANT_COEFFS_POISSON branch)
  *   oracle_pres_sp_src   src/source.f90:311-346    oracle_pres_tw_src  src/source.f90:247-309 (constant-coefficient branch)
  *   oracle_pold_update   src/apps/single_phase/main__single_phase.f90:693-699, 734-740
@@ -516,9 +518,58 @@ static void dgtsv_homebrewed(int n, const double *a, const double *b, const doub
   for (int l = n - 2; l >= 0; --l) p[l * ps] = p[l * ps] - d[l] * p[(l + 1) * ps];
 }
 
+/* The same recurrences for GB adjacent columns at a time (columns i..i+m-1 of one j: one 64-byte cache line per level
+ * instead of one line per value).  Every column sees exactly the operations of dgtsv_homebrewed in the same order
+ * (the library is built with -ffp-contract=off), so the results are bit-identical to the column-at-a-time sweep; only the
+ * order in which memory is touched changes.  d: n*GB scratch.  lam: the m eigenvalues of the block. */
+#define GB 8
+static void dgtsv_block(int n, int m, const double *a, const double *b, const double *lam, const double *c, double *p, long ps,
+                        double *d) {
+  for (int q = 0; q < m; ++q) {
+    const double z = 1.0 / (b[0] + lam[q]);
+    d[q] = c[0] * z;
+    p[q] = p[q] * z;
+  }
+  for (int l = 1; l < n - 1; ++l) {
+    double *pl = p + l * ps, *pm = p + (l - 1) * ps, *dl = d + (long)l * GB, *dm = d + (long)(l - 1) * GB;
+    for (int q = 0; q < m; ++q) {
+      const double z = 1.0 / ((b[l] + lam[q]) - a[l] * dm[q]);
+      dl[q] = c[l] * z;
+      pl[q] = (pl[q] - a[l] * pm[q]) * z;
+    }
+  }
+  {
+    double *pl = p + (long)(n - 1) * ps, *pm = p + (long)(n - 2) * ps, *dm = d + (long)(n - 2) * GB;
+    for (int q = 0; q < m; ++q) {
+      const double z = (b[n - 1] + lam[q]) - a[n - 1] * dm[q];
+      if (z != 0.0) pl[q] = (pl[q] - a[n - 1] * pm[q]) / z;
+      else pl[q] = 0.0;
+    }
+  }
+  for (int l = n - 2; l >= 0; --l) {
+    double *pl = p + l * ps, *pp = p + (l + 1) * ps, *dl = d + (long)l * GB;
+    for (int q = 0; q < m; ++q) pl[q] = pl[q] - dl[q] * pp[q];
+  }
+}
+
 /* src/solver_cpu.f90:117-145 ; pz is (nx,ny,n) dense */
 void oracle_gaussel(int nx, int ny, int n, const double *a, const double *b, const double *c,
                     const double *lambdaxy, double *pz) {
+  if (!g_force_definition_path && n >= 3) {
+    const int nib = (nx + GB - 1) / GB;
+#pragma omp parallel
+    {
+      double *d = (double *)malloc(sizeof(double) * (size_t)n * GB);
+#pragma omp for collapse(2) schedule(static)
+      for (int j = 0; j < ny; ++j)
+        for (int ib = 0; ib < nib; ++ib) {
+          const int i = ib * GB, m = nx - i < GB ? nx - i : GB;
+          dgtsv_block(n, m, a, b, lambdaxy + i + (long)nx * j, c, pz + i + (long)nx * j, (long)nx * ny, d);
+        }
+      free(d);
+    }
+    return;
+  }
 #pragma omp parallel
   {
     double *bb = (double *)malloc(sizeof(double) * (size_t)n), *d = (double *)malloc(sizeof(double) * (size_t)n);
@@ -536,6 +587,33 @@ void oracle_gaussel(int nx, int ny, int n, const double *a, const double *b, con
 void oracle_gaussel_periodic(int nx, int ny, int n, const double *a, const double *b, const double *c,
                              const double *lambdaxy, double *pz) {
   const long ps = (long)nx * ny;
+  if (!g_force_definition_path && n >= 4) {                 /* blocks of GB columns, as above: bit-identical */
+    const int nib = (nx + GB - 1) / GB;
+#pragma omp parallel
+    {
+      double *d = (double *)malloc(sizeof(double) * (size_t)n * GB);
+      double *p1 = (double *)malloc(sizeof(double) * (size_t)n * GB), *p2 = (double *)malloc(sizeof(double) * (size_t)n * GB);
+#pragma omp for collapse(2) schedule(static)
+      for (int j = 0; j < ny; ++j)
+        for (int ib = 0; ib < nib; ++ib) {
+          const int i = ib * GB, m = nx - i < GB ? nx - i : GB;
+          double *p = pz + i + (long)nx * j;
+          const double *lam = lambdaxy + i + (long)nx * j;
+          for (int l = 0; l < n - 1; ++l)
+            for (int q = 0; q < m; ++q) { p1[(long)l * GB + q] = p[l * ps + q]; p2[(long)l * GB + q] = 0.0; }
+          for (int q = 0; q < m; ++q) { p2[q] = -a[0]; p2[(long)(n - 2) * GB + q] = -c[n - 2]; }
+          dgtsv_block(n - 1, m, a, b, lam, c, p1, GB, d);
+          dgtsv_block(n - 1, m, a, b, lam, c, p2, GB, d);
+          for (int q = 0; q < m; ++q)
+            p[(n - 1) * ps + q] = (p[(n - 1) * ps + q] - c[n - 1] * p1[q] - a[n - 1] * p1[(long)(n - 2) * GB + q]) /
+                                  ((b[n - 1] + lam[q]) + c[n - 1] * p2[q] + a[n - 1] * p2[(long)(n - 2) * GB + q]);
+          for (int l = 0; l < n - 1; ++l)
+            for (int q = 0; q < m; ++q) p[l * ps + q] = p1[(long)l * GB + q] + p2[(long)l * GB + q] * p[(n - 1) * ps + q];
+        }
+      free(d); free(p1); free(p2);
+    }
+    return;
+  }
 #pragma omp parallel
   {
     double *bb = (double *)malloc(sizeof(double) * (size_t)n), *d = (double *)malloc(sizeof(double) * (size_t)n);

@@ -99,6 +99,31 @@ def test_fast_path_matches_definition_path(kind, n):
         assert np.max(np.abs(got - ref)) <= 5e-15 * max(1.0, np.max(np.abs(ref))) * np.log2(n)
 
 
+@pytest.mark.parametrize("shape,bcz,gr", [((13, 5, 16), "NN", 0.0), ((8, 3, 7), "NN", 2.0), ((17, 4, 12), "PP", 0.0),
+                                          ((3, 2, 4), "PP", 0.0), ((16, 16, 64), "DD", 1.0), ((9, 2, 3), "ND", 0.0),
+                                          ((24, 3, 2), "NN", 0.0)])
+def test_blocked_gaussel_is_bit_identical_to_the_column_sweep(shape, bcz, gr):
+    """gaussel / gaussel_periodic (src/solver_cpu.f90:117-223) sweep one column at a time; the oracle's default runs the same
+    recurrences on eight adjacent columns at once (one cache line per level).  Same operations in the same order per column
+    (-ffp-contract=off), so the two must agree bit for bit -- including the singular column's z == 0 branch."""
+    from flutas_b200 import initsolver
+    nx, ny, n = shape
+    rng = np.random.default_rng(nx * 100 + n)
+    dzc, dzf = initsolver.initgrid(n, gr, 1.0, 1)
+    a, b, c = initsolver.tridmatrix(bcz, n, 1, 1.0 / dzc, 1.0 / dzf)
+    lam = np.asfortranarray(-rng.uniform(0, 4 * n * n, (nx, ny)))
+    lam[0, 0] = 0.0
+    rhs = np.asfortranarray(rng.uniform(-1, 1, (nx, ny, n)))
+    try:
+        oracle.set_definition_path(True)
+        ref = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bcz == "PP")
+    finally:
+        oracle.set_definition_path(False)
+    got = oracle.gaussel(a, b, c, lam, rhs.copy(order="F"), bcz == "PP")
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)])
+
+
 @pytest.mark.parametrize("kind", [k for k in KINDS if k != "HC2R"])
 @pytest.mark.parametrize("n", [2, 6, 8, 12, 30])
 def test_r2r_matches_longdouble_definition(kind, n):
