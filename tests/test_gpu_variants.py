@@ -16,6 +16,7 @@ VARIANTS = {
     "z-double-buffer": {"FLUTAS_B200_THOMAS_UNI": "0", "FLUTAS_B200_THOMAS_NBUF": "2"},
     "y-8-values": {"FLUTAS_B200_Y8": "1"},
     "y-wide": {"FLUTAS_B200_YWIDE": "1"},
+    "y-narrow": {"FLUTAS_B200_YWIDE": "0"},
     "y-8-values-wide": {"FLUTAS_B200_Y8": "1", "FLUTAS_B200_Y8WIDE": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "x-8-values": {"FLUTAS_B200_X8": "1", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
     "x-16-values": {"FLUTAS_B200_X8": "0", "_file": "test_gpu_fft.py", "_subset": "arrplan"},
