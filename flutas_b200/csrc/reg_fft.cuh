@@ -8,11 +8,14 @@
 //
 //   * a length-N real line is one length-M = N/2 complex Stockham FFT; T = M/16 threads own a line, each
 //     holds 16 complex values in registers from the global load to the global store;
-//   * passes are radix-16 (4x4 in registers) preceded by one radix-2/4/8 pass when M is not a power of 16;
+//   * passes are radix-16 (4x4 in registers) followed by one radix-2/4/8 pass when M is not a power of 16;
 //     between passes the T threads exchange through a small shared-memory buffer (write scattered, read
 //     position j + T*u -- the same set in every pass), so M = 256 needs ONE exchange, M = 512..2048 two;
 //   * the real split / Makhoul post-twiddle (forward) and merge / pre-twiddle (backward) are computed per
-//     mode k from Z_k and Z_{M-k}, fetched through one more exchange;
+//     mode k from Z_k and Z_{M-k}.  M = 512, 1024: the small-radix pass runs on symmetric butterfly pairs so that
+//     a thread holds both (reg_pair_pass_split / reg_pair_merge_pass; the backward line then runs the
+//     transposed schedule, reg_fft_passes_T_tail) -- no further exchange.  Other lengths, and the 8-values
+//     schedule, fetch Z_{M-k} through one more exchange (reg_scatter_modes + reg_split / reg_merge);
 //   * the spectrum is left in natural order, interleaved: row 2k = Re X_k, row 2k+1 = Im X_k
 //     (row 0 = X_0, row 1 = X_M); `reg_mode_index` tells the host which FFTW mode sits in which row so that
 //     lambdaxy is permuted once at plan time (initsolver.f90:136-139 order -> this order).
