@@ -66,9 +66,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: host-clock window of the load; samples outside it (the sampler starts before the warm-up so that
+        nvidia-smi is already streaming when the timed region begins) are dropped."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -79,6 +81,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
+            if t0 is not None and not (t0 <= r[-1] <= t1 + 0.12):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -355,21 +359,23 @@ def main():
 
     # ---- timed region: K solver calls ----------------------------------------------------------
     fill()
+    sampler = ClockSampler(local_rank)                  # started before the warm-up: nvidia-smi needs ~0.2 s to its first sample
+    sampler.start()
     for _ in range(args.warmup):
         solve()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     api.profile_enable(True)
     api.profile_read()
     l0 = api.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_load0 = time.time()
     e0.record()
     for _ in range(args.steps):
         solve()
     e1.record()
     barrier()
+    t_load1 = time.time()
     launches = api.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
     if world > 1:                                       # max over ranks, on the device clock
@@ -378,7 +384,19 @@ def main():
         ms_total = float(t.item())
     stages = api.profile_read()
     api.profile_enable(False)
-    clocks = sampler.stop()
+    # A timed region shorter than a few sampling periods (8 GPUs: 20 solves = 60 ms) would leave no clock sample: keep the
+    # same load running, untimed, for ~0.6 s more.  The number of extra solves follows from ms_total, which is identical on
+    # every rank after the all-reduce (the slab solve is collective).
+    extra_steps = 0
+    if ms_total < 400.0:
+        extra_steps = int(min(2000, max(1, 600.0 / max(ms_total / args.steps, 1e-3))))
+        for _ in range(extra_steps):
+            solve()
+        barrier()
+        t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1)
+    if extra_steps:
+        clocks["window"] = "timed region (%.0f ms) + %d untimed solves of the same load" % (ms_total, extra_steps)
     ms_step = ms_total / args.steps
     value = npts / (ms_step * 1e-3) / 1e9
 
